@@ -1,0 +1,1470 @@
+// az_engine.cu -- B200 (sm_100a) self-play MCTS engine behind the C-ABI of include/az_b200.h.
+//
+// Replaces, for thousands of independent trees at once, the reference's per-game Python search:
+//   Node.select/get_value  mcts.py:38-52,68-80     -> sim_select()   (fp64 PUCT, lanes-per-tree argmax)
+//   Node.expand            mcts.py:54-66           -> expand_node()
+//   Node.update_recursive  mcts.py:82-89           -> backup_path()
+//   MCTS.playout/search    mcts.py:126-180         -> k_step main loop
+//   expand_root_dirichlet  mcts.py:182-190         -> consume_root_eval()
+//   MCTS.update_root       mcts.py:192-203         -> reroot_compact()
+//   AlphaZeroBot.step      alphazerobot.py:42-93   -> finish_move()
+//   play_game_self targets game_utils.py:168-204   -> emit_record()
+//   state_to_board         network.py:9-18         -> write_obs()
+//
+// Data layout in HBM (per engine):
+//   hdr   [n_trees]            64-byte tree header (root/pending positions, phase, arena cursor)
+//   NL    [n_trees][2][cap]    uint2 {N, link}; link = first_child << 8 | n_children   (8 B / node)
+//   Q     [n_trees][2][cap]    double mean value                                      (8 B / node)
+//   P     [n_trees][2][cap]    double prior                                           (8 B / node)
+//   path  [n_trees][MAXD]      node indices root..leaf of the in-flight simulation
+// The children of a node are ONE contiguous block in legal (ascending action) order, so a lane group
+// reads a node's child statistics with three coalesced loads; the winning child's {N, link} comes back by
+// shuffle, which makes one dependent load round per tree level.  Actions are never stored: child k of a
+// node is the k-th legal move of the position, recomputed from the register-resident bitboards.
+// The two arena halves double-buffer the re-root compaction (BFS copy of the kept subtree).
+//
+// All PUCT / backup arithmetic is fp64 with explicit round-to-nearest intrinsics in the reference's
+// operation order; the file is also compiled with -fmad=false.
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+#include "../../include/az_b200.h"
+#include "az_games.cuh"
+
+namespace az {
+
+constexpr int PH_BEGIN = 6;  // internal: a search must be started (root eval request or first simulation)
+constexpr int BLOCK = 128;
+
+struct __align__(16) TreeHdr {
+  uint64_t root_b0, root_b1;
+  uint64_t pend_b0, pend_b1;
+  int32_t root_node;
+  int32_t alloc;
+  int32_t sims_done;
+  int32_t pend_node;
+  int32_t pend_depth;
+  int32_t pend_ply;
+  int32_t root_ply;
+  int32_t game_seq;
+  uint8_t phase, half, err, pad;
+  int32_t pad2[3];
+};
+static_assert(sizeof(TreeHdr) == 80, "TreeHdr size");
+
+struct Params {
+  TreeHdr* hdr;
+  uint2* NL;
+  double* Q;
+  double* P;
+  int32_t* path;
+  uint8_t* rec;
+  unsigned long long* rec_count;
+  unsigned long long* ctr;
+  long long rec_cap;
+  int rec_stride;
+  int n_trees, cap;
+  int n_playouts, num_prob, noise_mode, eval_mode, eval_shift, max_sims, start_mod;
+  uint32_t flags;
+  uint64_t seed;
+  double c_puct, keep, noise_w, alpha, temperature;
+  Geo geo;
+};
+
+struct StepIO {
+  const void* priors;
+  const void* values;
+  const double* noise;
+  void* obs;
+  int obs_format;
+};
+
+// ---------------------------------------------------------------- lane-group helpers
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+  if constexpr (G >= 32) {
+    return 0xffffffffu;
+  } else {
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));
+  }
+}
+template <int G, class T>
+__device__ __forceinline__ T gshfl(unsigned m, T v, int src) { return __shfl_sync(m, v, src, G); }
+template <int G, class T>
+__device__ __forceinline__ T gshfl_xor(unsigned m, T v, int off) { return __shfl_xor_sync(m, v, off, G); }
+template <int G>
+__device__ __forceinline__ int gsum(unsigned m, int v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o, G);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ double gsumd(unsigned m, double v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o, G);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ int gscan_incl(unsigned m, int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) {
+    const int t = __shfl_up_sync(m, v, o, G);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+// argmax with first-index tie-break over (value, index); index INT_MAX = no candidate
+template <int G>
+__device__ __forceinline__ void gargmax(unsigned m, double& v, int& i) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(m, v, o, G);
+    const int oi = __shfl_xor_sync(m, i, o, G);
+    if (oi != 0x7fffffff && (i == 0x7fffffff || ov > v || (ov == v && oi < i))) { v = ov; i = oi; }
+  }
+}
+
+__device__ __forceinline__ void ctr_add(unsigned long long* s_ctr, int which, unsigned long long v) {
+  if (v) atomicAdd(&s_ctr[which], v);
+}
+
+// ---------------------------------------------------------------- evaluator inputs
+struct EvalKey {
+  uint64_t k;
+};
+__device__ __forceinline__ EvalKey eval_key(const Params& p, const St& s) {
+  EvalKey e;
+  e.k = mix64(s.b0 ^ mix64(s.b1 ^ mix64(p.seed + (uint64_t)(s.ply & 1))));
+  return e;
+}
+__device__ __forceinline__ double eval_prior(const Params& p, const StepIO& io, int tree, const EvalKey& ek, int a) {
+  if (p.eval_mode == AZ_EVAL_EXTERNAL) {
+    const size_t idx = (size_t)tree * p.geo.n_actions + a;
+    return (p.flags & AZ_F_PRIORS_F64) ? ((const double*)io.priors)[idx] : (double)((const float*)io.priors)[idx];
+  }
+  if (p.eval_mode == AZ_EVAL_UNIFORM) return 1.0 / (double)p.geo.n_actions;
+  const uint64_t ha = mix64(ek.k + (uint64_t)(a + 1) * 0xD1B54A32D192ED03ULL);
+  return (double)(1 + (int)((ha >> 40) & 0x3FF)) * exp2((double)-(10 + p.eval_shift));
+}
+__device__ __forceinline__ double eval_value(const Params& p, const StepIO& io, int tree, const EvalKey& ek) {
+  if (p.eval_mode == AZ_EVAL_EXTERNAL)
+    return (p.flags & AZ_F_PRIORS_F64) ? ((const double*)io.values)[tree] : (double)((const float*)io.values)[tree];
+  if (p.eval_mode == AZ_EVAL_UNIFORM) return 0.0;
+  return (double)((int)((ek.k >> 20) & 31) - 16) / 16.0;
+}
+
+// Gamma(alpha<1) by Marsaglia-Tsang on alpha+1 with the U^(1/alpha) boost; counter stream 5.
+__device__ double gamma_draw(double alpha, uint64_t seed, uint64_t tree, uint64_t gseq, uint64_t ply, int child) {
+  const double d = alpha + 1.0 - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (int att = 0; att < 64; ++att) {
+    const uint64_t r0 = counter(seed, tree, gseq, ply, (uint64_t)child * 256 + att * 3 + 0, 5);
+    const uint64_t r1 = counter(seed, tree, gseq, ply, (uint64_t)child * 256 + att * 3 + 1, 5);
+    const uint64_t r2 = counter(seed, tree, gseq, ply, (uint64_t)child * 256 + att * 3 + 2, 5);
+    const double u0 = ((double)(r0 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+    const double u1 = ((double)(r1 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)(r2 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+    const double x = sqrt(-2.0 * log(u0)) * cospi(2.0 * u1);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    const uint64_t r3 = counter(seed, tree, gseq, ply, (uint64_t)child * 256 + att * 3 + 200, 5);
+    const double u3 = ((double)(r3 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+    if (log(u3) < 0.5 * x * x + d - d * v + d * log(v)) return d * v * pow(u2, 1.0 / alpha);
+  }
+  return alpha;
+}
+
+// ---------------------------------------------------------------- observation (network.py:9-18)
+template <class GM, int G>
+__device__ __forceinline__ void write_obs(const Params& p, const StepIO& io, int tree, int lane, const St& s) {
+  if (io.obs_format == AZ_OBS_NONE || io.obs == nullptr) return;
+  const int n = p.geo.cells;
+  const uint64_t pl0 = GM::plane(s, p.geo, 0), pl1 = GM::plane(s, p.geo, 1), pl2 = GM::plane(s, p.geo, 2);
+  const int cur = s.ply & 1;
+  if (io.obs_format == AZ_OBS_BF16_NHWC) {
+    uint2* out = reinterpret_cast<uint2*>(io.obs) + (size_t)tree * n;
+    const uint32_t one = 0x3F80u;  // bf16 1.0
+    for (int c = lane; c < n; c += G) {
+      uint2 v;
+      v.x = (((pl0 >> c) & 1ULL) ? one : 0u) | ((((pl1 >> c) & 1ULL) ? one : 0u) << 16);
+      v.y = (((pl2 >> c) & 1ULL) ? one : 0u) | ((cur ? one : 0u) << 16);
+      out[c] = v;
+    }
+  } else {
+    float* out = reinterpret_cast<float*>(io.obs) + (size_t)tree * 4 * n;
+    for (int i = lane; i < 4 * n; i += G) {
+      const int ch = i / n, c = i - ch * n;
+      const uint64_t pm = ch == 0 ? pl0 : (ch == 1 ? pl1 : pl2);
+      out[i] = ch == 3 ? (float)cur : (float)((pm >> c) & 1ULL);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- tree primitives
+struct Arena {
+  uint2* NL;
+  double* Q;
+  double* P;
+};
+__device__ __forceinline__ Arena arena_of(const Params& p, int tree, int half) {
+  const size_t base = ((size_t)tree * 2 + half) * (size_t)p.cap;
+  Arena a;
+  a.NL = p.NL + base;
+  a.Q = p.Q + base;
+  a.P = p.P + base;
+  return a;
+}
+
+// Node.update_recursive (mcts.py:82-89): node at path[j] receives v * (-1)^(depth-j); Q <- (N*Q + v)/(N+1).
+template <int G>
+__device__ __forceinline__ void backup_path(const Arena& a, const int32_t* path, int depth, double v_leaf, int lane) {
+  for (int j = lane; j <= depth; j += G) {
+    const int node = path[j];
+    const double v = ((depth - j) & 1) ? -v_leaf : v_leaf;
+    const uint2 nl = a.NL[node];
+    const double q = a.Q[node];
+    a.Q[node] = __ddiv_rn(__dadd_rn(__dmul_rn((double)nl.x, q), v), (double)(nl.x + 1u));
+    a.NL[node].x = nl.x + 1u;
+  }
+}
+
+// Node.expand (mcts.py:54-66).  noise != nullptr: root Dirichlet mix (mcts.py:186-189), eta indexed by legal position.
+// Returns false on arena overflow (nothing written).
+template <class GM, int G>
+__device__ __forceinline__ bool expand_node(const Params& p, const StepIO& io, const Arena& a, TreeHdr& h, int tree,
+                                            int node, const St& s, int lane, unsigned gm, bool root_mix,
+                                            const double* eta_lane /* [SLOTS] per-lane eta values */, int* L_out) {
+  const typename GM::Legal lg = GM::legal(s, p.geo);
+  const int L = GM::count(lg);
+  *L_out = L;
+  const uint2 nl = a.NL[node];
+  int fc;
+  bool fresh;
+  if ((nl.y & 0xffu) != 0) {  // children exist (re-expanded root): overwrite P only
+    fc = (int)(nl.y >> 8);
+    fresh = false;
+  } else {
+    if (h.alloc + L > p.cap) return false;
+    fc = h.alloc;
+    h.alloc += L;
+    fresh = true;
+    if (lane == 0) a.NL[node].y = ((unsigned)fc << 8) | (unsigned)L;
+  }
+  const EvalKey ek = eval_key(p, s);
+#pragma unroll
+  for (int sl = 0; sl < GM::SLOTS; ++sl) {
+    const int i = lane + sl * G;
+    if (i < L) {
+      const int act = GM::action_of(lg, s, p.geo, i);
+      double pr = eval_prior(p, io, tree, ek, act);
+      if (root_mix) pr = __dadd_rn(__dmul_rn(p.keep, pr), __dmul_rn(p.noise_w, eta_lane[sl]));
+      a.P[fc + i] = pr;
+      if (fresh) {
+        a.NL[fc + i] = make_uint2(0u, 0u);
+        a.Q[fc + i] = 0.0;
+      }
+    }
+  }
+  __syncwarp(gm);
+  return true;
+}
+
+// One PUCT descent (mcts.py:139-142).  On return: node/depth/state of the childless node reached; path in spath.
+template <class GM, int G>
+__device__ __forceinline__ void sim_select(const Params& p, const Arena& a, int root, St& s, int& node, int& depth,
+                                           int32_t* spath, int lane, unsigned gm, unsigned long long& n_children,
+                                           bool& depth_overflow) {
+  node = root;
+  depth = 0;
+  if (lane == 0) spath[0] = root;
+  uint2 cur = a.NL[root];
+  for (;;) {
+    const int nc = (int)(cur.y & 0xffu);
+    if (nc == 0) break;
+    if (depth + 1 >= GM::MAXD) { depth_overflow = true; break; }
+    const int fc = (int)(cur.y >> 8);
+    const double sq = __dsqrt_rn((double)cur.x);
+    double best = 0.0;
+    int bi = 0x7fffffff;
+    uint2 bnl = make_uint2(0u, 0u);
+#pragma unroll
+    for (int sl = 0; sl < GM::SLOTS; ++sl) {
+      const int i = lane + sl * G;
+      if (i < nc) {
+        const uint2 nl = a.NL[fc + i];
+        const double q = a.Q[fc + i];
+        const double pp = a.P[fc + i];
+        // Q + (((c_puct * P) * sqrt(N_parent)) / (N + 1))      mcts.py:78
+        const double u = __ddiv_rn(__dmul_rn(__dmul_rn(p.c_puct, pp), sq), (double)(nl.x + 1u));
+        const double sc = __dadd_rn(q, u);
+        if (bi == 0x7fffffff || sc > best) { best = sc; bi = i; bnl = nl; }
+      }
+    }
+    int wi = bi;
+    gargmax<G>(gm, best, wi);
+    const int owner = wi % G;  // the owner lane's local best is the winner
+    cur.x = gshfl<G>(gm, bnl.x, owner);
+    cur.y = gshfl<G>(gm, bnl.y, owner);
+    const typename GM::Legal lg = GM::legal(s, p.geo);
+    s = GM::apply(s, p.geo, GM::action_of(lg, s, p.geo, wi));
+    node = fc + wi;
+    ++depth;
+    if (lane == 0) spath[depth] = node;
+    n_children += (unsigned long long)nc;
+  }
+  __syncwarp(gm);
+}
+
+// game_utils.py:182-194 -- greedy descent by N+P among visited children.
+template <class GM, int G>
+__device__ double offpolicy_value(const Arena& a, int root, int lane, unsigned gm) {
+  int node = root;
+  uint2 cur = a.NL[root];
+  double value = 0.0, mult = 1.0;
+  for (;;) {
+    const int nc = (int)(cur.y & 0xffu);
+    if (nc == 0) break;
+    const int fc = (int)(cur.y >> 8);
+    value = a.Q[node];
+    double best = 0.0;
+    int bi = 0x7fffffff;
+    uint2 bnl = make_uint2(0u, 0u);
+#pragma unroll
+    for (int sl = 0; sl < GM::SLOTS; ++sl) {
+      const int i = lane + sl * G;
+      if (i < nc) {
+        const uint2 nl = a.NL[fc + i];
+        const double sc = nl.x > 0 ? __dadd_rn((double)nl.x, a.P[fc + i]) : -99.0;
+        if (bi == 0x7fffffff || sc > best) { best = sc; bi = i; bnl = nl; }
+      }
+    }
+    int wi = bi;
+    gargmax<G>(gm, best, wi);
+    const int owner = wi % G;
+    cur.x = gshfl<G>(gm, bnl.x, owner);
+    cur.y = gshfl<G>(gm, bnl.y, owner);
+    node = fc + wi;
+    mult = -mult;
+  }
+  if (cur.x > 0) {
+    value = a.Q[node];
+    mult = -mult;
+  }
+  return value * mult;
+}
+
+// MCTS.update_root (mcts.py:192-203) + compaction: BFS-copy the subtree of `child` into the other arena half.
+template <class GM, int G>
+__device__ void reroot_compact(const Params& p, TreeHdr& h, int tree, int child, int lane, unsigned gm,
+                               unsigned long long& copied) {
+  const Arena src = arena_of(p, tree, h.half);
+  const Arena dst = arena_of(p, tree, h.half ^ 1);
+  if (lane == 0) {
+    dst.NL[0] = src.NL[child];
+    dst.Q[0] = src.Q[child];
+    dst.P[0] = src.P[child];
+  }
+  __syncwarp(gm);
+  int head = 0, tail = 1;
+  while (head < tail) {
+    const int nb = min(G, tail - head);
+    const int idx = head + lane;
+    int mync = 0, oldfc = 0;
+    if (lane < nb) {
+      const uint2 nl = dst.NL[idx];
+      mync = (int)(nl.y & 0xffu);
+      oldfc = (int)(nl.y >> 8);
+    }
+    const int incl = gscan_incl<G>(gm, mync, lane);
+    const int total = gshfl<G>(gm, incl, G - 1);
+    if (mync > 0) {
+      const int newfc = tail + incl - mync;
+      dst.NL[idx].y = ((unsigned)newfc << 8) | (unsigned)mync;
+      for (int j = 0; j < mync; ++j) {
+        dst.NL[newfc + j] = src.NL[oldfc + j];
+        dst.Q[newfc + j] = src.Q[oldfc + j];
+        dst.P[newfc + j] = src.P[oldfc + j];
+      }
+    }
+    __syncwarp(gm);
+    tail += total;
+    head += nb;
+  }
+  copied += (unsigned long long)tail;
+  h.half ^= 1;
+  h.root_node = 0;
+  h.alloc = tail;
+}
+
+template <int G>
+__device__ __forceinline__ void fresh_tree(const Params& p, TreeHdr& h, int tree, int lane, unsigned gm) {
+  const Arena a = arena_of(p, tree, h.half);
+  if (lane == 0) {
+    a.NL[0] = make_uint2(0u, 0u);  // Node(None, 0.0)  mcts.py:122
+    a.Q[0] = 0.0;
+    a.P[0] = 0.0;
+  }
+  h.root_node = 0;
+  h.alloc = 1;
+  __syncwarp(gm);
+}
+
+template <class GM>
+__device__ St start_position(const Params& p, int tree, int gseq) {
+  St s = GM::initial(p.geo);
+  if (!(p.flags & AZ_F_RANDOM_START) || p.start_mod <= 0) return s;
+  const int k = (int)(counter(p.seed, tree, gseq, 0, 0, 4) % (uint64_t)p.start_mod);
+  for (uint64_t attempt = 0;; ++attempt) {
+    s = GM::initial(p.geo);
+    bool ok = true;
+    for (int j = 0; j < k; ++j) {
+      const typename GM::Legal lg = GM::legal(s, p.geo);
+      const int n = GM::count(lg);
+      const int pick = (int)(counter(p.seed, tree, gseq, j, attempt, 3) % (uint64_t)n);
+      s = GM::apply(s, p.geo, GM::action_of(lg, s, p.geo, pick));
+      if (GM::outcome(s, p.geo) >= 0) { ok = false; break; }
+    }
+    if (ok) return s;
+  }
+}
+
+// training record (game_utils.py:168-194); returns through *slot_out the record slot or -1
+template <class GM, int G>
+__device__ void emit_record(const Params& p, int tree, const TreeHdr& h, const St& s, int kind, int action, int n_legal,
+                            int root_n, double root_q, double v_a0c, double v_off, const int* counts_lane, int lane,
+                            unsigned gm, unsigned long long* s_ctr) {
+  long long slot = 0;
+  if (lane == 0) slot = (long long)atomicAdd(p.rec_count, 1ULL);
+  slot = gshfl<G>(gm, slot, 0);
+  if (slot >= p.rec_cap) {
+    if (lane == 0) ctr_add(s_ctr, AZ_CTR_OVERFLOW, 1);
+    return;
+  }
+  uint8_t* base = p.rec + (size_t)slot * p.rec_stride;
+  if (lane == 0) {
+    az_record r;
+    r.tree = tree;
+    r.game_seq = h.game_seq;
+    r.ply = s.ply;
+    r.action = action;
+    r.n_legal = n_legal;
+    r.kind = kind;
+    r.root_n = root_n;
+    r.pad = 0;
+    r.bb[0] = s.b0;
+    r.bb[1] = s.b1;
+    r.root_q = root_q;
+    r.v_a0c = v_a0c;
+    r.v_offpolicy = v_off;
+    *reinterpret_cast<az_record*>(base) = r;
+  }
+  int32_t* cnt = reinterpret_cast<int32_t*>(base + sizeof(az_record));
+#pragma unroll
+  for (int sl = 0; sl < GM::SLOTS; ++sl) {
+    const int i = lane + sl * G;
+    if (i < GM::MAXC) cnt[i] = (counts_lane && i < n_legal) ? counts_lane[sl] : 0;
+  }
+}
+
+// AlphaZeroBot.step after the search (alphazerobot.py:72-93) + play_game_self bookkeeping (game_utils.py:156-204).
+// Sets h.phase to PH_BEGIN / AZ_PH_IDLE / AZ_PH_SEARCH_DONE.
+template <class GM, int G>
+__device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, unsigned gm, unsigned long long* s_ctr) {
+  const Arena a = arena_of(p, tree, h.half);
+  St s;
+  s.b0 = h.root_b0;
+  s.b1 = h.root_b1;
+  s.ply = h.root_ply;
+  const typename GM::Legal lg = GM::legal(s, p.geo);
+  const int L = GM::count(lg);
+  const uint2 rnl = a.NL[h.root_node];
+  const int fc = (int)(rnl.y >> 8);
+  const int nc = (int)(rnl.y & 0xffu);  // == L once expanded
+  int cnt[GM::SLOTS];
+  double qv[GM::SLOTS];
+  int total = 0;
+  double a0c = -99.0;
+  int a0c_i = 0x7fffffff;
+#pragma unroll
+  for (int sl = 0; sl < GM::SLOTS; ++sl) {
+    const int i = lane + sl * G;
+    cnt[sl] = 0;
+    qv[sl] = 0.0;
+    if (i < nc) {
+      cnt[sl] = (int)a.NL[fc + i].x;
+      qv[sl] = a.Q[fc + i];
+      const double v = cnt[sl] > 0 ? qv[sl] : -99.0;
+      if (a0c_i == 0x7fffffff || v > a0c) { a0c = v; a0c_i = i; }
+    }
+    total += cnt[sl];
+  }
+  total = gsum<G>(gm, total);
+  gargmax<G>(gm, a0c, a0c_i);
+  const double root_q = a.Q[h.root_node];
+  double v_off = 0.0;
+  if ((p.flags & AZ_F_RECORDS) && (p.flags & AZ_F_OFFPOLICY)) v_off = offpolicy_value<GM, G>(a, h.root_node, lane, gm);
+
+  if (p.flags & AZ_F_MANUAL) {
+    if (p.flags & AZ_F_RECORDS)
+      emit_record<GM, G>(p, tree, h, s, 0, -1, L, (int)rnl.x, root_q, a0c, v_off, cnt, lane, gm, s_ctr);
+    h.phase = AZ_PH_SEARCH_DONE;
+    return;
+  }
+
+  // ---- move choice
+  int k = 0;
+  if ((p.flags & AZ_F_SAMPLE_MOVES) && s.ply < p.num_prob && total > 0) {
+    const uint64_t r64 = counter(p.seed, tree, h.game_seq, s.ply, 0, 2);
+    if (p.temperature == 1.0) {
+      // proportional to visit counts: r = floor(u32 * total / 2^32); first child with cumulative count > r
+      const long long r = (long long)(((r64 >> 32) * (uint64_t)total) >> 32);
+      int off = 0, pick = 0x7fffffff;
+#pragma unroll
+      for (int sl = 0; sl < GM::SLOTS; ++sl) {
+        const int incl = gscan_incl<G>(gm, cnt[sl], lane) + off;
+        if (incl > r && cnt[sl] > 0) pick = min(pick, lane + sl * G);
+        off = gshfl<G>(gm, incl, G - 1);
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) pick = min(pick, __shfl_xor_sync(gm, pick, o, G));
+      k = pick;
+    } else {
+      // p_i ~ count_i^(1/T)  (alphazerobot.py:78); serial inverse-CDF over children on every lane
+      const double invT = 1.0 / p.temperature;
+      double wsum = 0.0;
+      for (int i = 0; i < nc; ++i) {
+        const int c = gshfl<G>(gm, cnt[i / G], i % G);
+        wsum += pow((double)c, invT);
+      }
+      const double u = ((double)(r64 >> 11)) * (1.0 / 9007199254740992.0) * wsum;
+      double cum = 0.0;
+      k = -1;
+      int lastpos = 0;
+      for (int i = 0; i < nc; ++i) {
+        const int c = gshfl<G>(gm, cnt[i / G], i % G);
+        if (c > 0) lastpos = i;
+        cum += pow((double)c, invT);
+        if (k < 0 && c > 0 && cum > u) k = i;
+      }
+      if (k < 0) k = lastpos;
+    }
+  } else {
+    // np.argmax: first maximal visit count (alphazerobot.py:86)
+    double bv = -1.0;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int sl = 0; sl < GM::SLOTS; ++sl) {
+      const int i = lane + sl * G;
+      if (i < nc && (bi == 0x7fffffff || (double)cnt[sl] > bv)) { bv = (double)cnt[sl]; bi = i; }
+    }
+    gargmax<G>(gm, bv, bi);
+    k = bi;
+  }
+  const int action = GM::action_of(lg, s, p.geo, k);
+  if (p.flags & AZ_F_RECORDS)
+    emit_record<GM, G>(p, tree, h, s, 0, action, L, (int)rnl.x, root_q, a0c, v_off, cnt, lane, gm, s_ctr);
+
+  // ---- apply (game_utils.py:197)
+  const St s2 = GM::apply(s, p.geo, action);
+  if (lane == 0) ctr_add(s_ctr, AZ_CTR_MOVES, 1);
+  const int out = GM::outcome(s2, p.geo);
+  if (out >= 0) {
+    if (p.flags & AZ_F_RECORDS) {
+      const double ret0 = out == 2 ? 0.0 : (out == 0 ? 1.0 : -1.0);
+      emit_record<GM, G>(p, tree, h, s2, 1, -1, 0, 0, ret0, 0.0, 0.0, nullptr, lane, gm, s_ctr);
+    }
+    if (lane == 0) ctr_add(s_ctr, AZ_CTR_GAMES, 1);
+    if (p.flags & AZ_F_AUTO_RESTART) {
+      h.game_seq += 1;
+      const St s0 = start_position<GM>(p, tree, h.game_seq);
+      h.root_b0 = s0.b0;
+      h.root_b1 = s0.b1;
+      h.root_ply = s0.ply;
+      fresh_tree<G>(p, h, tree, lane, gm);
+      h.phase = PH_BEGIN;
+    } else {
+      h.root_b0 = s2.b0;
+      h.root_b1 = s2.b1;
+      h.root_ply = s2.ply;
+      h.phase = AZ_PH_IDLE;
+    }
+    return;
+  }
+  h.root_b0 = s2.b0;
+  h.root_b1 = s2.b1;
+  h.root_ply = s2.ply;
+  if ((p.flags & AZ_F_KEEP_TREE) && nc > 0) {
+    unsigned long long copied = 0;
+    reroot_compact<GM, G>(p, h, tree, fc + k, lane, gm, copied);
+    if (lane == 0) ctr_add(s_ctr, AZ_CTR_COMPACT_NODES, copied);
+  } else {
+    fresh_tree<G>(p, h, tree, lane, gm);
+  }
+  h.phase = PH_BEGIN;
+}
+
+// ---------------------------------------------------------------- the step kernel
+template <class GM>
+__global__ void __launch_bounds__(BLOCK) k_step(const Params p, const StepIO io) {
+  constexpr int G = GM::G;
+  __shared__ int32_t s_path[BLOCK / G][GM::MAXD];
+  __shared__ unsigned long long s_ctr[AZ_CTR_COUNT];
+  if (threadIdx.x < AZ_CTR_COUNT) s_ctr[threadIdx.x] = 0ULL;
+  __syncthreads();
+  const int tree = (int)((blockIdx.x * (unsigned)BLOCK + threadIdx.x) / G);
+  const int lane = threadIdx.x % G;
+  if (tree < p.n_trees) {
+    const unsigned gm = group_mask<G>();
+    int32_t* spath = s_path[threadIdx.x / G];
+    int32_t* gpath = p.path + (size_t)tree * GM::MAXD;
+    TreeHdr h = p.hdr[tree];
+    unsigned long long c_sims = 0, c_depth = 0, c_children = 0, c_exp = 0, c_legal = 0, c_term = 0;
+
+    // ---------------- 1. consume the evaluator outputs of the pending request
+    if (h.phase == AZ_PH_LEAF_EVAL) {
+      const Arena a = arena_of(p, tree, h.half);
+      St s;
+      s.b0 = h.pend_b0;
+      s.b1 = h.pend_b1;
+      s.ply = h.pend_ply;
+      int L = 0;
+      const bool ok = expand_node<GM, G>(p, io, a, h, tree, h.pend_node, s, lane, gm, false, nullptr, &L);
+      if (!ok) {
+        h.err = 1;
+        if (lane == 0) ctr_add(s_ctr, AZ_CTR_OVERFLOW, 1);
+      }
+      const double v = eval_value(p, io, tree, eval_key(p, s));
+      // node.update_recursive(-leaf_value)   mcts.py:152
+      backup_path<G>(a, gpath, h.pend_depth, -v, lane);
+      __syncwarp(gm);
+      h.sims_done += 1;
+      h.phase = AZ_PH_RUN;
+      c_sims += 1;
+      c_depth += h.pend_depth;
+      c_exp += 1;
+      c_legal += L;
+    } else if (h.phase == AZ_PH_ROOT_EVAL) {
+      const Arena a = arena_of(p, tree, h.half);
+      St s;
+      s.b0 = h.root_b0;
+      s.b1 = h.root_b1;
+      s.ply = h.root_ply;
+      const typename GM::Legal lg = GM::legal(s, p.geo);
+      const int L = GM::count(lg);
+      double eta[GM::SLOTS];
+#pragma unroll
+      for (int sl = 0; sl < GM::SLOTS; ++sl) eta[sl] = 0.0;
+      if (p.noise_mode == AZ_NOISE_HOST) {
+#pragma unroll
+        for (int sl = 0; sl < GM::SLOTS; ++sl) {
+          const int i = lane + sl * G;
+          if (i < L) eta[sl] = io.noise[(size_t)tree * GM::MAXC + i];
+        }
+      } else if (p.noise_mode == AZ_NOISE_COUNTER) {
+        double sum = 0.0;  // sequential sum in legal order, identical on every lane (oracle: oz_selfplay_game)
+        for (int i = 0; i < L; ++i) {
+          const double u = (double)((counter(p.seed, tree, h.game_seq, s.ply, i, 1) >> 11) + 1ULL) *
+                           (1.0 / 9007199254740992.0);
+          sum = __dadd_rn(sum, u);
+          if (i % G == lane) eta[i / G] = u;
+        }
+#pragma unroll
+        for (int sl = 0; sl < GM::SLOTS; ++sl) eta[sl] = __ddiv_rn(eta[sl], sum);
+      } else if (p.noise_mode == AZ_NOISE_DIRICHLET) {
+        double sum = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < GM::SLOTS; ++sl) {
+          const int i = lane + sl * G;
+          if (i < L) eta[sl] = gamma_draw(p.alpha, p.seed, tree, h.game_seq, s.ply, i);
+          sum += eta[sl];
+        }
+        sum = gsumd<G>(gm, sum);
+#pragma unroll
+        for (int sl = 0; sl < GM::SLOTS; ++sl) eta[sl] = sum > 0.0 ? eta[sl] / sum : 1.0 / (double)L;
+      }
+      int L2 = 0;
+      const bool ok = expand_node<GM, G>(p, io, a, h, tree, h.root_node, s, lane, gm, true, eta, &L2);
+      if (!ok) {
+        h.err = 1;
+        if (lane == 0) ctr_add(s_ctr, AZ_CTR_OVERFLOW, 1);
+      }
+      h.phase = AZ_PH_RUN;
+      if (lane == 0) ctr_add(s_ctr, AZ_CTR_ROOT_EVALS, 1);
+    }
+
+    // ---------------- 2. run until the next evaluator request
+    int sims_this_step = 0;
+    bool advanced = false;
+    for (;;) {
+      if (h.phase == PH_BEGIN) {
+        h.sims_done = 0;
+        if (p.noise_mode != AZ_NOISE_NONE) {
+          St s;
+          s.b0 = h.root_b0;
+          s.b1 = h.root_b1;
+          s.ply = h.root_ply;
+          h.phase = AZ_PH_ROOT_EVAL;
+          h.pend_b0 = s.b0;
+          h.pend_b1 = s.b1;
+          h.pend_ply = s.ply;
+          h.pend_depth = 0;
+          h.pend_node = h.root_node;
+          write_obs<GM, G>(p, io, tree, lane, s);
+          break;
+        }
+        h.phase = AZ_PH_RUN;
+      }
+      if (h.phase != AZ_PH_RUN) {
+        if (lane == 0) ctr_add(s_ctr, AZ_CTR_IDLE_SLOTS, 1);
+        break;
+      }
+      if (h.sims_done >= p.n_playouts) {
+        if (advanced) {
+          if (lane == 0) ctr_add(s_ctr, AZ_CTR_IDLE_SLOTS, 1);
+          break;
+        }
+        finish_move<GM, G>(p, h, tree, lane, gm, s_ctr);
+        advanced = true;
+        continue;
+      }
+      if (p.max_sims > 0 && sims_this_step >= p.max_sims) {
+        if (lane == 0) ctr_add(s_ctr, AZ_CTR_IDLE_SLOTS, 1);
+        break;
+      }
+      // ---- one simulation (mcts.py:126-153)
+      const Arena a = arena_of(p, tree, h.half);
+      St s;
+      s.b0 = h.root_b0;
+      s.b1 = h.root_b1;
+      s.ply = h.root_ply;
+      int node, depth;
+      bool dovf = false;
+      sim_select<GM, G>(p, a, h.root_node, s, node, depth, spath, lane, gm, c_children, dovf);
+      if (dovf) {
+        h.err = 1;
+        h.phase = AZ_PH_ERROR;
+        if (lane == 0) ctr_add(s_ctr, AZ_CTR_OVERFLOW, 1);
+        break;
+      }
+      const int out = depth > 0 ? GM::outcome(s, p.geo) : -1;
+      ++sims_this_step;
+      if (out >= 0) {
+        // terminal leaf: leaf_value = -player_return(mover); update_recursive(-leaf_value)   mcts.py:148-152
+        backup_path<G>(a, spath, depth, mover_return(out, s.ply), lane);
+        __syncwarp(gm);
+        h.sims_done += 1;
+        c_sims += 1;
+        c_depth += depth;
+        c_term += 1;
+        continue;
+      }
+      // non-terminal leaf: request the evaluator (mcts.py:146)
+      h.pend_b0 = s.b0;
+      h.pend_b1 = s.b1;
+      h.pend_ply = s.ply;
+      h.pend_node = node;
+      h.pend_depth = depth;
+      h.phase = AZ_PH_LEAF_EVAL;
+      for (int j = lane; j <= depth; j += G) gpath[j] = spath[j];
+      write_obs<GM, G>(p, io, tree, lane, s);
+      break;
+    }
+
+    if (lane == 0) {
+      p.hdr[tree] = h;
+      ctr_add(s_ctr, AZ_CTR_SIMS, c_sims);
+      ctr_add(s_ctr, AZ_CTR_DEPTH, c_depth);
+      ctr_add(s_ctr, AZ_CTR_CHILDREN, c_children);
+      ctr_add(s_ctr, AZ_CTR_EXPANSIONS, c_exp);
+      ctr_add(s_ctr, AZ_CTR_LEGAL, c_legal);
+      ctr_add(s_ctr, AZ_CTR_TERMINAL, c_term);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < AZ_CTR_COUNT && s_ctr[threadIdx.x]) atomicAdd(&p.ctr[threadIdx.x], s_ctr[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------- control kernels
+template <class GM>
+__global__ void k_reset(const Params p) {
+  constexpr int G = GM::G;
+  const int tree = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G);
+  const int lane = threadIdx.x % G;
+  if (tree >= p.n_trees) return;
+  const unsigned gm = group_mask<G>();
+  TreeHdr h;
+  memset(&h, 0, sizeof(h));
+  const St s0 = start_position<GM>(p, tree, 0);
+  h.root_b0 = s0.b0;
+  h.root_b1 = s0.b1;
+  h.root_ply = s0.ply;
+  h.game_seq = 0;
+  h.half = 0;
+  fresh_tree<G>(p, h, tree, lane, gm);
+  h.phase = (p.flags & AZ_F_MANUAL) ? AZ_PH_IDLE : PH_BEGIN;
+  if (lane == 0) p.hdr[tree] = h;
+}
+
+// set positions by replaying histories; tree nodes untouched
+template <class GM>
+__global__ void k_set_positions(const Params p, const int32_t* hist, const int32_t* len, int max_len, int32_t* bad) {
+  const int tree = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tree >= p.n_trees) return;
+  const int n = len[tree];
+  if (n < 0) return;
+  St s = GM::initial(p.geo);
+  for (int j = 0; j < n; ++j) {
+    const typename GM::Legal lg = GM::legal(s, p.geo);
+    const int a = hist[(size_t)tree * max_len + j];
+    if (GM::outcome(s, p.geo) >= 0 || GM::rank_of(lg, s, p.geo, a) < 0) {
+      atomicAdd(bad, 1);
+      return;
+    }
+    s = GM::apply(s, p.geo, a);
+  }
+  p.hdr[tree].root_b0 = s.b0;
+  p.hdr[tree].root_b1 = s.b1;
+  p.hdr[tree].root_ply = s.ply;
+}
+
+template <class GM>
+__global__ void k_command(const Params p, const int32_t* upd, const int32_t* rst, const int32_t* beg, int32_t* bad) {
+  constexpr int G = GM::G;
+  __shared__ unsigned long long s_ctr[AZ_CTR_COUNT];
+  if (threadIdx.x < AZ_CTR_COUNT) s_ctr[threadIdx.x] = 0ULL;
+  __syncthreads();
+  const int tree = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G);
+  const int lane = threadIdx.x % G;
+  if (tree < p.n_trees) {
+    const unsigned gm = group_mask<G>();
+    TreeHdr h = p.hdr[tree];
+    bool dirty = false;
+    if (rst && rst[tree]) {
+      fresh_tree<G>(p, h, tree, lane, gm);
+      h.phase = AZ_PH_IDLE;
+      dirty = true;
+    }
+    if (upd && upd[tree] >= 0) {
+      const int action = upd[tree];
+      const Arena a = arena_of(p, tree, h.half);
+      St s;
+      s.b0 = h.root_b0;
+      s.b1 = h.root_b1;
+      s.ply = h.root_ply;
+      const typename GM::Legal lg = GM::legal(s, p.geo);
+      const int k = GM::outcome(s, p.geo) >= 0 ? -1 : GM::rank_of(lg, s, p.geo, action);
+      const uint2 rnl = a.NL[h.root_node];
+      if ((rnl.y & 0xffu) == 0) {
+        fresh_tree<G>(p, h, tree, lane, gm);  // root is a leaf -> Node(None, 0.0)   mcts.py:198-199
+      } else if (k < 0) {
+        if (lane == 0) atomicAdd(bad, 1);     // KeyError in the reference (mcts.py:202)
+      } else {
+        unsigned long long copied = 0;
+        reroot_compact<GM, G>(p, h, tree, (int)(rnl.y >> 8) + k, lane, gm, copied);
+        if (lane == 0) ctr_add(s_ctr, AZ_CTR_COMPACT_NODES, copied);
+      }
+      if (k >= 0) {
+        const St s2 = GM::apply(s, p.geo, action);
+        h.root_b0 = s2.b0;
+        h.root_b1 = s2.b1;
+        h.root_ply = s2.ply;
+      }
+      h.phase = AZ_PH_IDLE;
+      dirty = true;
+    }
+    if (beg && beg[tree]) {
+      h.phase = PH_BEGIN;
+      h.sims_done = 0;
+      dirty = true;
+    }
+    if (dirty && lane == 0) p.hdr[tree] = h;
+  }
+  __syncthreads();
+  if (threadIdx.x < AZ_CTR_COUNT && s_ctr[threadIdx.x]) atomicAdd(&p.ctr[threadIdx.x], s_ctr[threadIdx.x]);
+}
+
+template <class GM>
+__global__ void k_status(const Params p, int32_t* phase, int32_t* sims, int32_t* ply, int32_t* req_legal) {
+  const int tree = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tree >= p.n_trees) return;
+  const TreeHdr h = p.hdr[tree];
+  if (phase) phase[tree] = h.phase == PH_BEGIN ? AZ_PH_RUN : h.phase;
+  if (sims) sims[tree] = h.sims_done;
+  if (ply) ply[tree] = h.root_ply;
+  if (req_legal) {
+    int L = 0;
+    if (h.phase == AZ_PH_LEAF_EVAL || h.phase == AZ_PH_ROOT_EVAL) {
+      St s;
+      s.b0 = h.pend_b0;
+      s.b1 = h.pend_b1;
+      s.ply = h.pend_ply;
+      L = GM::count(GM::legal(s, p.geo));
+    }
+    req_legal[tree] = L;
+  }
+}
+
+template <class GM>
+__global__ void k_request_info(const Params p, uint64_t* bb, int32_t* ply, int32_t* path_actions, int32_t* depth_out,
+                               int max_depth) {
+  const int tree = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tree >= p.n_trees) return;
+  const TreeHdr h = p.hdr[tree];
+  const bool pending = h.phase == AZ_PH_LEAF_EVAL || h.phase == AZ_PH_ROOT_EVAL;
+  if (bb) {
+    bb[2 * tree] = pending ? h.pend_b0 : 0;
+    bb[2 * tree + 1] = pending ? h.pend_b1 : 0;
+  }
+  if (ply) ply[tree] = pending ? h.pend_ply : -1;
+  const int depth = h.phase == AZ_PH_LEAF_EVAL ? h.pend_depth : (pending ? 0 : -1);
+  if (depth_out) depth_out[tree] = depth;
+  if (path_actions && depth > 0) {
+    const Arena a = arena_of(p, tree, h.half);
+    const int32_t* gpath = p.path + (size_t)tree * GM::MAXD;
+    St s;
+    s.b0 = h.root_b0;
+    s.b1 = h.root_b1;
+    s.ply = h.root_ply;
+    for (int j = 0; j < depth && j < max_depth; ++j) {
+      const int fc = (int)(a.NL[gpath[j]].y >> 8);
+      const int k = gpath[j + 1] - fc;
+      const typename GM::Legal lg = GM::legal(s, p.geo);
+      const int act = GM::action_of(lg, s, p.geo, k);
+      path_actions[(size_t)tree * max_depth + j] = act;
+      s = GM::apply(s, p.geo, act);
+    }
+  }
+}
+
+template <class GM>
+__global__ void k_root_stats(const Params p, int32_t* root_n, double* root_q, int32_t* n_children, int32_t* child_action,
+                             int32_t* child_n, double* child_q, double* child_p, double* v_a0c, double* v_off) {
+  constexpr int G = GM::G;
+  const int tree = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) / G);
+  const int lane = threadIdx.x % G;
+  if (tree >= p.n_trees) return;
+  const unsigned gm = group_mask<G>();
+  const TreeHdr h = p.hdr[tree];
+  const Arena a = arena_of(p, tree, h.half);
+  const uint2 rnl = a.NL[h.root_node];
+  const int nc = (int)(rnl.y & 0xffu), fc = (int)(rnl.y >> 8);
+  St s;
+  s.b0 = h.root_b0;
+  s.b1 = h.root_b1;
+  s.ply = h.root_ply;
+  const typename GM::Legal lg = GM::legal(s, p.geo);
+  if (lane == 0) {
+    if (root_n) root_n[tree] = (int)rnl.x;
+    if (root_q) root_q[tree] = a.Q[h.root_node];
+    if (n_children) n_children[tree] = nc;
+  }
+  double a0c = -99.0;
+  int a0c_i = 0x7fffffff;
+#pragma unroll
+  for (int sl = 0; sl < GM::SLOTS; ++sl) {
+    const int i = lane + sl * G;
+    if (i < GM::MAXC) {
+      const size_t o = (size_t)tree * GM::MAXC + i;
+      const bool have = i < nc;
+      const uint2 nl = have ? a.NL[fc + i] : make_uint2(0u, 0u);
+      const double q = have ? a.Q[fc + i] : 0.0;
+      if (child_action) child_action[o] = have ? GM::action_of(lg, s, p.geo, i) : -1;
+      if (child_n) child_n[o] = have ? (int)nl.x : 0;
+      if (child_q) child_q[o] = q;
+      if (child_p) child_p[o] = have ? a.P[fc + i] : 0.0;
+      if (have) {
+        const double v = nl.x > 0 ? q : -99.0;
+        if (a0c_i == 0x7fffffff || v > a0c) { a0c = v; a0c_i = i; }
+      }
+    }
+  }
+  gargmax<G>(gm, a0c, a0c_i);
+  if (v_a0c && lane == 0) v_a0c[tree] = a0c;
+  if (v_off) {
+    const double v = offpolicy_value<GM, G>(a, h.root_node, lane, gm);
+    if (lane == 0) v_off[tree] = v;
+  }
+}
+
+template <class GM>
+__global__ void k_positions(const Params p, uint64_t* bb, int32_t* ply, int32_t* terminal, double* ret0) {
+  const int tree = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tree >= p.n_trees) return;
+  const TreeHdr h = p.hdr[tree];
+  St s;
+  s.b0 = h.root_b0;
+  s.b1 = h.root_b1;
+  s.ply = h.root_ply;
+  const int out = GM::outcome(s, p.geo);
+  if (bb) {
+    bb[2 * tree] = s.b0;
+    bb[2 * tree + 1] = s.b1;
+  }
+  if (ply) ply[tree] = s.ply;
+  if (terminal) terminal[tree] = out >= 0;
+  if (ret0) ret0[tree] = out == 0 ? 1.0 : (out == 1 ? -1.0 : 0.0);
+}
+
+// ---------------------------------------------------------------- stateless game kernels (parity tests)
+template <class GM>
+__global__ void k_game_replay(const Geo geo, int n, const int32_t* hist, const int32_t* len, int max_len, uint64_t* bb,
+                              int32_t* status, double* ret0, int32_t* n_legal, int32_t* legal, void* obs,
+                              int obs_format) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  St s = GM::initial(geo);
+  int st = 0;
+  for (int j = 0; j < len[i]; ++j) {
+    const typename GM::Legal lg = GM::legal(s, geo);
+    const int a = hist[(size_t)i * max_len + j];
+    if (GM::outcome(s, geo) >= 0 || GM::rank_of(lg, s, geo, a) < 0) {
+      st |= 2;
+      break;
+    }
+    s = GM::apply(s, geo, a);
+  }
+  const int out = GM::outcome(s, geo);
+  if (out >= 0) st |= 1;
+  if (bb) {
+    bb[2 * i] = s.b0;
+    bb[2 * i + 1] = s.b1;
+  }
+  if (status) status[i] = st;
+  if (ret0) ret0[i] = out == 0 ? 1.0 : (out == 1 ? -1.0 : 0.0);
+  const typename GM::Legal lg = GM::legal(s, geo);
+  const int L = out >= 0 ? 0 : GM::count(lg);
+  if (n_legal) n_legal[i] = L;
+  if (legal)
+    for (int k = 0; k < GM::MAXC; ++k) legal[(size_t)i * GM::MAXC + k] = k < L ? GM::action_of(lg, s, geo, k) : -1;
+  if (obs && obs_format != AZ_OBS_NONE) {
+    Params p;
+    p.geo = geo;
+    StepIO io;
+    io.obs = obs;
+    io.obs_format = obs_format;
+    write_obs<GM, 1>(p, io, i, 0, s);
+  }
+}
+
+template <class GM>
+__global__ void k_game_random_playouts(const Geo geo, int n, uint64_t seed, int max_plies, int32_t* hist, int32_t* len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  St s = GM::initial(geo);
+  int j = 0;
+  for (; j < max_plies; ++j) {
+    if (GM::outcome(s, geo) >= 0) break;
+    const typename GM::Legal lg = GM::legal(s, geo);
+    const int L = GM::count(lg);
+    const int a = GM::action_of(lg, s, geo, (int)(counter(seed, i, 0, j, 0, 3) % (uint64_t)L));
+    hist[(size_t)i * max_plies + j] = a;
+    s = GM::apply(s, geo, a);
+  }
+  len[i] = j;
+}
+
+}  // namespace az
+
+// =====================================================================================================
+// Host side: the C-ABI
+// =====================================================================================================
+using namespace az;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) return fail(-2, "%s failed: %s", #call, cudaGetErrorString(_e));   \
+  } while (0)
+
+struct az_engine {
+  az_config cfg;
+  Params p;
+  int max_children, maxd, group;
+  int64_t bytes;
+  int32_t* d_cmd;  // 3 * n_trees command staging + 1 error word
+  int32_t* d_bad;
+};
+
+static Geo make_geo(int game_id, int rows, int cols) {
+  Geo g;
+  memset(&g, 0, sizeof(g));
+  if (game_id == AZ_GAME_CONNECT_FOUR) {
+    rows = 6;
+    cols = 7;
+  }
+  g.rows = rows;
+  g.cols = cols;
+  g.cells = rows * cols;
+  g.n_actions = game_id == AZ_GAME_CONNECT_FOUR ? 7 : rows * cols * 12;
+  g.all = g.cells >= 64 ? ~0ULL : ((1ULL << g.cells) - 1ULL);
+  uint64_t c0 = 0, cl = 0;
+  for (int r = 0; r < rows; ++r) {
+    c0 |= 1ULL << (r * cols);
+    cl |= 1ULL << (r * cols + cols - 1);
+  }
+  g.notcol0 = g.all & ~c0;
+  g.notcolL = g.all & ~cl;
+  g.row0 = cols >= 64 ? ~0ULL : ((1ULL << cols) - 1ULL);
+  g.rowL = g.row0 << ((rows - 1) * cols);
+  return g;
+}
+
+static int check_game(int game_id, int rows, int cols) {
+  if (game_id == AZ_GAME_CONNECT_FOUR) return 0;
+  if (game_id != AZ_GAME_BREAKTHROUGH) return fail(-1, "unknown game_id %d", game_id);
+  if (rows < 4 || cols < 2 || rows * cols > 64 || cols > 16)
+    return fail(-1, "breakthrough %dx%d unsupported (need rows>=4, cols>=2, rows*cols<=64)", rows, cols);
+  return 0;
+}
+
+template <class F>
+static int dispatch_game(int game_id, F&& f) {
+  if (game_id == AZ_GAME_CONNECT_FOUR) return f(C4());
+  return f(BT());
+}
+
+static inline int groups_grid(int n_trees, int G, int block) { return (int)(((long long)n_trees * G + block - 1) / block); }
+
+extern "C" {
+
+const char* az_last_error(void) { return g_err; }
+int az_version(void) { return 1; }
+
+int az_create(const az_config* cfg_in, az_engine** out) {
+  if (!cfg_in || !out) return fail(-1, "null argument");
+  az_config cfg = *cfg_in;
+  if (check_game(cfg.game_id, cfg.rows, cfg.cols)) return -1;
+  if (cfg.game_id == AZ_GAME_CONNECT_FOUR) {
+    cfg.rows = 6;
+    cfg.cols = 7;
+  }
+  if (cfg.n_trees <= 0) return fail(-1, "n_trees must be positive");
+  if (cfg.n_playouts <= 0) return fail(-1, "n_playouts must be positive");
+  if (cfg.temperature <= 0.0) cfg.temperature = 1.0;
+  if (cfg.dirichlet_alpha <= 0.0) cfg.dirichlet_alpha = 0.3;
+  if (cfg.noise_weight == 0.0) cfg.noise_weight = 0.25;
+  if (cfg.num_probabilistic_actions <= 0) cfg.num_probabilistic_actions = 1000;
+  if (cfg.noise_mode < 0 || cfg.noise_mode > 3) return fail(-1, "bad noise_mode");
+  if (cfg.eval_mode < 0 || cfg.eval_mode > 2) return fail(-1, "bad eval_mode");
+  const int maxc = cfg.game_id == AZ_GAME_CONNECT_FOUR ? C4::MAXC : BT::MAXC;
+  const int maxd = cfg.game_id == AZ_GAME_CONNECT_FOUR ? C4::MAXD : BT::MAXD;
+  const int group = cfg.game_id == AZ_GAME_CONNECT_FOUR ? C4::G : BT::G;
+  if (cfg.node_capacity <= 0) {
+    // every playout expands at most one leaf (<= maxc children); a kept subtree is at most the previous arena
+    const int branch = cfg.game_id == AZ_GAME_CONNECT_FOUR ? 7 : 3 * cfg.cols + 8;
+    long long c = (long long)(cfg.n_playouts + 2) * branch * 3 + 64;
+    if (c > (1 << 24) - 1) c = (1 << 24) - 1;
+    cfg.node_capacity = (int)c;
+  }
+  if (cfg.node_capacity >= (1 << 24)) return fail(-1, "node_capacity must be < 2^24");
+  if (cfg.record_capacity <= 0) cfg.record_capacity = cfg.n_trees * 64 < (1 << 20) ? (1 << 20) : cfg.n_trees * 64;
+  if (!(cfg.flags & AZ_F_RECORDS)) cfg.record_capacity = 1;
+
+  CK(cudaSetDevice(cfg.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg.device));
+  if (prop.major < 10) return fail(-3, "az_b200 needs an sm_100a GPU (found sm_%d%d)", prop.major, prop.minor);
+
+  az_engine* e = new (std::nothrow) az_engine();
+  if (!e) return fail(-4, "out of host memory");
+  memset(e, 0, sizeof(*e));
+  e->cfg = cfg;
+  e->max_children = maxc;
+  e->maxd = maxd;
+  e->group = group;
+  Params& p = e->p;
+  p.n_trees = cfg.n_trees;
+  p.cap = cfg.node_capacity;
+  p.n_playouts = cfg.n_playouts;
+  p.num_prob = cfg.num_probabilistic_actions;
+  p.noise_mode = cfg.noise_mode;
+  p.eval_mode = cfg.eval_mode;
+  p.eval_shift = cfg.eval_shift;
+  p.max_sims = cfg.max_sims_per_step;
+  p.start_mod = cfg.start_plies_mod;
+  p.flags = cfg.flags;
+  p.seed = cfg.seed;
+  p.c_puct = cfg.c_puct;
+  p.keep = 1.0 - cfg.dirichlet_ratio;
+  p.noise_w = cfg.noise_weight;
+  p.alpha = cfg.dirichlet_alpha;
+  p.temperature = cfg.temperature;
+  p.geo = make_geo(cfg.game_id, cfg.rows, cfg.cols);
+  p.rec_stride = (int)((sizeof(az_record) + 4 * (size_t)maxc + 7) / 8 * 8);
+  p.rec_cap = cfg.record_capacity;
+
+  const size_t nodes = (size_t)cfg.n_trees * 2 * (size_t)cfg.node_capacity;
+  size_t bytes = 0;
+  auto alloc = [&](void** ptr, size_t n) -> cudaError_t {
+    bytes += n;
+    return cudaMalloc(ptr, n);
+  };
+  cudaError_t err = cudaSuccess;
+  if ((err = alloc((void**)&p.hdr, sizeof(TreeHdr) * (size_t)cfg.n_trees)) != cudaSuccess ||
+      (err = alloc((void**)&p.NL, sizeof(uint2) * nodes)) != cudaSuccess ||
+      (err = alloc((void**)&p.Q, sizeof(double) * nodes)) != cudaSuccess ||
+      (err = alloc((void**)&p.P, sizeof(double) * nodes)) != cudaSuccess ||
+      (err = alloc((void**)&p.path, sizeof(int32_t) * (size_t)cfg.n_trees * maxd)) != cudaSuccess ||
+      (err = alloc((void**)&p.rec, (size_t)p.rec_stride * (size_t)p.rec_cap)) != cudaSuccess ||
+      (err = alloc((void**)&p.rec_count, sizeof(unsigned long long))) != cudaSuccess ||
+      (err = alloc((void**)&p.ctr, sizeof(unsigned long long) * AZ_CTR_COUNT)) != cudaSuccess ||
+      (err = alloc((void**)&e->d_cmd, sizeof(int32_t) * ((size_t)cfg.n_trees * 3))) != cudaSuccess ||
+      (err = alloc((void**)&e->d_bad, sizeof(int32_t))) != cudaSuccess) {
+    fail(-2, "cudaMalloc failed (%zu bytes requested so far): %s", bytes, cudaGetErrorString(err));
+    az_destroy(e);
+    return -2;
+  }
+  e->bytes = (int64_t)bytes;
+  CK(cudaMemset(p.rec_count, 0, sizeof(unsigned long long)));
+  CK(cudaMemset(p.ctr, 0, sizeof(unsigned long long) * AZ_CTR_COUNT));
+  CK(cudaMemset(e->d_bad, 0, sizeof(int32_t)));
+  *out = e;
+  int rc = az_reset(e, nullptr);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int az_destroy(az_engine* e) {
+  if (!e) return 0;
+  Params& p = e->p;
+  cudaFree(p.hdr);
+  cudaFree(p.NL);
+  cudaFree(p.Q);
+  cudaFree(p.P);
+  cudaFree(p.path);
+  cudaFree(p.rec);
+  cudaFree(p.rec_count);
+  cudaFree(p.ctr);
+  cudaFree(e->d_cmd);
+  cudaFree(e->d_bad);
+  delete e;
+  return 0;
+}
+
+int az_config_get(const az_engine* e, az_config* out) {
+  if (!e || !out) return fail(-1, "null argument");
+  *out = e->cfg;
+  return 0;
+}
+int az_max_children(const az_engine* e) { return e ? e->max_children : -1; }
+int az_num_actions(const az_engine* e) { return e ? e->p.geo.n_actions : -1; }
+int az_record_stride(const az_engine* e) { return e ? e->p.rec_stride : -1; }
+int64_t az_device_bytes(const az_engine* e) { return e ? e->bytes : -1; }
+
+int az_reset(az_engine* e, void* stream) {
+  if (!e) return fail(-1, "null engine");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Params p = e->p;
+  dispatch_game(e->cfg.game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_reset<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int check_bad(az_engine* e, cudaStream_t st, const char* what) {
+  int32_t bad = 0;
+  CK(cudaMemcpyAsync(&bad, e->d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (bad) {
+    cudaMemsetAsync(e->d_bad, 0, sizeof(int32_t), st);
+    return fail(-5, "%s: %d tree(s) got an illegal action", what, bad);
+  }
+  return 0;
+}
+
+int az_set_positions(az_engine* e, const int32_t* hist_host, const int32_t* len_host, int32_t max_len, void* stream) {
+  if (!e || !len_host) return fail(-1, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Params p = e->p;
+  int32_t *d_hist = nullptr, *d_len = nullptr;
+  const size_t hn = (size_t)p.n_trees * (size_t)(max_len > 0 ? max_len : 1);
+  CK(cudaMalloc((void**)&d_hist, sizeof(int32_t) * hn));
+  CK(cudaMalloc((void**)&d_len, sizeof(int32_t) * (size_t)p.n_trees));
+  if (max_len > 0 && hist_host) CK(cudaMemcpyAsync(d_hist, hist_host, sizeof(int32_t) * hn, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_len, len_host, sizeof(int32_t) * (size_t)p.n_trees, cudaMemcpyHostToDevice, st));
+  dispatch_game(e->cfg.game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_set_positions<GM><<<(p.n_trees + 127) / 128, 128, 0, st>>>(p, d_hist, d_len, max_len > 0 ? max_len : 1, e->d_bad);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  int rc = check_bad(e, st, "az_set_positions");
+  cudaFree(d_hist);
+  cudaFree(d_len);
+  return rc;
+}
+
+int az_command(az_engine* e, const int32_t* update_root_host, const int32_t* reset_tree_host, const int32_t* begin_host,
+               void* stream) {
+  if (!e) return fail(-1, "null engine");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Params p = e->p;
+  const size_t n = (size_t)p.n_trees;
+  int32_t* d_upd = update_root_host ? e->d_cmd : nullptr;
+  int32_t* d_rst = reset_tree_host ? e->d_cmd + n : nullptr;
+  int32_t* d_beg = begin_host ? e->d_cmd + 2 * n : nullptr;
+  if (d_upd) CK(cudaMemcpyAsync(d_upd, update_root_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  if (d_rst) CK(cudaMemcpyAsync(d_rst, reset_tree_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  if (d_beg) CK(cudaMemcpyAsync(d_beg, begin_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  dispatch_game(e->cfg.game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_command<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, d_upd, d_rst, d_beg, e->d_bad);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return check_bad(e, st, "az_command(update_root)");
+}
+
+int az_step(az_engine* e, const void* priors_dev, const void* values_dev, const double* noise_dev, void* obs_dev,
+            int32_t obs_format, void* stream) {
+  if (!e) return fail(-1, "null engine");
+  if (obs_format < 0 || obs_format > 2) return fail(-1, "bad obs_format");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Params p = e->p;
+  StepIO io;
+  io.priors = priors_dev;
+  io.values = values_dev;
+  io.noise = noise_dev;
+  io.obs = obs_dev;
+  io.obs_format = obs_format;
+  if (p.noise_mode == AZ_NOISE_HOST && !noise_dev) return fail(-1, "AZ_NOISE_HOST needs noise_dev");
+  dispatch_game(e->cfg.game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_step<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int az_status(az_engine* e, int32_t* phase_dev, int32_t* sims_dev, int32_t* ply_dev, int32_t* req_legal_dev, void* stream) {
+  if (!e) return fail(-1, "null engine");
+  const Params p = e->p;
+  dispatch_game(e->cfg.game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_status<GM><<<(p.n_trees + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, phase_dev, sims_dev, ply_dev, req_legal_dev);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int az_request_info(az_engine* e, uint64_t* bb_dev, int32_t* ply_dev, int32_t* path_actions_dev, int32_t* depth_dev,
+                    int32_t max_depth, void* stream) {
+  if (!e) return fail(-1, "null engine");
+  const Params p = e->p;
+  dispatch_game(e->cfg.game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_request_info<GM><<<(p.n_trees + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, bb_dev, ply_dev, path_actions_dev,
+                                                                                 depth_dev, max_depth);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int az_root_stats(az_engine* e, int32_t* root_n_dev, double* root_q_dev, int32_t* n_children_dev, int32_t* child_action_dev,
+                  int32_t* child_n_dev, double* child_q_dev, double* child_p_dev, double* v_a0c_dev,
+                  double* v_offpolicy_dev, void* stream) {
+  if (!e) return fail(-1, "null engine");
+  const Params p = e->p;
+  dispatch_game(e->cfg.game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_root_stats<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, (cudaStream_t)stream>>>(
+        p, root_n_dev, root_q_dev, n_children_dev, child_action_dev, child_n_dev, child_q_dev, child_p_dev, v_a0c_dev,
+        v_offpolicy_dev);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int az_positions(az_engine* e, uint64_t* bb_dev, int32_t* ply_dev, int32_t* terminal_dev, double* return0_dev, void* stream) {
+  if (!e) return fail(-1, "null engine");
+  const Params p = e->p;
+  dispatch_game(e->cfg.game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_positions<GM><<<(p.n_trees + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p, bb_dev, ply_dev, terminal_dev, return0_dev);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int az_drain_records(az_engine* e, void* host_buf, int64_t max_records, int64_t* n_out, void* stream) {
+  if (!e || !n_out) return fail(-1, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long n = 0;
+  CK(cudaMemcpyAsync(&n, e->p.rec_count, sizeof(n), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if ((long long)n > e->p.rec_cap) n = (unsigned long long)e->p.rec_cap;
+  if ((int64_t)n > max_records) return fail(-6, "host buffer too small: %lld records buffered, room for %lld", (long long)n, (long long)max_records);
+  if (n && host_buf) CK(cudaMemcpyAsync(host_buf, e->p.rec, (size_t)n * e->p.rec_stride, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemsetAsync(e->p.rec_count, 0, sizeof(unsigned long long), st));
+  CK(cudaStreamSynchronize(st));
+  *n_out = (int64_t)n;
+  return 0;
+}
+
+int az_counters(az_engine* e, uint64_t* out_host, void* stream) {
+  if (!e || !out_host) return fail(-1, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(out_host, e->p.ctr, sizeof(uint64_t) * AZ_CTR_COUNT, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int az_game_replay(int32_t game_id, int32_t rows, int32_t cols, int32_t n, const int32_t* hist_dev, const int32_t* len_dev,
+                   int32_t max_len, uint64_t* bb_dev, int32_t* status_dev, double* returns0_dev, int32_t* n_legal_dev,
+                   int32_t* legal_dev, void* obs_dev, int32_t obs_format, void* stream) {
+  if (check_game(game_id, rows, cols)) return -1;
+  if (n <= 0) return 0;
+  const Geo geo = make_geo(game_id, rows, cols);
+  dispatch_game(game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_game_replay<GM><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(geo, n, hist_dev, len_dev, max_len, bb_dev, status_dev,
+                                                                        returns0_dev, n_legal_dev, legal_dev, obs_dev,
+                                                                        obs_format);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t n, uint64_t seed, int32_t max_plies,
+                            int32_t* hist_dev, int32_t* len_dev, void* stream) {
+  if (check_game(game_id, rows, cols)) return -1;
+  if (n <= 0) return 0;
+  const Geo geo = make_geo(game_id, rows, cols);
+  dispatch_game(game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_game_random_playouts<GM><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(geo, n, seed, max_plies, hist_dev, len_dev);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

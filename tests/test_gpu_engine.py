@@ -1,0 +1,118 @@
+"""GPU parity: the CUDA engine (through the C-ABI) vs the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from tests import oracle_util as ou
+
+pytestmark = pytest.mark.gpu
+
+GAMES = ["connect_four", "breakthrough(rows=6,columns=6)", "breakthrough"]
+
+
+@pytest.mark.parametrize("game", GAMES)
+def test_game_dynamics_bit_exact(game):
+    """legal sets / terminal / returns / observation planes vs the oracle on random playouts."""
+    import torch
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    n, max_plies = 4096, 42 if game == "connect_four" else 160
+    hist, lens = E.game_random_playouts(game, n, seed=11, max_plies=max_plies)
+    hist_h, lens_h = hist.cpu().numpy(), lens.cpu().numpy()
+    rng = np.random.RandomState(0)
+    cut = np.array([rng.randint(0, l + 1) for l in lens_h], dtype=np.int32)  # random prefixes incl. full games
+    cut[: n // 8] = lens_h[: n // 8]
+    out = E.game_replay_dev(game, hist, torch.from_numpy(cut).to(hist.device), L.OBS_F32_NCHW)
+    out_bf = E.game_replay_dev(game, hist, torch.from_numpy(cut).to(hist.device), L.OBS_BF16_NHWC)
+    o = {k: v.cpu().numpy() for k, v in out.items()}
+    obs_bf = out_bf["obs"].float().cpu().numpy()
+    bb = o["bb"].view(np.uint64)
+    n_term = 0
+    for i in range(0, n, 4):
+        ref = ou.replay(game, hist_h[i, :cut[i]])
+        assert o["status"][i] == (1 if ref["terminal"] else 0)
+        assert (int(bb[i, 0]), int(bb[i, 1])) == ref["bb"]
+        assert o["return0"][i] == ref["returns0"]
+        assert list(o["legal"][i, :o["n_legal"][i]]) == ref["legal"]
+        if not ref["terminal"]:
+            assert np.array_equal(o["obs"][i].astype(np.float64), ref["board"])
+            assert np.array_equal(obs_bf[i].transpose(2, 0, 1).astype(np.float64), ref["board"])
+        n_term += ref["terminal"]
+    assert n_term > 50
+
+
+def _run_engine_selfplay(game, n_trees, n_playouts, seed, noise, sample, keep, flags_extra=0, max_steps=200000,
+                         max_sims_per_step=0):
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    flags = L.F_RECORDS | L.F_OFFPOLICY | flags_extra
+    if keep:
+        flags |= L.F_KEEP_TREE
+    if sample:
+        flags |= L.F_SAMPLE_MOVES
+    eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=noise, eval_mode=L.EVAL_HASH, flags=flags,
+                   seed=seed, max_sims_per_step=max_sims_per_step)
+    steps = 0
+    while True:
+        for _ in range(64):
+            eng.step()
+        steps += 64
+        ph = eng.phases()
+        if int((ph != L.PH_IDLE).sum()) == 0:
+            break
+        assert steps < max_steps
+    recs = eng.drain_records()
+    ctr = eng.counters()
+    eng.close()
+    return recs, ctr
+
+
+@pytest.mark.parametrize("game,n_trees,n_playouts", [("connect_four", 64, 100), ("connect_four", 16, 800),
+                                                     ("breakthrough(rows=6,columns=6)", 16, 200),
+                                                     ("breakthrough", 8, 120)])
+@pytest.mark.parametrize("keep", [1, 0])
+def test_selfplay_visit_counts_bit_exact(game, n_trees, n_playouts, keep):
+    """Whole self-play games, counter-mode noise + sampling, hash evaluator: every ply's root visit counts, Q,
+    A0C / off-policy targets, chosen action and position must equal the oracle's exactly."""
+    from alphazero_openspiel_b200 import _lib as L
+    seed = 1234
+    recs, ctr = _run_engine_selfplay(game, n_trees, n_playouts, seed, L.NOISE_COUNTER, 1, keep)
+    assert ctr["overflow"] == 0
+    cfg = ou.selfplay_cfg(game, n_playouts, use_dirichlet=2, sample_moves=1, keep_tree=keep, seed=seed)
+    tot = np.zeros(8, dtype=np.int64)
+    for t in range(n_trees):
+        mine = recs[recs["tree"] == t]
+        plies = mine[mine["kind"] == 0]
+        end = mine[mine["kind"] == 1]
+        ref, ret, c = ou.selfplay_game(cfg, t)
+        tot += np.array(c, dtype=np.int64)
+        assert len(plies) == len(ref) and len(end) == 1
+        order = np.argsort(plies["ply"])
+        for r, g in zip(ref, plies[order]):
+            assert g["ply"] == r["ply"] and g["n_legal"] == r["n_legal"]
+            assert list(g["counts"][:r["n_legal"]]) == r["counts"], (t, r["ply"])
+            assert g["action"] == r["action"]
+            assert (int(g["bb"][0]), int(g["bb"][1])) == r["bb"]
+            assert g["root_n"] == r["root_n"]
+            assert g["root_q"] == r["root_q"]
+            assert g["v_a0c"] == r["v_a0c"]
+            assert g["v_offpolicy"] == r["v_offpolicy"]
+        assert end[0]["root_q"] == ret[0]
+    assert ctr["sims"] == tot[0] and ctr["depth"] == tot[1] and ctr["children"] == tot[2]
+    assert ctr["expansions"] == tot[3] and ctr["legal"] == tot[4] and ctr["terminal"] == tot[5]
+    assert ctr["root_evals"] == tot[6]
+
+
+def test_no_dirichlet_argmax_and_sim_cap():
+    """use_dirichlet=False + argmax moves; a per-step simulation cap must not change any result."""
+    from alphazero_openspiel_b200 import _lib as L
+    game, n_trees, n_playouts, seed = "connect_four", 32, 60, 7
+    cfg = ou.selfplay_cfg(game, n_playouts, use_dirichlet=0, sample_moves=0, keep_tree=1, seed=seed)
+    for cap in (0, 3):
+        recs, ctr = _run_engine_selfplay(game, n_trees, n_playouts, seed, L.NOISE_NONE, 0, 1, max_sims_per_step=cap)
+        assert ctr["overflow"] == 0
+        for t in range(0, n_trees, 8):
+            plies = recs[(recs["tree"] == t) & (recs["kind"] == 0)]
+            plies = plies[np.argsort(plies["ply"])]
+            ref, ret, _ = ou.selfplay_game(cfg, t)
+            assert len(plies) == len(ref)
+            for r, g in zip(ref, plies):
+                assert list(g["counts"][:r["n_legal"]]) == r["counts"] and g["action"] == r["action"]
+                assert g["root_q"] == r["root_q"]
