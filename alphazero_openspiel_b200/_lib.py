@@ -24,7 +24,7 @@ class AzConfig(C.Structure):
         ("noise_weight", C.c_double), ("temperature", C.c_double),
         ("num_probabilistic_actions", C.c_int32), ("noise_mode", C.c_int32), ("eval_mode", C.c_int32),
         ("eval_shift", C.c_int32), ("max_sims_per_step", C.c_int32), ("start_plies_mod", C.c_int32),
-        ("record_capacity", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
+        ("record_capacity", C.c_int32), ("max_games", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
         ("seed", C.c_uint64),
     ]
 

@@ -68,7 +68,9 @@ struct Params {
   uint8_t* rec;
   unsigned long long* rec_count;
   unsigned long long* ctr;
+  int* games_started;
   long long rec_cap;
+  int max_games;
   int rec_stride;
   int n_trees, cap;
   int n_playouts, num_prob, noise_mode, eval_mode, eval_shift, max_sims, start_mod;
@@ -439,8 +441,8 @@ __device__ St start_position(const Params& p, int tree, int gseq) {
 // training record (game_utils.py:168-194); returns through *slot_out the record slot or -1
 template <class GM, int G>
 __device__ void emit_record(const Params& p, int tree, const TreeHdr& h, const St& s, int kind, int action, int n_legal,
-                            int root_n, double root_q, double v_a0c, double v_off, const int* counts_lane, int lane,
-                            unsigned gm, unsigned long long* s_ctr) {
+                            int root_n, double root_q, double v_a0c, double v_off, const int* counts_lane,
+                            const typename GM::Legal* lg, int lane, unsigned gm, unsigned long long* s_ctr) {
   long long slot = 0;
   if (lane == 0) slot = (long long)atomicAdd(p.rec_count, 1ULL);
   slot = gshfl<G>(gm, slot, 0);
@@ -467,10 +469,15 @@ __device__ void emit_record(const Params& p, int tree, const TreeHdr& h, const S
     *reinterpret_cast<az_record*>(base) = r;
   }
   int32_t* cnt = reinterpret_cast<int32_t*>(base + sizeof(az_record));
+  int16_t* act = reinterpret_cast<int16_t*>(base + sizeof(az_record) + 4 * GM::MAXC);
 #pragma unroll
   for (int sl = 0; sl < GM::SLOTS; ++sl) {
     const int i = lane + sl * G;
-    if (i < GM::MAXC) cnt[i] = (counts_lane && i < n_legal) ? counts_lane[sl] : 0;
+    if (i < GM::MAXC) {
+      const bool have = counts_lane && lg && i < n_legal;
+      cnt[i] = have ? counts_lane[sl] : 0;
+      act[i] = have ? (int16_t)GM::action_of(*lg, s, p.geo, i) : (int16_t)-1;
+    }
   }
 }
 
@@ -514,7 +521,7 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
 
   if (p.flags & AZ_F_MANUAL) {
     if (p.flags & AZ_F_RECORDS)
-      emit_record<GM, G>(p, tree, h, s, 0, -1, L, (int)rnl.x, root_q, a0c, v_off, cnt, lane, gm, s_ctr);
+      emit_record<GM, G>(p, tree, h, s, 0, -1, L, (int)rnl.x, root_q, a0c, v_off, cnt, &lg, lane, gm, s_ctr);
     h.phase = AZ_PH_SEARCH_DONE;
     return;
   }
@@ -570,7 +577,7 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
   }
   const int action = GM::action_of(lg, s, p.geo, k);
   if (p.flags & AZ_F_RECORDS)
-    emit_record<GM, G>(p, tree, h, s, 0, action, L, (int)rnl.x, root_q, a0c, v_off, cnt, lane, gm, s_ctr);
+    emit_record<GM, G>(p, tree, h, s, 0, action, L, (int)rnl.x, root_q, a0c, v_off, cnt, &lg, lane, gm, s_ctr);
 
   // ---- apply (game_utils.py:197)
   const St s2 = GM::apply(s, p.geo, action);
@@ -579,10 +586,17 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
   if (out >= 0) {
     if (p.flags & AZ_F_RECORDS) {
       const double ret0 = out == 2 ? 0.0 : (out == 0 ? 1.0 : -1.0);
-      emit_record<GM, G>(p, tree, h, s2, 1, -1, 0, 0, ret0, 0.0, 0.0, nullptr, lane, gm, s_ctr);
+      emit_record<GM, G>(p, tree, h, s2, 1, -1, 0, 0, ret0, 0.0, 0.0, nullptr, nullptr, lane, gm, s_ctr);
     }
     if (lane == 0) ctr_add(s_ctr, AZ_CTR_GAMES, 1);
-    if (p.flags & AZ_F_AUTO_RESTART) {
+    bool restart = (p.flags & AZ_F_AUTO_RESTART) != 0;
+    if (restart && p.max_games > 0) {
+      int ticket = 0;
+      if (lane == 0) ticket = atomicAdd(p.games_started, 1);
+      ticket = gshfl<G>(gm, ticket, 0);
+      restart = ticket < p.max_games;
+    }
+    if (restart) {
       h.game_seq += 1;
       const St s0 = start_position<GM>(p, tree, h.game_seq);
       h.root_b0 = s0.b0;
@@ -1208,7 +1222,8 @@ int az_create(const az_config* cfg_in, az_engine** out) {
   p.alpha = cfg.dirichlet_alpha;
   p.temperature = cfg.temperature;
   p.geo = make_geo(cfg.game_id, cfg.rows, cfg.cols);
-  p.rec_stride = (int)((sizeof(az_record) + 4 * (size_t)maxc + 7) / 8 * 8);
+  p.rec_stride = (int)((sizeof(az_record) + 6 * (size_t)maxc + 7) / 8 * 8);
+  p.max_games = cfg.max_games;
   p.rec_cap = cfg.record_capacity;
 
   const size_t nodes = (size_t)cfg.n_trees * 2 * (size_t)cfg.node_capacity;
@@ -1226,6 +1241,7 @@ int az_create(const az_config* cfg_in, az_engine** out) {
       (err = alloc((void**)&p.rec, (size_t)p.rec_stride * (size_t)p.rec_cap)) != cudaSuccess ||
       (err = alloc((void**)&p.rec_count, sizeof(unsigned long long))) != cudaSuccess ||
       (err = alloc((void**)&p.ctr, sizeof(unsigned long long) * AZ_CTR_COUNT)) != cudaSuccess ||
+      (err = alloc((void**)&p.games_started, sizeof(int))) != cudaSuccess ||
       (err = alloc((void**)&e->d_cmd, sizeof(int32_t) * ((size_t)cfg.n_trees * 3))) != cudaSuccess ||
       (err = alloc((void**)&e->d_bad, sizeof(int32_t))) != cudaSuccess) {
     fail(-2, "cudaMalloc failed (%zu bytes requested so far): %s", bytes, cudaGetErrorString(err));
@@ -1254,6 +1270,7 @@ int az_destroy(az_engine* e) {
   cudaFree(p.rec);
   cudaFree(p.rec_count);
   cudaFree(p.ctr);
+  cudaFree(p.games_started);
   cudaFree(e->d_cmd);
   cudaFree(e->d_bad);
   delete e;
@@ -1274,6 +1291,7 @@ int az_reset(az_engine* e, void* stream) {
   if (!e) return fail(-1, "null engine");
   cudaStream_t st = (cudaStream_t)stream;
   const Params p = e->p;
+  CK(cudaMemcpyAsync(p.games_started, &e->cfg.n_trees, sizeof(int), cudaMemcpyHostToDevice, st));
   dispatch_game(e->cfg.game_id, [&](auto gm) {
     using GM = decltype(gm);
     k_reset<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p);

@@ -11,13 +11,13 @@ from . import _lib as L
 def parse_game_name(name):
     """pyspiel.load_game names used by the reference (train.py:24): -> (game_id, rows, cols)."""
     name = name.strip()
-    if name == "connect_four":
+    if name in ("connect_four", "connect_four()"):
         return L.GAME_CONNECT_FOUR, 6, 7
     m = re.fullmatch(r"breakthrough(?:\((.*)\))?", name)
     if not m:
         raise ValueError("unsupported game for the B200 engine: %r" % (name,))
     rows = cols = 8
-    if m.group(1):
+    if m.group(1) and m.group(1).strip():
         for kv in m.group(1).split(","):
             k, v = [t.strip() for t in kv.split("=")]
             if k == "rows":
@@ -38,10 +38,10 @@ def game_shape(name):
 def record_dtype(max_children, stride):
     return np.dtype({
         "names": ["tree", "game_seq", "ply", "action", "n_legal", "kind", "root_n", "bb", "root_q", "v_a0c",
-                  "v_offpolicy", "counts"],
+                  "v_offpolicy", "counts", "actions"],
         "formats": ["<i4", "<i4", "<i4", "<i4", "<i4", "<i4", "<i4", ("<u8", (2,)), "<f8", "<f8", "<f8",
-                    ("<i4", (max_children,))],
-        "offsets": [0, 4, 8, 12, 16, 20, 24, 32, 48, 56, 64, 72],
+                    ("<i4", (max_children,)), ("<i2", (max_children,))],
+        "offsets": [0, 4, 8, 12, 16, 20, 24, 32, 48, 56, 64, 72, 72 + 4 * max_children],
         "itemsize": stride,
     })
 
@@ -56,7 +56,7 @@ class Engine:
     def __init__(self, game_name, n_trees, n_playouts=100, c_puct=2.5, dirichlet_ratio=0.25, temperature=1.0,
                  num_probabilistic_actions=1000, noise_mode=L.NOISE_DIRICHLET, eval_mode=L.EVAL_EXTERNAL,
                  eval_shift=None, flags=L.F_KEEP_TREE, seed=0, device=0, node_capacity=0, max_sims_per_step=0,
-                 start_plies_mod=0, record_capacity=0):
+                 start_plies_mod=0, record_capacity=0, max_games=0):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise L.EngineUnavailable("the B200 engine needs a CUDA device; there is no CPU fallback")
@@ -74,6 +74,7 @@ class Engine:
         cfg.eval_shift = (2 if gid == L.GAME_CONNECT_FOUR else 4) if eval_shift is None else eval_shift
         cfg.max_sims_per_step, cfg.start_plies_mod = max_sims_per_step, start_plies_mod
         cfg.record_capacity, cfg.device, cfg.flags, cfg.seed = record_capacity, device, flags, seed
+        cfg.max_games = max_games
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(self.lib.az_create(C.byref(cfg), C.byref(h)))

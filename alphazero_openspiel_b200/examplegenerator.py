@@ -1,0 +1,268 @@
+"""Drop-in for the reference's examplegenerator.py self-play generator, batched on the GPU.
+
+  ExampleGenerator(net, game_name, device, n_pools=1, n_processes=1, **kwargs)   examplegenerator.py:80-104
+      .generate_examples(n_games) -> list[game] of list[[info_state_str, board (C+1,H,W) float64,
+                                                          policy list[A], value]]  examplegenerator.py:164-175
+
+The reference runs one OS process per game plus a `handle_gpu` process that batches whichever boards happen
+to be ready (examplegenerator.py:57-77,106-138).  Here every game is a search tree in HBM; one az_step() +
+one batched bf16 ResNet forward advances ALL games by one evaluator round trip, with both captured in a single
+CUDA graph.  `n_pools` / `n_processes` are accepted for signature parity and ignored: parallelism is the
+number of concurrent trees (`n_trees`, default min(n_games, 16384)).  With torch.distributed initialised
+(one process per GPU) each rank plays its share of the games and the training records are all-gathered over
+NCCL (parallel.gather_records); weights are broadcast with parallel.broadcast_weights.
+
+Host-side conversion of device records to the reference's example format uses the reference's own numpy
+expressions (visit counts -> normalised -> remove_illegal_actions), so policy targets are bit-identical
+(SURVEY A.9).
+"""
+import copy
+import logging
+import time
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import Engine, parse_game_name, record_dtype
+from .network import BatchedEvaluator
+
+logger = logging.getLogger("alphazero")
+
+DEFAULT_MAX_TREES = 16384
+
+
+def boards_from_bitboards(game_id, rows, cols, bb, ply):
+    """Vectorised state_to_board (network.py:9-18) from canonical bitboards: -> float64 [n, 4, rows, cols]."""
+    n = bb.shape[0]
+    cells = rows * cols
+    shifts = np.arange(cells, dtype=np.uint64)
+    p0 = ((bb[:, 0:1] >> shifts) & np.uint64(1)).astype(np.float64)
+    p1 = ((bb[:, 1:2] >> shifts) & np.uint64(1)).astype(np.float64)
+    empty = 1.0 - p0 - p1
+    cur = np.broadcast_to((ply.astype(np.int64) & 1).astype(np.float64)[:, None], (n, cells))
+    if game_id == L.GAME_CONNECT_FOUR:
+        planes = [empty, p1, p0, cur]       # empty, 'o' (player 1), 'x' (player 0)  -- SURVEY B.2
+    else:
+        planes = [p0, p1, empty, cur]       # black, white, empty                   -- SURVEY B.3
+    return np.stack(planes, axis=1).reshape(n, 4, rows, cols)
+
+
+def policy_target(counts, actions, n_legal, num_actions):
+    """Visit counts -> the reference's policy target list (mcts.py:161-162 + alphazerobot.py:7-18,89-93)."""
+    visits = [0] * num_actions
+    legal = []
+    for k in range(n_legal):
+        visits[int(actions[k])] = int(counts[k])
+        legal.append(int(actions[k]))
+    total = sum(visits)
+    probs = np.array([float(v) / total for v in visits])
+    mask = np.zeros(probs.shape, dtype=bool)
+    mask[legal] = True
+    probs[~mask] = 0.0
+    if np.sum(probs) > 1e-6:
+        probs = probs / np.sum(probs)
+    else:
+        probs = np.zeros(len(probs))
+        probs[legal] = 1. / len(legal)
+    out = [0.0] * num_actions
+    for a in legal:
+        out[a] = probs[a]
+    return out
+
+
+def records_to_games(records, game_name, backup="on-policy"):
+    """Device training records -> list of games in the reference's example format (game_utils.py:168-204).
+    Only games that have their closing (kind 1) record are returned."""
+    gid, rows, cols = parse_game_name(game_name)
+    num_actions = 7 if gid == L.GAME_CONNECT_FOUR else rows * cols * 12
+    if len(records) == 0:
+        return []
+    order = np.lexsort((records["kind"], records["ply"], records["game_seq"], records["tree"]))
+    recs = records[order]
+    boards = boards_from_bitboards(gid, rows, cols, recs["bb"], recs["ply"])
+    key = recs["tree"].astype(np.int64) * (1 << 32) + recs["game_seq"].astype(np.int64)
+    starts = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
+    ends = np.r_[starts[1:], len(recs)]
+    games = []
+    for s, e in zip(starts, ends):
+        if recs["kind"][e - 1] != 1:
+            continue  # unfinished game
+        history = []
+        game = []
+        for i in range(s, e - 1):
+            r = recs[i]
+            pol = policy_target(r["counts"], r["actions"], int(r["n_legal"]), num_actions)
+            if backup == "soft-Z":
+                value = -float(r["root_q"])
+            elif backup == "A0C":
+                value = float(r["v_a0c"])
+            elif backup == "off-policy":
+                value = float(r["v_offpolicy"])
+            else:
+                value = None
+            game.append([", ".join(str(a) for a in history), boards[i], pol, value])
+            history.append(int(r["action"]))
+        if backup == "on-policy":
+            reward = float(recs["root_q"][e - 1])  # kind-1 record carries returns()[0]
+            for ex in game:
+                ex[3] = reward
+                reward *= -1
+        games.append(game)
+    return games
+
+
+class SelfPlayRunner:
+    """Engine + batched evaluator wired together; one `round()` = az_step + ResNet forward in one CUDA graph."""
+
+    def __init__(self, net, game_name, device, n_trees, n_playouts=100, c_puct=2.5, use_dirichlet=True,
+                 dirichlet_ratio=0.25, temperature=1.0, num_probabilistic_actions=1000, keep_search_tree=True,
+                 backup="on-policy", seed=0, max_games=0, auto_restart=True, random_start_mod=0,
+                 max_sims_per_step=16, records=True, use_graph=True, noise_mode=None, node_capacity=0,
+                 record_capacity=0, **_ignored):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.EngineUnavailable("SelfPlayRunner needs a CUDA device; there is no CPU fallback")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        flags = L.F_SAMPLE_MOVES
+        if keep_search_tree:
+            flags |= L.F_KEEP_TREE
+        if auto_restart:
+            flags |= L.F_AUTO_RESTART
+        if records:
+            flags |= L.F_RECORDS
+            if backup == "off-policy":
+                flags |= L.F_OFFPOLICY
+        if random_start_mod > 0:
+            flags |= L.F_RANDOM_START
+        if noise_mode is None:
+            noise_mode = L.NOISE_DIRICHLET if use_dirichlet else L.NOISE_NONE
+        self.backup = backup
+        self.game_name = game_name
+        with torch.cuda.device(self.device):
+            self.engine = Engine(game_name, n_trees, n_playouts=n_playouts, c_puct=c_puct,
+                                 dirichlet_ratio=dirichlet_ratio, temperature=temperature,
+                                 num_probabilistic_actions=num_probabilistic_actions, noise_mode=noise_mode,
+                                 eval_mode=L.EVAL_EXTERNAL, flags=flags, seed=seed, device=dev_index,
+                                 max_sims_per_step=max_sims_per_step, start_plies_mod=random_start_mod,
+                                 max_games=max_games, node_capacity=node_capacity,
+                                 record_capacity=record_capacity)
+            self.evaluator = BatchedEvaluator(net, n_trees, self.device, use_graph=False)
+        self.use_graph = use_graph
+        self._graph = None
+        self._first = True
+        self.rounds = 0
+
+    def load_weights(self, net):
+        """New generation's weights (host or device Net) into the captured evaluator, in place."""
+        self.evaluator.load(net)
+
+    @torch.no_grad()
+    def _round_eager(self):
+        ev = self.evaluator
+        self.engine.step(ev.priors, ev.values, None, ev.obs, L.OBS_BF16_NHWC)
+        ev()
+
+    @torch.no_grad()
+    def round(self, n=1):
+        """n evaluator round trips for every tree."""
+        with torch.cuda.device(self.device):
+            if self._first:
+                # first call: no evaluator outputs yet -- produce the initial requests, then evaluate them
+                self.engine.step(None, None, None, self.evaluator.obs, L.OBS_BF16_NHWC)
+                self.evaluator()
+                self._first = False
+            if self.use_graph and self._graph is None:
+                s = torch.cuda.Stream(self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    for _ in range(3):
+                        self._round_eager()
+                torch.cuda.current_stream(self.device).wait_stream(s)
+                self.rounds += 3
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._round_eager()
+                self.rounds += 1  # capture does not execute, but keep the count conservative
+            for _ in range(n):
+                if self.use_graph:
+                    self._graph.replay()
+                else:
+                    self._round_eager()
+            self.rounds += n
+
+    def counters(self):
+        return self.engine.counters()
+
+    def drain(self):
+        return self.engine.drain_records()
+
+    def all_idle(self):
+        return int((self.engine.phases() != L.PH_IDLE).sum().item()) == 0
+
+    def close(self):
+        self.engine.close()
+
+
+class ExampleGenerator:
+    def __init__(self, net, game_name, device, n_pools=1, n_processes=1, **kwargs):
+        self.is_test = bool(kwargs.get("is_test", False))
+        if self.is_test:
+            raise NotImplementedError("generate_tests (evaluation harness) is out of scope: SURVEY 8(f).2")
+        self.n_pools = n_pools            # accepted for signature parity; the GPU batch replaces pools/processes
+        self.n_processes = n_processes
+        self.net = copy.deepcopy(net)     # weights are frozen for the whole call (examplegenerator.py:86-87)
+        self.net.to("cpu")
+        self.net.eval()
+        self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        self.game_name = game_name
+        self.kwargs = kwargs
+        self.last_stats = {}
+
+    def generate_examples(self, n_games):
+        """Play n_games self-play games (split over ranks when torch.distributed is initialised)."""
+        from . import parallel
+        rank, world = parallel.rank_world()
+        share = n_games // world + (1 if rank < n_games % world else 0)
+        t0 = time.time()
+        records, stats = self._play(share, seed_offset=rank)
+        if world > 1:
+            records = parallel.gather_records(records, self.device)
+        backup = str(self.kwargs.get("backup", "on-policy"))
+        games = records_to_games(records, self.game_name, backup)
+        stats["seconds"] = time.time() - t0
+        self.last_stats = stats
+        logger.info("Generated " + str(len(games)) + " games")
+        return games
+
+    def _play(self, n_games, seed_offset=0):
+        kw = dict(self.kwargs)
+        n_trees = int(kw.pop("n_trees", min(max(n_games, 1), DEFAULT_MAX_TREES)))
+        n_trees = max(1, min(n_trees, max(n_games, 1)))
+        seed = int(kw.pop("seed", np.random.randint(0, 2 ** 31 - 1))) + seed_offset
+        if self.device.type != "cuda":
+            raise L.EngineUnavailable("ExampleGenerator needs a CUDA device; there is no CPU fallback")
+        if n_games == 0:
+            gid, _, _ = parse_game_name(self.game_name)
+            maxc = 7 if gid == L.GAME_CONNECT_FOUR else 48
+            return np.empty((0,), dtype=record_dtype(maxc, (72 + 6 * maxc + 7) // 8 * 8)), {}
+        runner = SelfPlayRunner(self.net, self.game_name, self.device, n_trees, seed=seed, max_games=n_games,
+                                auto_restart=True, records=True, **kw)
+        chunks = []
+        try:
+            while True:
+                runner.round(64)
+                if runner.all_idle():
+                    break
+                if runner.rounds % 4096 < 64:
+                    chunks.append(runner.drain())
+            chunks.append(runner.drain())
+            stats = runner.counters()
+            stats["rounds"] = runner.rounds
+            if stats["overflow"]:
+                raise RuntimeError("search arena / record buffer overflow (%d); raise node_capacity" %
+                                   stats["overflow"])
+        finally:
+            runner.close()
+        return np.concatenate(chunks), stats

@@ -1,0 +1,40 @@
+"""Drop-in for the self-play driver of the reference's game_utils.py: play_game_self (game_utils.py:148-206).
+
+One game, one AlphaZeroBot for both sides, host-side `policy_fn(state)`; emits per ply
+[information_state string, state_to_board planes, dense policy list, value] with the value target chosen by
+`backup` (on-policy / soft-Z / A0C / off-policy).  The three tree-derived targets are computed on the device
+(az_root_stats) instead of walking Python Node objects.  Needs `pyspiel` for the State objects, exactly like
+the reference; the batched, pyspiel-free path is examplegenerator.ExampleGenerator.
+"""
+from .alphazerobot import AlphaZeroBot
+from .network import state_to_board
+
+
+def play_game_self(policy_fn, game_name, **kwargs):
+    import pyspiel  # the caller's OpenSpiel, as in the reference (game_utils.py:2)
+    game = pyspiel.load_game(game_name)
+    state = game.new_initial_state()
+    state_shape = game.information_state_normalized_vector_shape()
+    n_actions = game.num_distinct_actions()
+    kwargs = dict(kwargs)
+    kwargs.setdefault("game_name", game_name)
+    bot = AlphaZeroBot(game, 0, policy_fn, self_play=True, **kwargs)
+    backup = str(kwargs.get("backup", "on-policy"))
+    examples = []
+    while not state.is_terminal():
+        policy, action = bot.step(state)
+        by_action = dict(policy)
+        policy_list = [by_action.get(i, 0.0) for i in range(n_actions)]
+        value = None
+        if backup in ("soft-Z", "A0C", "off-policy"):
+            soft_z, a0c, off_policy = bot.mcts.value_targets()
+            value = {"soft-Z": soft_z, "A0C": a0c, "off-policy": off_policy}[backup]
+        if backup in ("on-policy", "soft-Z", "A0C", "off-policy"):
+            examples.append([state.information_state(), state_to_board(state, state_shape), policy_list, value])
+        state.apply_action(action)
+    if backup == "on-policy":
+        reward = state.returns()[0]
+        for ex in examples:
+            ex[3] = reward
+            reward *= -1
+    return examples

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- self-play MCTS throughput of the B200 engine (BASELINE.json metric: MCTS simulations/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the oracle port of the reference
+    torchrun ... bench.py --gpus N ...                             # one rank per GPU, NCCL
+
+Workload (BASELINE.json configs[2]): Connect Four, 800 sims/move, 16,384 concurrent trees per GPU, Dirichlet
+root noise, tree reuse, synthetic start positions (k = counter % 21 random plies), random-init ResNet of the
+reference architecture in bf16.  One "step" = one evaluator round trip for every tree: az_step (consume +
+PUCT simulations + move bookkeeping + observation encode) followed by the batched ResNet forward.  Weak
+scaling: every GPU runs its own independent 16,384-tree pool; there is no data-path collective.
+
+One JSON line on stdout (rank 0).  `value` = simulations completed in the timed region (device counters,
+summed over ranks) / max-over-ranks CUDA-event time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOPS_PER_EVAL = {"connect_four": 17211600, "breakthrough(rows=6,columns=6)": 16282800, "breakthrough": 31097600}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(d, game_cells, num_actions):
+    """SURVEY 8(d) bytes/simulation summed over the region, from the engine's counters (delta dict)."""
+    state_bytes = 16
+    return (8 * d["depth"] + 20 * d["children"]                       # select: per level 8 B node + 20 B per child
+            + 24 * (d["depth"] + d["sims"])                           # backup: N,Q read+write along the path
+            + d["expansions"] * (8 + 4 * (num_actions + 1) + 2 * 4 * game_cells)  # link + fp32 NN out + bf16 NN in
+            + 20 * d["legal"]                                         # child records written at expansion
+            + state_bytes * d["sims"])                                # root position read
+
+
+def cpu_baseline(game, n_playouts, seconds_budget=20.0, max_plies=None):
+    """The oracle's Python port of the reference's multi-process self-play (examplegenerator.py) on host cores."""
+    import torch
+    from oracle import ref_port, ref_net, pyspiel_shim
+    torch.manual_seed(0)
+    g = pyspiel_shim.load_game(game)
+    net = ref_net.RefNet(g.information_state_normalized_vector_shape(), g.num_distinct_actions())
+    net.eval()
+    cores = os.cpu_count() or 2
+    workers = max(1, min(cores - 1, 32))
+    # bounded sample: every worker plays the first `max_plies` plies of one game
+    if max_plies is None:
+        per_ply = n_playouts / 450.0  # ~450 sims/s/process for the Python path
+        max_plies = max(1, int(seconds_budget / max(per_ply, 1e-3)))
+        max_plies = min(max_plies, 12)
+    res = ref_port.time_selfplay(net, game, workers, workers, n_playouts=n_playouts, c_puct=2.5,
+                                 dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", max_plies=max_plies)
+    sample = ("%d games x first %d plies, %d sims/move, %d worker processes + 1 evaluator process (fp32 CPU ResNet), "
+              "%d sims in %.1f s" % (res["n_games"], max_plies, n_playouts, workers, res["sims"], res["seconds"]))
+    return {"value": res["sims_per_s"], "unit": "sims/s", "cores": workers + 1, "kind": "port", "sample": sample,
+            "host_cpus": cores, "games_per_s_equiv": res["sims_per_s"] / (n_playouts * 25.0)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    game = args.game
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3)) if args.ref_repeat else 1):
+        base = cpu_baseline(game, args.playouts, seconds_budget=args.cpu_seconds)
+        vals.append(base["value"])
+    v = sum(vals) / len(vals)
+    base["value"] = v
+    line = {"metric": "mcts_simulations_per_sec", "value": v, "unit": "sims/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(args), "trees_per_gpu": args.trees,
+                                            "n_playouts": args.playouts, "game": game},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return "%s batched self-play, %d sims/move, %d concurrent trees per GPU" % (args.game, args.playouts, args.trees)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from alphazero_openspiel_b200 import _lib as L
+    from alphazero_openspiel_b200.engine import game_shape, parse_game_name
+    from alphazero_openspiel_b200.examplegenerator import SelfPlayRunner
+    from alphazero_openspiel_b200.network import Net
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L.load()  # fail loudly if the CUDA extension is missing
+
+    game = args.game
+    shape, n_actions = game_shape(game)
+    _, rows, cols = parse_game_name(game)
+    torch.manual_seed(0)
+    net = Net(shape, n_actions)  # random-init weights of the reference architecture (no checkpoints off-box)
+    net.eval()
+    if world > 1:
+        from alphazero_openspiel_b200 import parallel
+        parallel.broadcast_weights(net, src=0, device=dev)  # NCCL: the per-generation weight broadcast
+
+    runner = SelfPlayRunner(net, game, dev, args.trees, n_playouts=args.playouts, c_puct=2.5, use_dirichlet=True,
+                            dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", seed=0xC4 + rank,
+                            auto_restart=True, random_start_mod=21, max_sims_per_step=args.sim_cap, records=True,
+                            use_graph=not args.no_graph)
+    # ---- warm-up (untimed): builds the first searches so trees are in steady state
+    runner.round(args.warmup)
+    runner.drain()
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- timed region: K rounds, CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    c0 = runner.counters()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    runner.round(args.steps)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    c1 = runner.counters()
+    d = {k: c1[k] - c0[k] for k in c1}
+
+    # ---- e2e: same metric through the public API with HOST buffers: host weights -> device (H2D), K rounds,
+    # training records + counters back to host memory (D2H), wall clock around all of it
+    host_net = Net(shape, n_actions)
+    host_net.load_state_dict(net.state_dict())
+    for t in list(host_net.parameters()) + list(host_net.buffers()):
+        t.data = t.data.pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in list(host_net.parameters()) + list(host_net.buffers()))
+    runner.drain()
+    barrier()
+    e0 = runner.counters()
+    t0 = time.perf_counter()
+    runner.load_weights(host_net)
+    runner.round(args.steps)
+    recs = runner.drain()
+    e1 = runner.counters()
+    torch.cuda.synchronize(dev)
+    t_e2e = time.perf_counter() - t0
+    d2h = recs.nbytes + 8 * len(L.CTR_NAMES)
+    e2e_sims = e1["sims"] - e0["sims"]
+
+    # ---- per-launch duration of the hand-written kernel (k_step), live, CUDA events around each az_step
+    n_probe = min(args.steps, 200)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
+    nn_evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_probe)]
+    p0 = runner.counters()
+    ev = runner.evaluator
+    for a, b in zip(evs, nn_evs):
+        a[0].record()
+        runner.engine.step(ev.priors, ev.values, None, ev.obs, L.OBS_BF16_NHWC)
+        a[1].record()
+        ev()
+        b.record()
+    torch.cuda.synchronize(dev)
+    p1 = runner.counters()
+    pd = {k: p1[k] - p0[k] for k in p1}
+    step_ms = sum(a.elapsed_time(b) for a, b in evs) / n_probe
+    nn_ms = sum(a[1].elapsed_time(b) for a, b in zip(evs, nn_evs)) / n_probe
+    alg_bytes_per_launch = algorithmic_bytes(pd, rows * cols, n_actions) / n_probe
+
+    # ---- reduce over ranks
+    stats = torch.tensor([ms, float(d["sims"]), float(d["moves"]), float(d["games"]), float(d["overflow"]),
+                          t_e2e, float(e2e_sims)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        ms, t_e2e = float(mx[0]), float(mx[5])
+    else:
+        ms, t_e2e = float(stats[0]), float(stats[5])
+    sims, moves, games, overflow, e2e_sims = float(stats[1]), float(stats[2]), float(stats[3]), float(stats[4]), \
+        float(stats[6])
+    runner.close()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    value = sims / (ms / 1e3)
+    evals_per_s = args.trees * world * args.steps / (ms / 1e3)
+    flops = FLOPS_PER_EVAL.get(game, 0)
+    hbm_ach = alg_bytes_per_launch / (step_ms / 1e3) / 1e9
+    nn_tflops = args.trees * flops / (nn_ms / 1e3) / 1e12
+    line = {
+        "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "game": game, "n_playouts": args.playouts,
+                   "trees_per_gpu": args.trees, "parallelism": "independent game pool per GPU (x%d)" % world,
+                   "evaluator": "ResNet 5x50 bf16 channels-last via PyTorch, random-init weights",
+                   "noise": "device Dirichlet(0.3), ratio 0.25", "start": "counter % 21 random plies",
+                   "sim_cap_per_step": args.sim_cap, "cuda_graph": not args.no_graph,
+                   "l2_policy": "working set (%.1f GB node arenas + %.0f MB activations per step) exceeds the 126 MB L2"
+                                % (runner.engine.device_bytes / 1e9, args.trees * rows * cols * 64 * 2 * 3 / 1e6)},
+        "games_per_sec": games / (ms / 1e3), "moves_per_sec": moves / (ms / 1e3), "evals_per_sec": evals_per_s,
+        "sims_per_eval_slot": sims / (args.trees * world * args.steps), "overflow": overflow,
+        "e2e": {"value": e2e_sims / t_e2e, "unit": "sims/s", "h2d_bytes_per_step": h2d / args.steps,
+                "d2h_bytes_per_step": d2h / args.steps,
+                "what": "SelfPlayRunner.load_weights(host net) + round(K) + drain()/counters() to host, wall clock"},
+        "gpu_launches": args.steps * world,
+        "roofline": {"kernel": "k_step (select/expand/backup/advance/encode)", "bound": "hbm",
+                     "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": step_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                     "share_of_step": step_ms / (step_ms + nn_ms)},
+        "nn_roofline": {"kernel": "ResNet forward (cuDNN/cuBLAS via PyTorch)", "bound": "tensor",
+                        "achieved": nn_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": nn_tflops / peaks["bf16_tflops_sustained"], "avg_forward_ms": nn_ms,
+                        "flops_per_eval": flops, "peak_source": peaks["source"]},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(game, args.playouts, seconds_budget=args.cpu_seconds)
+        except Exception as e:  # the baseline must never hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "sims/s", "cores": 0, "kind": "port",
+                                    "sample": "failed: %r" % (e,)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=1200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--game", default="connect_four")
+    ap.add_argument("--trees", type=int, default=16384)
+    ap.add_argument("--playouts", type=int, default=800)
+    ap.add_argument("--sim-cap", type=int, default=16)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--ref-repeat", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

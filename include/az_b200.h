@@ -99,6 +99,7 @@ typedef struct az_config {
   int32_t max_sims_per_step;   /* cap on in-kernel (terminal-leaf) simulations per tree per step; 0 = unlimited */
   int32_t start_plies_mod;     /* AZ_F_RANDOM_START: k = counter % mod */
   int32_t record_capacity;     /* training records buffered on device; 0 = default */
+  int32_t max_games;           /* AZ_F_AUTO_RESTART: total games to start over all trees; 0 = unlimited */
   int32_t device;              /* CUDA device ordinal */
   uint32_t flags;              /* AZ_F_* */
   uint64_t seed;
@@ -115,7 +116,8 @@ typedef struct az_record {
   double root_q;                       /* soft-Z target is -root_q (game_utils.py:174); kind 1: returns()[0] */
   double v_a0c;                        /* game_utils.py:178 */
   double v_offpolicy;                  /* game_utils.py:183-194 (AZ_F_OFFPOLICY) */
-  /* followed by int32 counts[max_children]: root child visits in legal (ascending action) order */
+  /* followed by int32 counts[max_children]: root child visits in legal (ascending action) order,
+   * then int16 actions[max_children]: the action id of each child (-1 beyond n_legal) */
 } az_record;
 
 /* counters (az_counters): the measured means SURVEY 8(d) needs for bytes/simulation */

@@ -100,6 +100,9 @@ class State:
     def raw(self):
         return self._s
 
+    def get_game(self):
+        return self._game
+
     def __str__(self):
         g = self._game
         sym = ".xo" if g.game_id == cbind.GAME_CONNECT_FOUR else ".bw"

@@ -237,8 +237,11 @@ def selfplay_game(policy_fn, game_name, load_game, stats=None, **kwargs):
     n_actions = game.num_distinct_actions()
     bot = PortBot(game, 0, policy_fn, self_play=True, **kwargs)
     backup = str(kwargs.get("backup", "on-policy"))
+    max_plies = int(kwargs.get("max_plies", 0))  # port-only knob: bounded sample for the CPU baseline timing
     examples = []
     while not state.is_terminal():
+        if max_plies and len(examples) >= max_plies:
+            break
         policy, action = bot.step(state)
         sparse = dict(policy)
         dense = [sparse.get(i, 0.0) for i in range(n_actions)]
@@ -285,8 +288,10 @@ def _worker(job):  # examplegenerator.py:17-22
     from . import pyspiel_shim
     game = pyspiel_shim.load_game(game_name)
     stats = {}
+    t0 = time.time()
     ex = selfplay_game(PipeEvaluator(conn, game.information_state_normalized_vector_shape()), game_name,
                        pyspiel_shim.load_game, stats=stats, **kwargs)
+    stats["t_start"], stats["t_end"] = t0, time.time()
     return ex, stats
 
 
@@ -348,7 +353,12 @@ class PortGenerator:
             for ex, st in res.get():
                 games.append(ex)
                 for k, v in st.items():
-                    stats[k] = stats.get(k, 0) + v
+                    if k == "t_start":
+                        stats[k] = min(stats.get(k, v), v)
+                    elif k == "t_end":
+                        stats[k] = max(stats.get(k, v), v)
+                    else:
+                        stats[k] = stats.get(k, 0) + v
             pool.close()
             pool.join()
             server.terminate()
@@ -360,10 +370,10 @@ class PortGenerator:
 def time_selfplay(net, game_name, n_games, n_processes, **kwargs):
     """Wall-clock the multi-process generator; returns dict(sims_per_s, games_per_s, plies, cores, seconds)."""
     gen = PortGenerator(net, game_name, "cpu", n_pools=1, n_processes=n_processes, **kwargs)
-    t0 = time.time()
     games = gen.generate_examples(n_games)
-    dt = time.time() - t0
+    st = gen.last_stats
+    dt = st["t_end"] - st["t_start"]  # first worker start .. last worker end (process spawn / imports excluded)
     plies = sum(len(g) for g in games)
-    sims = gen.last_stats.get("sims", plies * int(kwargs.get("n_playouts", 100)))
-    return {"sims_per_s": sims / dt, "games_per_s": len(games) / dt, "plies": plies, "seconds": dt,
+    sims = st.get("sims", plies * int(kwargs.get("n_playouts", 100)))
+    return {"sims_per_s": sims / dt, "games_per_s": len(games) / dt, "plies": plies, "seconds": dt, "sims": sims,
             "cores": n_processes + 1, "host_cpus": os.cpu_count(), "n_games": len(games)}

@@ -1,0 +1,170 @@
+"""GPU parity of the drop-in Python API (MCTS / AlphaZeroBot / play_game_self / Net / ExampleGenerator)
+against the oracle's port of the reference (oracle.ref_port, pinned to /root/reference in test_oracle_vs_reference)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def shim():
+    from oracle import pyspiel_shim
+    return pyspiel_shim.install()  # stands in for the caller's OpenSpiel
+
+
+def _hash_policy(seed=77):
+    from oracle import cbind
+    lib = cbind.lib()
+
+    def fn(state):
+        A = state.get_game().num_distinct_actions()
+        pri = (C.c_double * A)()
+        v = C.c_double()
+        lib.oz_synth_eval(C.byref(state.raw()), 1, seed, 2 if A == 7 else 4, pri, C.byref(v))
+        return list(pri), v.value
+    return fn
+
+
+@pytest.mark.parametrize("game", ["connect_four", "breakthrough(rows=6,columns=6)"])
+def test_mcts_search_update_root_matches_reference_port(shim, game):
+    from oracle import ref_port
+    from alphazero_openspiel_b200.mcts import MCTS
+    g = shim.load_game(game)
+    A = g.num_distinct_actions()
+    fn = _hash_policy()
+    for dirichlet in (True, False):
+        ours = MCTS(fn, A, n_playouts=120, use_dirichlet=dirichlet, game_name=game)
+        ref = ref_port.PortMCTS(fn, A, n_playouts=120, use_dirichlet=dirichlet)
+        s = g.new_initial_state()
+        for move in range(4):
+            np.random.seed(10 + move)
+            a = ours.search(s)
+            np.random.seed(10 + move)
+            b = ref.search(s)
+            assert a == b
+            assert ours.root.N == ref.visits[ref.root] and ours.root.Q == ref.mean[ref.root]
+            kids = ours.root.children
+            acts, ids = ref.kids[ref.root]
+            assert list(kids.keys()) == acts
+            for act, j in zip(acts, ids):
+                assert kids[act].N == ref.visits[j] and kids[act].Q == ref.mean[j] and kids[act].P == ref.prior[j]
+            sz, a0c, off = ours.value_targets()
+            assert sz == ref.target_soft_z() and a0c == ref.target_a0c() and off == ref.target_off_policy()
+            act = int(np.argmax(a))
+            ours.update_root(act)
+            ref.update_root(act)
+            s.apply_action(act)
+        with pytest.raises(KeyError):
+            ours.update_root(A + 5 if game == "connect_four" else 0)
+
+
+@pytest.mark.parametrize("game,backup", [("connect_four", "on-policy"), ("connect_four", "soft-Z"),
+                                         ("connect_four", "A0C"), ("connect_four", "off-policy"),
+                                         ("breakthrough(rows=6,columns=6)", "off-policy")])
+def test_play_game_self_matches_reference_port(shim, game, backup):
+    """Whole games through AlphaZeroBot.step with the global numpy RNG: examples must be identical."""
+    from oracle import ref_port
+    from alphazero_openspiel_b200.game_utils import play_game_self
+    fn = _hash_policy(5)
+    np.random.seed(42)
+    ours = play_game_self(fn, game, n_playouts=40, backup=backup, c_puct=2.5)
+    np.random.seed(42)
+    ref = ref_port.selfplay_game(fn, game, shim.load_game, n_playouts=40, backup=backup, c_puct=2.5)
+    assert len(ours) == len(ref) > 4
+    for a, b in zip(ours, ref):
+        assert a[0] == b[0]
+        assert np.array_equal(a[1], b[1])
+        assert list(a[2]) == list(b[2])
+        assert a[3] == b[3]
+
+
+def test_bot_two_player_mode_and_restart(shim):
+    """keep_search_tree with two update_root calls per step (alphazerobot.py:60-64) and argmax moves."""
+    from oracle import ref_port
+    from alphazero_openspiel_b200.alphazerobot import AlphaZeroBot
+    g = shim.load_game("connect_four")
+    fn = _hash_policy(9)
+    ours = AlphaZeroBot(g, 0, fn, n_playouts=50, use_dirichlet=False)
+    ref = ref_port.PortBot(g, 0, fn, n_playouts=50, use_dirichlet=False)
+    s = g.new_initial_state()
+    rng = np.random.RandomState(0)
+    while not s.is_terminal() and len(s.history()) < 14:
+        pa, aa = ours.step(s)
+        pb, ab = ref.step(s)
+        assert aa == ab and [(x, float(y)) for x, y in pa] == [(x, float(y)) for x, y in pb]
+        s.apply_action(int(aa))
+        if not s.is_terminal():
+            s.apply_action(int(rng.choice(s.legal_actions())))
+    ours.restart()
+    assert ours.mcts.root.N == 0 and ours.mcts.root.is_leaf()
+
+
+def test_net_matches_fp32_reference_and_bf16_evaluator(shim):
+    """Net == oracle RefNet in fp32 (same state_dict); BatchedEvaluator (bf16, folded BN) within bf16 tolerance."""
+    import torch
+    from oracle import ref_net
+    from alphazero_openspiel_b200.network import Net, BatchedEvaluator
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    for game in ("connect_four", "breakthrough(rows=6,columns=6)"):
+        shape, A = E.game_shape(game)
+        torch.manual_seed(3)
+        ref = ref_net.RefNet(shape, A).eval()
+        with torch.no_grad():  # non-trivial BatchNorm statistics
+            for m in ref.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.running_mean.uniform_(-0.3, 0.3)
+                    m.running_var.uniform_(0.5, 1.5)
+                    m.weight.uniform_(0.5, 1.5)
+                    m.bias.uniform_(-0.2, 0.2)
+        net = Net(shape, A).eval()
+        net.load_state_dict(ref.state_dict())
+        B = 256
+        hist, lens = E.game_random_playouts(game, B, seed=5, max_plies=20)
+        out = E.game_replay_dev(game, hist, lens, L.OBS_F32_NCHW)
+        out_bf = E.game_replay_dev(game, hist, lens, L.OBS_BF16_NHWC)
+        x = out["obs"].cpu()
+        with torch.no_grad():
+            p_ref, v_ref = ref(x)
+            p_net, v_net = net(x)
+        assert torch.equal(p_ref, p_net) and torch.equal(v_ref, v_net)
+        ev = BatchedEvaluator(net, B, "cuda:0")
+        p, v = ev.eval_batch(out_bf["obs"])
+        # bf16 tolerance: 8-bit mantissa through 11 layers
+        assert (p.cpu() - p_ref).abs().max().item() < 3e-2
+        assert (v.cpu() - v_ref[:, 0]).abs().max().item() < 6e-2
+        assert (p.cpu().argmax(1) == p_ref.argmax(1)).float().mean().item() > 0.9
+
+
+def test_example_generator_contract(shim):
+    """ExampleGenerator.generate_examples: n_games finished games in the reference's example format, consistent
+    with the game rules (boards replay from the info-state string, targets are distributions over legal moves)."""
+    import torch
+    from alphazero_openspiel_b200.examplegenerator import ExampleGenerator
+    from alphazero_openspiel_b200.network import Net
+    from tests import oracle_util as ou
+    torch.manual_seed(0)
+    net = Net([3, 6, 7], 7).eval()
+    gen = ExampleGenerator(net, "connect_four", torch.device("cuda:0"), n_playouts=30, c_puct=2.5,
+                           dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", n_trees=16, seed=3)
+    games = gen.generate_examples(40)
+    assert len(games) == 40
+    assert gen.last_stats["overflow"] == 0 and gen.last_stats["games"] == 40
+    for game in games:
+        assert 7 <= len(game) <= 42
+        for i, (key, board, pol, value) in enumerate(game):
+            hist = [int(t) for t in key.split(", ")] if key else []
+            assert len(hist) == i
+            ref = ou.replay("connect_four", hist)
+            assert board.dtype == np.float64 and np.array_equal(board, ref["board"])
+            assert len(pol) == 7 and abs(sum(pol) - 1.0) < 1e-12
+            assert all((p == 0.0) for a, p in enumerate(pol) if a not in ref["legal"])
+            assert value in (-1.0, 0.0, 1.0)
+        vals = [ex[3] for ex in game]
+        assert all(vals[i] == -vals[i + 1] for i in range(len(vals) - 1))
+    # soft-Z / A0C / off-policy targets are finite numbers in [-1, 1]
+    gen2 = ExampleGenerator(net, "connect_four", torch.device("cuda:0"), n_playouts=30, backup="off-policy",
+                            n_trees=8, seed=4)
+    for game in gen2.generate_examples(8):
+        assert all(-1.0 <= ex[3] <= 1.0 for ex in game)
