@@ -1,0 +1,223 @@
+"""CPU: the oracle (C restatement + Python port + RefNet) against the golden vectors generated from the
+UNMODIFIED reference by tests/golden/make_golden.py, and -- when /root/reference is present (this container) --
+against the reference itself run live."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import cbind, pyspiel_shim, ref_port
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "reference_golden.json")) as f:
+    GOLD = json.load(f)
+L = cbind.lib()
+
+
+def _state(game, hist):
+    s = pyspiel_shim.load_game(game).new_initial_state()
+    for a in hist:
+        s.apply_action(a)
+    return s
+
+
+def _eval_cb(kind, seed):
+    def cb(sp, pp, vp, _u):
+        A = L.oz_num_actions(sp)
+        L.oz_synth_eval(sp, kind, seed, 2 if A == 7 else 4, pp, vp)
+    return cbind.EVAL_FN(cb)
+
+
+def _hash_policy(seed):
+    def fn(st):
+        A = st.get_game().num_distinct_actions()
+        pri = (C.c_double * A)()
+        v = C.c_double()
+        L.oz_synth_eval(C.byref(st.raw()), 1, seed, 2 if A == 7 else 4, pri, C.byref(v))
+        return list(pri), v.value
+    return fn
+
+
+def test_known_answer_vectors_c_oracle():
+    """SURVEY C.3 vectors (uniform evaluator) reproduced by the C oracle."""
+    for case in GOLD["known_answers"]:
+        game = case["game"]
+        A = pyspiel_shim.load_game(game).num_distinct_actions()
+        t = L.oz_tree_new(A, 2.5, case["n_playouts"], 0, 0.25)
+        cb = _eval_cb(0, 0)
+        counts = (C.c_int64 * A)()
+        if "reuse_after" in case:
+            s0 = _state(game, case["reuse_after"][0])
+            L.oz_tree_search(t, C.byref(s0.raw()), cb, None, None, counts)
+            L.oz_tree_update_root(t, case["reuse_after"][1])
+        s = _state(game, case["history"])
+        L.oz_tree_search(t, C.byref(s.raw()), cb, None, None, counts)
+        assert L.oz_tree_root_n(t) == case["root_n"]
+        assert L.oz_tree_root_q(t) == case["root_q"]
+        if "n" in case:
+            n = (C.c_int64 * A)()
+            q = (C.c_double * A)()
+            p = (C.c_double * A)()
+            L.oz_tree_root_children(t, n, q, p)
+            assert list(n) == case["n"] and list(q) == case["q"]
+        else:
+            assert [counts[a] for a in case["legal"]] == case["n_legal_order"]
+        L.oz_tree_free(t)
+
+
+def test_known_answers_are_the_survey_vectors():
+    ka = GOLD["known_answers"]
+    assert ka[0]["n"] == [15, 14, 14, 14, 14, 14, 14] and ka[0]["root_n"] == 100
+    assert ka[1]["n"] == [115, 114, 114, 114, 114, 114, 114]
+    assert ka[2]["n"] == [3, 3, 3, 3, 3, 81, 3] and ka[2]["root_q"] == -0.81
+    assert ka[3]["n"] == [6, 6, 7, 6, 6, 762, 6]
+    assert ka[4]["root_n"] == 114 and ka[4]["n"] == [17, 16, 16, 16, 16, 16, 16]
+    assert ka[5]["n_legal_order"] == [13] * 7 + [12] * 9
+
+
+@pytest.mark.parametrize("impl", ["c", "port"])
+def test_hash_evaluator_searches_with_injected_noise(impl):
+    """Reference visit counts / Q / P (incl. Dirichlet-mixed priors and re-rooted second searches), bit-exact."""
+    for case in GOLD["hash_searches"]:
+        game = case["game"]
+        g = pyspiel_shim.load_game(game)
+        A = g.num_distinct_actions()
+        s = _state(game, case["history"])
+        if impl == "c":
+            t = L.oz_tree_new(A, 2.5, case["n_playouts"], 1, 0.25)
+            cb = _eval_cb(1, 77)
+        else:
+            m = ref_port.PortMCTS(_hash_policy(77), A, n_playouts=case["n_playouts"])
+        for srch in case["searches"]:
+            legal = s.legal_actions()
+            assert legal == srch["legal"]
+            if impl == "c":
+                counts = (C.c_int64 * A)()
+                nz = (C.c_double * len(legal))(*srch["noise"])
+                L.oz_tree_search(t, C.byref(s.raw()), cb, None, nz, counts)
+                n = (C.c_int64 * A)()
+                q = (C.c_double * A)()
+                p = (C.c_double * A)()
+                L.oz_tree_root_children(t, n, q, p)
+                got = ([n[a] for a in legal], [q[a] for a in legal], [p[a] for a in legal],
+                       L.oz_tree_root_n(t), L.oz_tree_root_q(t))
+            else:
+                import numpy.random as npr
+                orig = npr.dirichlet
+                npr.dirichlet = lambda alpha, _n=srch["noise"]: np.array(_n)  # inject the recorded draw
+                try:
+                    m.search(s)
+                finally:
+                    npr.dirichlet = orig
+                acts, ids = m.kids[m.root]
+                assert acts == legal
+                got = ([m.visits[j] for j in ids], [m.mean[j] for j in ids], [m.prior[j] for j in ids],
+                       m.visits[m.root], m.mean[m.root])
+            assert got[0] == srch["n"], (game, case["history"])
+            assert got[1] == srch["q"] and got[2] == srch["p"]
+            assert got[3] == srch["root_n"] and got[4] == srch["root_q"]
+            a = srch["then_action"]
+            if impl == "c":
+                L.oz_tree_update_root(t, a)
+            else:
+                m.update_root(a)
+            s.apply_action(a)
+        if impl == "c":
+            L.oz_tree_free(t)
+
+
+def test_selfplay_examples_port_vs_golden():
+    """play_game_self examples for all four backup targets under np.random.seed(5), from the reference."""
+    for case in GOLD["selfplay"]:
+        np.random.seed(case["np_seed"])
+        ex = ref_port.selfplay_game(_hash_policy(77), case["game"], pyspiel_shim.load_game,
+                                    n_playouts=case["n_playouts"], backup=case["backup"], c_puct=2.5)
+        assert [e[0] for e in ex] == case["keys"]
+        assert [float(e[3]) for e in ex] == case["values"]
+        pol = [[[i, float(p)] for i, p in enumerate(e[2]) if p != 0.0] for e in ex]
+        assert pol == case["policies"]
+        sums = [float(np.sum(e[1] * np.arange(e[1].size).reshape(e[1].shape))) for e in ex]
+        assert sums == case["board_sums"]
+
+
+def test_encoding_pins_with_shipped_checkpoint():
+    """reference Net outputs on 64 Connect Four positions (shipped checkpoint) reproduced by the
+    oracle's RefNet over the oracle's observation planes -> pins plane order, row orientation and action ids."""
+    import torch
+    from oracle import ref_net
+    pins = GOLD["encoding_pins"]
+    sd = torch.load(os.path.join(HERE, "golden", "example_model_connect_four.pth"), map_location="cpu",
+                    weights_only=True)
+    net = ref_net.RefNet([3, 6, 7], 7).eval()
+    net.load_state_dict(sd)  # same key names as the reference checkpoints
+    boards = []
+    for h in pins["c4"]["histories"]:
+        boards.append(ref_port.board_planes(_state("connect_four", h), [3, 6, 7]))
+    with torch.no_grad():
+        p, v = net(torch.from_numpy(np.array(boards)).float())
+    assert np.abs(p.numpy() - np.array(pins["c4"]["p"])).max() < 1e-5
+    assert np.abs(v.numpy()[:, 0] - np.array(pins["c4"]["v"])).max() < 1e-5
+    assert int(np.argmax(pins["c4_fixture16"]["p"])) == 5 and pins["c4_fixture16"]["v"] > 0.5
+    assert pins["bt6_legal_mass_mean"] > 0.98
+
+
+def test_game_rules_properties():
+    """Random playouts: legal lists ascending, terminal <=> no legal moves, returns zero-sum, C4 draw only at 42."""
+    rng = np.random.RandomState(1)
+    for game in ["connect_four", "breakthrough(rows=6,columns=6)", "breakthrough", "breakthrough(rows=8,columns=5)"]:
+        g = pyspiel_shim.load_game(game)
+        for _ in range(60):
+            s = g.new_initial_state()
+            while not s.is_terminal():
+                legal = s.legal_actions()
+                assert legal == sorted(set(legal)) and len(legal) > 0
+                assert s.current_player() == len(s.history()) % 2
+                assert all(0 <= a < g.num_distinct_actions() for a in legal)
+                illegal = [a for a in range(min(g.num_distinct_actions(), 40)) if a not in legal]
+                if illegal:
+                    c = s.clone()
+                    with pytest.raises(RuntimeError):
+                        c.apply_action(illegal[0])
+                s.apply_action(int(rng.choice(legal)))
+            r = s.returns()
+            assert r[0] == -r[1] and s.legal_actions() == [] and s.current_player() == -4
+            if game == "connect_four":
+                assert (r[0] != 0) or len(s.history()) == 42
+            else:
+                assert r[0] != 0
+                assert r[(len(s.history()) - 1) % 2] == 1.0  # the mover wins in breakthrough
+    s = pyspiel_shim.load_game("breakthrough(rows=6,columns=6)").new_initial_state()
+    assert s.legal_actions() == [74, 76, 84, 86, 88, 96, 98, 100, 108, 110, 112, 120, 122, 124, 132, 134]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference only exists in the build container")
+def test_port_and_c_oracle_vs_live_reference():
+    """Live cross-check against /root/reference (mcts.py / game_utils.py run unmodified over the shim)."""
+    pyspiel_shim.install()
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import game_utils as ref_gu
+    import mcts as ref_mcts
+    fn = _hash_policy(123)
+    for game in ["connect_four", "breakthrough(rows=6,columns=6)"]:
+        for backup in ["on-policy", "off-policy"]:
+            np.random.seed(11)
+            a = ref_gu.play_game_self(fn, game, n_playouts=25, backup=backup)
+            np.random.seed(11)
+            b = ref_port.selfplay_game(fn, game, pyspiel_shim.load_game, n_playouts=25, backup=backup)
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                assert x[0] == y[0] and np.array_equal(x[1], y[1]) and x[2] == y[2] and x[3] == y[3]
+    g = pyspiel_shim.load_game("connect_four")
+    s = g.new_initial_state()
+    m = ref_mcts.MCTS(fn, 7, use_dirichlet=False, n_playouts=300)
+    m.search(s)
+    t = L.oz_tree_new(7, 2.5, 300, 0, 0.25)
+    counts = (C.c_int64 * 7)()
+    L.oz_tree_search(t, C.byref(s.raw()), _eval_cb(1, 123), None, None, counts)
+    assert list(counts) == [m.root.children[a].N for a in range(7)]
+    assert L.oz_tree_root_q(t) == m.root.Q
+    L.oz_tree_free(t)
