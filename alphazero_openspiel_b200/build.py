@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libaz_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "az_engine.cu")]
+SOURCES = [os.path.join(HERE, "csrc", "az_engine.cu"), os.path.join(HERE, "csrc", "az_resnet.cu")]
 DEPS = SOURCES + [os.path.join(HERE, "csrc", "az_games.cuh"),
                   os.path.join(HERE, "..", "include", "az_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1,0 +1,150 @@
+"""FusedEvaluator: the reference ResNet (network.py:21-104) on the hand-written sm_100a kernels of csrc/az_resnet.cu.
+
+Same contract as network.BatchedEvaluator -- obs bf16 [B,H,W,4] (written by az_step) -> priors fp32 [B,A], values
+fp32 [B] -- but the ten 3x3 convolutions run as tcgen05 implicit GEMMs with BatchNorm / LeakyReLU / bias / residual
+fused into their epilogues (11 launches instead of ~45 PyTorch kernels), on bf16 "padded rows" activations
+(see az_resnet.cu).  Host code here only folds/packs weights and sequences the launches; the FC head (a plain
+[B, P*64] x [P*64, A+1] GEMM) stays a cuBLAS call through torch, as does the softmax/tanh on its tiny output.
+
+Per evaluation:   stem(obs) -> U, X
+                  conv(U)+X -> X, T = lrelu(bn1_2(X))                  (block 1, conv2)
+                  for k = 2..5:  U = lrelu(conv(T) + b)  ;  X = conv(U) + X, T = lrelu(bn1_{k+1}(X))
+                  head: softmax / tanh (X_flat @ Wfc + b)
+"""
+import ctypes as C
+
+import torch
+from torch.nn import functional as F
+
+from . import _lib as L
+from .network import N_FILTERS, _fold_bn
+
+CH = 64
+LEAD = 16
+
+
+def pack_conv3x3(w):
+    """[64 out][64 in][3][3] (any float dtype, already zero-padded) -> bf16 [9][8][64][8] UMMA operand image."""
+    co, ci = w.shape[0], w.shape[1]
+    assert co == CH and ci == CH
+    t = w.permute(2, 3, 1, 0).reshape(9, ci, co)          # [tap][k][n]
+    t = t.reshape(9, 8, 8, co).permute(0, 1, 3, 2)          # [tap][kc][n][k%8]
+    return t.contiguous().to(torch.bfloat16)
+
+
+class FusedEvaluator:
+    def __init__(self, net, batch, device, n_ctas=0):
+        self.lib = L.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.EngineUnavailable("FusedEvaluator needs a CUDA device; there is no CPU fallback")
+        self.batch = batch
+        self.h, self.w, self.A = net.height, net.width, net.num_distinct_actions
+        self.Wp = self.w + 1
+        self.P = (self.h + 1) * self.Wp
+        self.n_ctas = n_ctas
+        rows = LEAD + batch * self.P + self.Wp + 1
+        self.rows_alloc = (rows + 127) // 128 * 128
+        dev = self.device
+        self.U = torch.zeros((self.rows_alloc, CH), dtype=torch.bfloat16, device=dev)
+        self.X = torch.zeros((self.rows_alloc, CH), dtype=torch.bfloat16, device=dev)
+        self.T = torch.zeros((self.rows_alloc, CH), dtype=torch.bfloat16, device=dev)
+        self.obs = torch.zeros((batch, self.h, self.w, 4), dtype=torch.bfloat16, device=dev)
+        self.priors = torch.zeros((batch, self.A), dtype=torch.float32, device=dev)
+        self.values = torch.zeros((batch,), dtype=torch.float32, device=dev)
+        self.par = None
+        self.load(net)
+
+    @torch.no_grad()
+    def load(self, net):
+        """Fold BatchNorm, pad 50->64 filters, pack the UMMA operand images.  In place after the first call, so a
+        captured CUDA graph keeps working when new weights arrive."""
+        dev = self.device
+        blocks = [getattr(net, "resblock%d" % i) for i in range(1, 6)]
+        new = {}
+        for k, blk in enumerate(blocks):
+            a1, b1 = _fold_bn(blk.bn1)
+            a2, b2 = _fold_bn(blk.bn2)
+            a1, b1, a2, b2 = a1.cpu(), b1.cpu(), a2.cpu(), b2.cpu()
+            w1 = blk.conv1.weight.double().cpu() * a2.view(-1, 1, 1, 1)       # bn2 folded into conv1
+            c1b = blk.conv1.bias.double().cpu() * a2 + b2
+            w2 = blk.conv2.weight.double().cpu()
+            c2b = blk.conv2.bias.double().cpu()
+            bias1 = torch.zeros(CH, dtype=torch.float64)
+            bias1[:N_FILTERS] = c1b
+            bias2 = torch.zeros(CH, dtype=torch.float64)
+            bias2[:N_FILTERS] = c2b
+            w2p = torch.zeros((CH, CH, 3, 3), dtype=torch.float64)
+            w2p[:N_FILTERS, :N_FILTERS] = w2
+            new["w2_%d" % k] = pack_conv3x3(w2p)
+            new["b2_%d" % k] = bias2.float()
+            new["b1_%d" % k] = bias1.float()
+            if k == 0:
+                cin = blk.conv1.in_channels
+                assert cin == 4 and blk.use_1x1conv
+                sw1 = torch.zeros((9, 4, CH), dtype=torch.float64)
+                sw1[:, :, :N_FILTERS] = w1.permute(2, 3, 1, 0).reshape(9, 4, N_FILTERS)
+                sw3 = torch.zeros((4, CH), dtype=torch.float64)
+                sw3[:, :N_FILTERS] = blk.conv3.weight.double().cpu().reshape(N_FILTERS, 4).t()
+                sb3 = torch.zeros(CH, dtype=torch.float64)
+                sb3[:N_FILTERS] = blk.conv3.bias.double().cpu()
+                new["stem_w1"], new["stem_w3"], new["stem_b3"] = sw1.float(), sw3.float(), sb3.float()
+                new["stem_s1"], new["stem_t1"] = a1.float(), b1.float()
+            else:
+                w1p = torch.zeros((CH, CH, 3, 3), dtype=torch.float64)
+                w1p[:N_FILTERS, :N_FILTERS] = w1
+                new["w1_%d" % k] = pack_conv3x3(w1p)
+                s = torch.zeros(CH, dtype=torch.float64)
+                t = torch.zeros(CH, dtype=torch.float64)
+                s[:N_FILTERS], t[:N_FILTERS] = a1, b1
+                new["s_%d" % k], new["t_%d" % k] = s.float(), t.float()   # bn1 of block k, applied by block k-1's epilogue
+        # FC head over the padded-rows flatten: [A+1][P][64]
+        fw = net.fc1.weight.double().cpu().view(self.A + 1, N_FILTERS, self.h, self.w)
+        fwp = torch.zeros((self.A + 1, self.h + 1, self.Wp, CH), dtype=torch.float64)
+        fwp[:, :self.h, :self.w, :N_FILTERS] = fw.permute(0, 2, 3, 1)
+        new["fw"] = fwp.reshape(self.A + 1, -1).to(torch.bfloat16)
+        new["fb"] = net.fc1.bias.double().cpu().float()
+        if self.par is None:
+            self.par = {k: v.contiguous().to(dev) for k, v in new.items()}
+        else:
+            for k, v in new.items():
+                self.par[k].copy_(v.to(dev))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu):
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        rc = self.lib.az_nn_conv3x3(p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), self.batch, self.h,
+                                    self.w, LEAD, self.rows_alloc, 1 if lrelu else 0, self.n_ctas, self._stream())
+        if rc:
+            raise RuntimeError("az_nn_conv3x3: " + self.lib.az_nn_last_error().decode())
+
+    @torch.no_grad()
+    def __call__(self):
+        """Evaluate self.obs into self.priors / self.values on the current stream (graph-capturable)."""
+        P_ = self.par
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        rc = self.lib.az_nn_stem(p(self.obs), p(P_["stem_w1"]), p(P_["b1_0"]), p(P_["stem_w3"]), p(P_["stem_b3"]),
+                                 p(P_["stem_s1"]), p(P_["stem_t1"]), p(self.U), p(self.X), self.batch, self.h, self.w,
+                                 LEAD, self._stream())
+        if rc:
+            raise RuntimeError("az_nn_stem: " + self.lib.az_nn_last_error().decode())
+        # block 1, second conv: X = conv(U) + X ; T = lrelu(bn1_2(X))
+        self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False)
+        for k in range(1, 5):
+            self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True)
+            last = k == 4
+            self._conv(self.U, P_["w2_%d" % k], P_["b2_%d" % k], self.X, self.X, None if last else self.T,
+                       None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False)
+        flat = self.X.view(-1)[LEAD * CH:(LEAD + self.batch * self.P) * CH].view(self.batch, self.P * CH)
+        out = F.linear(flat, P_["fw"]).float() + P_["fb"]
+        torch.softmax(out[:, :self.A], dim=1, out=self.priors)
+        torch.tanh(out[:, self.A], out=self.values)
+        return self.priors, self.values
+
+    @torch.no_grad()
+    def eval_batch(self, obs):
+        self.obs.copy_(obs.to(torch.bfloat16))
+        pr, v = self()
+        return pr.clone(), v.clone()

@@ -178,7 +178,7 @@ def run_ours(args):
     runner = SelfPlayRunner(net, game, dev, args.trees, n_playouts=args.playouts, c_puct=2.5, use_dirichlet=True,
                             dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", seed=0xC4 + rank,
                             auto_restart=True, random_start_mod=21, max_sims_per_step=args.sim_cap, records=True,
-                            use_graph=not args.no_graph)
+                            use_graph=not args.no_graph, evaluator=args.evaluator)
     # ---- warm-up (untimed): builds the first searches so trees are in steady state
     runner.round(args.warmup)
     runner.drain()
@@ -275,7 +275,9 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "game": game, "n_playouts": args.playouts,
                    "trees_per_gpu": args.trees, "parallelism": "independent game pool per GPU (x%d)" % world,
-                   "evaluator": "ResNet 5x50 bf16 channels-last via PyTorch, random-init weights",
+                   "evaluator": ("ResNet 5x50 bf16, hand-written tcgen05 implicit-GEMM convs (az_resnet.cu) + cuBLAS FC head"
+                                 if args.evaluator == "fused" else "ResNet 5x50 bf16 channels-last via PyTorch")
+                   + ", random-init weights",
                    "noise": "device Dirichlet(0.3), ratio 0.25", "start": "counter % 21 random plies",
                    "sim_cap_per_step": args.sim_cap, "cuda_graph": not args.no_graph,
                    "l2_policy": "working set (%.1f GB node arenas + %.0f MB activations per step) exceeds the 126 MB L2"
@@ -291,7 +293,7 @@ def run_ours(args):
                      "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": step_ms,
                      "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                      "share_of_step": step_ms / (step_ms + nn_ms)},
-        "nn_roofline": {"kernel": "ResNet forward (cuDNN/cuBLAS via PyTorch)", "bound": "tensor",
+        "nn_roofline": {"kernel": "ResNet forward (%s)" % args.evaluator, "bound": "tensor",
                         "achieved": nn_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": nn_tflops / peaks["bf16_tflops_sustained"], "avg_forward_ms": nn_ms,
                         "flops_per_eval": flops, "peak_source": peaks["source"]},
@@ -322,6 +324,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--ref-repeat", action="store_true")
+    ap.add_argument("--evaluator", default="fused", choices=["fused", "torch"])
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

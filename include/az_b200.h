@@ -220,6 +220,23 @@ int az_game_replay(int32_t game_id, int32_t rows, int32_t cols, int32_t n, const
 int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t n, uint64_t seed,
                             int32_t max_plies, int32_t* hist_dev, int32_t* len_dev, void* stream);
 
+/* ---- evaluator kernels (az_resnet.cu): the ResNet of network.py:21-104 for the batched evaluator ----
+ * Activations are bf16 "padded rows" [rows_alloc][64]: board b, cell (r,c) at row lead + b*(H+1)*(W+1) + r*(W+1) + c,
+ * pad rows/columns hold zeros; 50 filters are zero-padded to 64.  All pointers are device pointers.
+ *
+ * az_nn_conv3x3: out = conv3x3(in) + bias, optional LeakyReLU, optional + res; optional second output
+ *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  wpack is [9 taps][8][64][8] bf16
+ *   (tap = ky*3+kx, k-chunk, out-channel, in-channel%8).  tcgen05 implicit GEMM; n_ctas <= 0 -> one CTA per SM.
+ * az_nn_stem: the 4-plane first block input: u = LeakyReLU(conv1(LeakyReLU(s1*x+t1)) + b1) with w1 [9][4][64] fp32
+ *   (BatchNorm folded), r = conv1x1(x) + b3 with w3 [4][64] (network.py:99-103 for resblock1); obs is the az_step
+ *   AZ_OBS_BF16_NHWC batch [boards][H][W][4]. */
+const char* az_nn_last_error(void);
+int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
+                  const float* s2, const float* t2, int32_t boards, int32_t H, int32_t W, int32_t lead,
+                  int32_t rows_alloc, int32_t lrelu, int32_t n_ctas, void* stream);
+int az_nn_stem(const void* obs, const float* w1, const float* b1, const float* w3, const float* b3, const float* s1,
+               const float* t1, void* u, void* r, int32_t boards, int32_t H, int32_t W, int32_t lead, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

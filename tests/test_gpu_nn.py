@@ -1,0 +1,121 @@
+"""GPU numerics of the hand-written evaluator kernels (csrc/az_resnet.cu) against plain PyTorch fp32 references."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _padded_from_nchw(x, lead, rows_alloc):
+    """[B,64,H,W] float -> bf16 padded rows [rows_alloc,64] (zeros at pad rows/cols)."""
+    import torch
+    B, Cc, H, W = x.shape
+    Wp, P = W + 1, (H + 1) * (W + 1)
+    buf = torch.zeros((B, H + 1, Wp, Cc), dtype=torch.float32, device=x.device)
+    buf[:, :H, :W, :] = x.permute(0, 2, 3, 1)
+    out = torch.zeros((rows_alloc, Cc), dtype=torch.bfloat16, device=x.device)
+    out[lead:lead + B * P] = buf.reshape(B * P, Cc).to(torch.bfloat16)
+    return out
+
+
+def _nchw_from_padded(buf, lead, B, H, W):
+    Wp, P = W + 1, (H + 1) * (W + 1)
+    t = buf[lead:lead + B * P].float().reshape(B, H + 1, Wp, buf.shape[1])
+    return t[:, :H, :W, :].permute(0, 3, 1, 2).contiguous(), t
+
+
+@pytest.mark.parametrize("H,W,B", [(6, 7, 37), (6, 6, 300), (8, 8, 129), (6, 7, 4096)])
+def test_conv3x3_tcgen05_matches_torch(H, W, B):
+    """out = conv3x3(in) + bias [-> LeakyReLU] [+ res], out2 = LeakyReLU(s2*out+t2); pad rows stay exactly zero.
+    Tolerance: inputs/weights are bf16-exact on both sides, accumulation fp32 -> only the final bf16 rounding differs
+    (rel 2^-8) plus fp32 summation-order noise."""
+    import torch
+    import torch.nn.functional as F
+    from alphazero_openspiel_b200 import _lib as L
+    from alphazero_openspiel_b200.nn_fused import pack_conv3x3, LEAD
+    lib = L.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(H * 100 + W + B)
+    x = torch.randn((B, 64, H, W), generator=g).to(dev).to(torch.bfloat16).float()
+    w = (torch.randn((64, 64, 3, 3), generator=g) * 0.05).to(dev).to(torch.bfloat16).float()
+    bias = torch.randn((64,), generator=g).to(dev)
+    res = torch.randn((B, 64, H, W), generator=g).to(dev).to(torch.bfloat16).float()
+    s2 = (torch.rand((64,), generator=g) + 0.5).to(dev)
+    t2 = torch.randn((64,), generator=g).to(dev)
+    P = (H + 1) * (W + 1)
+    rows_alloc = (LEAD + B * P + W + 2 + 127) // 128 * 128
+    xin = _padded_from_nchw(x, LEAD, rows_alloc)
+    rin = _padded_from_nchw(res, LEAD, rows_alloc)
+    wp = pack_conv3x3(w).to(dev)
+    ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ref = F.conv2d(x, w, bias, padding=1)
+    for lrelu, use_res, use_out2 in [(0, 0, 0), (1, 0, 0), (0, 1, 1), (0, 1, 0)]:
+        out = torch.full((rows_alloc, 64), 7.0, dtype=torch.bfloat16, device=dev)
+        out2 = torch.full((rows_alloc, 64), 7.0, dtype=torch.bfloat16, device=dev) if use_out2 else None
+        rc = lib.az_nn_conv3x3(ptr(xin), ptr(wp), ptr(bias), ptr(rin) if use_res else None, ptr(out), ptr(out2),
+                               ptr(s2) if use_out2 else None, ptr(t2) if use_out2 else None, B, H, W, LEAD,
+                               rows_alloc, lrelu, 0, st)
+        assert rc == 0, lib.az_nn_last_error()
+        torch.cuda.synchronize()
+        want = ref
+        if lrelu:
+            want = F.leaky_relu(want)
+        if use_res:
+            want = want + res
+        got, full = _nchw_from_padded(out, LEAD, B, H, W)
+        err = (got - want).abs()
+        tol = 2.0 ** -7 * want.abs() + 2e-2
+        assert bool((err <= tol).all()), (lrelu, use_res, float(err.max()))
+        # pad rows / columns and the lead / tail rows are exactly zero
+        assert float(full[:, H, :, :].abs().max()) == 0.0 and float(full[:, :, W, :].abs().max()) == 0.0
+        assert float(out[:LEAD].float().abs().max()) == 0.0 and float(out[LEAD + B * P:].float().abs().max()) == 0.0
+        if use_out2:
+            want2 = F.leaky_relu(want * s2.view(1, -1, 1, 1) + t2.view(1, -1, 1, 1))
+            got2, full2 = _nchw_from_padded(out2, LEAD, B, H, W)
+            err2 = (got2 - want2).abs()
+            assert bool((err2 <= 2.0 ** -6 * want2.abs() + 4e-2).all()), float(err2.max())
+            assert float(full2[:, H, :, :].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("game", ["connect_four", "breakthrough(rows=6,columns=6)", "breakthrough"])
+def test_fused_evaluator_matches_fp32_reference(game):
+    """Whole network on the tcgen05 path vs the oracle's fp32 RefNet (bf16 tolerance, stated) and vs the PyTorch
+    bf16 evaluator (same precision class)."""
+    import torch
+    from oracle import ref_net
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    from alphazero_openspiel_b200.network import Net, BatchedEvaluator
+    from alphazero_openspiel_b200.nn_fused import FusedEvaluator
+    shape, A = E.game_shape(game)
+    torch.manual_seed(11)
+    ref = ref_net.RefNet(shape, A).eval()
+    with torch.no_grad():
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.uniform_(-0.3, 0.3)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    net = Net(shape, A).eval()
+    net.load_state_dict(ref.state_dict())
+    B = 1000
+    hist, lens = E.game_random_playouts(game, B, seed=5, max_plies=24)
+    x32 = E.game_replay_dev(game, hist, lens, L.OBS_F32_NCHW)["obs"]
+    xbf = E.game_replay_dev(game, hist, lens, L.OBS_BF16_NHWC)["obs"]
+    with torch.no_grad():
+        p_ref, v_ref = ref(x32.cpu())
+    fe = FusedEvaluator(net, B, "cuda:0")
+    p, v = fe.eval_batch(xbf)
+    p, v = p.cpu(), v.cpu()
+    assert torch.isfinite(p).all() and torch.isfinite(v).all()
+    assert (p.sum(1) - 1).abs().max().item() < 1e-3
+    assert (p - p_ref).abs().max().item() < 3e-2
+    assert (v - v_ref[:, 0]).abs().max().item() < 6e-2
+    assert (p.argmax(1) == p_ref.argmax(1)).float().mean().item() > 0.9
+    pe, ve = BatchedEvaluator(net, B, "cuda:0").eval_batch(xbf)
+    assert (p - pe.cpu()).abs().max().item() < 3e-2 and (v - ve.cpu()).abs().max().item() < 6e-2
+    # weights can be reloaded in place (new generation) and a second call is deterministic
+    p2, v2 = fe.eval_batch(xbf)
+    assert torch.equal(p2.cpu(), p) and torch.equal(v2.cpu(), v)
