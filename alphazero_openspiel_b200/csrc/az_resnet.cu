@@ -8,24 +8,30 @@
 //     LEAD + b*P + r*Wp + c,   Wp = W+1 (one shared zero column), P = (H+1)*Wp (one zero row per board)
 // and every pad row holds zeros, so a 3x3 convolution is 9 shifted copies of the same operand:
 //     out[m][:] = sum_tap  in[m + (ky-1)*Wp + (kx-1)][:] @ W_tap          (implicit GEMM, no im2col)
+// Pad rows are zero from allocation and are never read or written by these kernels.
 //
-// k_conv3x3: persistent CTAs (one per SM), warp-specialised:
-//   warps 0..3  producers (one per smem stage): cp.async the A slab (128 + 2*HALO rows) of a tile into its stage, laid out
-//               [k-chunk of 8 channels][row] x 16 B  == the UMMA "no-swizzle, K-major" canonical layout, so a tap is just a
-//               different 16-byte-aligned start address in the operand descriptor;
-//   warp 4      MMA issuer: one elected lane issues 9 taps x 4 k-steps of tcgen05.mma (M=128, N=64, K=16, bf16 -> fp32)
-//               into one of two TMEM accumulator stages, then tcgen05.commit -> mbarriers;
-//   warps 5..12 epilogue: tcgen05.ld the 128x64 fp32 tile (one row x 32 channels per thread), + bias, LeakyReLU, + residual, the next
-//               block's BatchNorm affine + LeakyReLU as a second output, zero the pad rows, store bf16.
-// The 3x3 weights of the layer (9 x 64 x 64 bf16 = 72 KB, BatchNorm folded) stay resident in smem for the whole launch.
+// k_conv<STEM>: persistent CTAs (one per SM), warp-specialised, 13 warps:
+//   warps 0..3  producers, one per smem stage: bring the A slab (128 + 2*HALO rows) of a tile into the stage, laid out
+//               [k-chunk of 8 channels][row] x 16 B == the UMMA "no-swizzle, K-major" canonical layout, so a tap is just a
+//               different 16-byte-aligned start address in the operand descriptor.
+//                 STEM=false: cp.async from the previous layer's activations.
+//                 STEM=true : built on the fly from the az_step observation planes: channels 0-3 = LeakyReLU(bn1(x)),
+//                             channels 4-7 = x (for the 1x1 skip projection), one k-step of 16.
+//   warp 4      MMA issuer: one elected lane issues tcgen05.mma (M=128, K=16, bf16 -> fp32 in TMEM):
+//                 STEM=false: 9 taps x 4 k-steps, N=64;  STEM=true: 9 taps x 1 k-step, N=128 (conv1 | skip).
+//               two TMEM accumulator stages; tcgen05.commit -> mbarriers.
+//   warps 5..12 epilogue: tcgen05.ld (32 rows x 32 channels per warp), + bias, LeakyReLU, + residual, second output
+//               (next block's BatchNorm + LeakyReLU, or the skip projection for STEM), bf16 stores coalesced through smem.
+// The layer's weights (72 KB / 36 KB, BatchNorm folded) are resident in smem for the whole launch.
 //
-// k_stem: the 4-channel first layer (bn1 affine + LeakyReLU + conv3x3 4->64 + folded bn2 + LeakyReLU, and the 1x1 skip
-// projection) on CUDA cores: K = 36 is too thin for the tensor cores and it is 0.6 % of the FLOPs.
+// Measured limiter (profiles/r01_summary.md): the shared-memory operand fetch of SS-mode MMAs at N=64 -- the slab is
+// re-read once per tap and tap-shifted core matrices straddle 128-byte lines -- about 78 cycles per MMA vs 32 of math.
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/az_b200.h"
 
@@ -33,27 +39,30 @@ namespace aznn {
 
 constexpr int CH = 64;            // padded channel count (50 filters -> 64)
 constexpr int TILE_M = 128;       // output rows per MMA tile
-constexpr int SLAB = 153;         // smem rows per A stage (>= 128 + 2*HALO; odd => conflict-free cp.async scatter)
+constexpr int SLAB = 153;         // smem rows per A stage (>= 128 + 2*HALO; odd => conflict-free scatter)
 constexpr int MAX_HALO = 12;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = 8 * SLAB * 16;        // 19,584
-constexpr int W_BYTES = 9 * CH * CH * 2;            // 73,728
+constexpr int W_BYTES = 9 * CH * CH * 2;            // 73,728 (STEM: 9 x 128 x 16 x 2 = 36,864)
 constexpr int NUM_THREADS = 416;                    // 13 warps: 4 producers, 1 MMA issuer, 8 epilogue
 constexpr int EPI_WARPS = 8;
 constexpr float LRELU_SLOPE = 0.01f;
 
 struct ConvParams {
-  const __nv_bfloat16* in;    // [rows_alloc][64]
-  const __nv_bfloat16* wpack; // [9][8][64][8]  (tap, k-chunk, n, k%8)
+  const __nv_bfloat16* in;    // [rows_alloc][64]            (STEM: observation planes [boards][H][W][4])
+  const __nv_bfloat16* wpack; // [9][8][64][8]  (tap, k-chunk, n, k%8)      (STEM: [9][2][128][8])
   const float* bias;          // [64]
   const __nv_bfloat16* res;   // [rows_alloc][64] or null
   __nv_bfloat16* out;         // [rows_alloc][64]
-  __nv_bfloat16* out2;        // [rows_alloc][64] or null: lrelu(s2*out + t2)
+  __nv_bfloat16* out2;        // [rows_alloc][64] or null: lrelu(s2*out + t2)   (STEM: skip projection + t2)
   const float* s2;
   const float* t2;
+  const float* stem_st;       // STEM: device [8]: bn1 scale[4], shift[4] of the input planes
   int rows_alloc;             // multiple of 128
   int n_tiles;
   int lead, boards, P, Wp, H, W;
+  int board0;                 // this launch handles boards [board0, board0 + boards)
+  int tile0;                  // first 128-row tile of that range
   int lrelu;                  // apply LeakyReLU to (acc + bias)
 };
 
@@ -97,9 +106,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128
-__device__ __forceinline__ uint32_t umma_idesc_bf16_m128_n64() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -110,7 +119,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -119,7 +128,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 __device__ __forceinline__ bool elect_one() {  // exactly one lane of a converged warp
   uint32_t pred;
   asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
@@ -130,22 +138,38 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : LRELU_SLOPE * x; }
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]);
+  o.y = pack_bf16(f[2], f[3]);
+  o.z = pack_bf16(f[4], f[5]);
+  o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
 
-// smem carve-up (dynamic): [weights 73,728][A stages 4 x 19,584][bias 256][s2 256][t2 256][barriers]
+// smem carve-up (dynamic): [weights 73,728][A stages 4 x 19,584][bias 256][s2 256][t2 256][barriers][epilogue staging]
 struct SmemLayout {
   static constexpr int W_OFF = 0;
   static constexpr int A_OFF = W_BYTES;
   static constexpr int BIAS_OFF = A_OFF + STAGES * A_STAGE_BYTES;
   static constexpr int S2_OFF = BIAS_OFF + 256;
   static constexpr int T2_OFF = S2_OFF + 256;
-  static constexpr int BAR_OFF = T2_OFF + 256;  // full[4], empty[4], tfull[2], tempty[2] (8 B each), tmem ptr
+  static constexpr int BAR_OFF = T2_OFF + 256;           // 13 mbarriers (8 B each), then the TMEM base address
   static constexpr int STG_OFF = BAR_OFF + 16 * 8 + 16;  // per epilogue warp: res / out / out2 staging, 32 rows x 80 B
   static constexpr int STG_ROW = 80;                     // 64 B (half a row) + 16 B pad: conflict-free row-per-thread access
   static constexpr int STG_WARP = 3 * 32 * STG_ROW;
   static constexpr int TOTAL = STG_OFF + EPI_WARPS * STG_WARP;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) {
+template <bool STEM>
+__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
+  constexpr int N_MMA = STEM ? 128 : 64;              // accumulator columns per tile
+  constexpr int K_STEPS = STEM ? 1 : 4;               // 16-channel k-steps per tap
+  constexpr int W_N = STEM ? 128 : 64;                // rows of the B operand image
+  constexpr int W_TAP_BYTES = W_N * 16 * 2 * K_STEPS; // bytes of one tap's weights
+  constexpr int W_TOTAL = 9 * W_TAP_BYTES;
+  constexpr uint32_t TMEM_COLS = STEM ? 256u : 128u;
+
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
@@ -159,10 +183,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) 
   auto bar_empty = [&](int s) { return s_bar + 8u * (STAGES + s); };
   auto bar_tfull = [&](int a) { return s_bar + 8u * (2 * STAGES + a); };
   auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * STAGES + 2 + a); };
-  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::BAR_OFF + 16 * 8);  // after 13 barriers
+  auto bar_w = [&]() { return s_bar + 8u * (2 * STAGES + 4); };
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::BAR_OFF + 16 * 8);
 
   // ---- one-time setup: barriers + TMEM (weights and epilogue vectors are loaded by the epilogue warps, see below)
-  auto bar_w = [&]() { return s_bar + 8u * (2 * STAGES + 4); };
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full(s), 1);
@@ -177,9 +201,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) 
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
-                 "r"(128u)
+                 "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (STEM) {  // k-chunk 1 (channels 8..15) of every stage is constant zero in stem mode
+    for (int i = threadIdx.x; i < STAGES * SLAB; i += NUM_THREADS) {
+      const int st = i / SLAB, r = i % SLAB;
+      *reinterpret_cast<uint4*>(smem + SmemLayout::A_OFF + st * A_STAGE_BYTES + (SLAB + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -189,50 +220,104 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) 
   const int halo = p.Wp + 1;
   const int slab_rows = TILE_M + 2 * halo;
   const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long long range_lo = (long long)p.lead + (long long)p.board0 * p.P;
+  const long long range_hi = range_lo + (long long)p.boards * p.P;
+  const int valid_pos = p.H * p.Wp;
 
   if (warp < STAGES) {
     // =========================== producers (one warp per smem stage) ===========================
-    // Warp w owns stage w and the tiles it == w (mod STAGES): wait until the MMA warp has released the stage, cp.async
-    // the slab, wait for ITS OWN copies only, make them visible to the tensor core's async proxy, signal `full`.
+    // Warp w owns stage w and the tiles it == w (mod STAGES): wait until the MMA warp has released the stage, fill the
+    // slab, wait for ITS OWN copies only, make them visible to the tensor core's async proxy, signal `full`.
     // Four such warps keep four slabs in flight without any cross-tile dependency between load issue and hand-off.
     const int stage = warp;
-    const uint32_t dst_lane = s_a + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)((lane & 7) * SLAB + (lane >> 3)) * 16u;
-    const int n_it = (slab_rows * 8 + 31) / 32;
     for (int it = stage, round = 0; it < my_tiles; it += STAGES, ++round) {
       mbar_wait(bar_empty(stage), ((uint32_t)round & 1u) ^ 1u);
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      const long long row0 = (long long)tile * TILE_M - halo;
-      const bool interior = row0 >= 0 && row0 + slab_rows <= p.rows_alloc;
-      const __nv_bfloat16* src_lane = p.in + (row0 + (lane >> 3)) * CH + (lane & 7) * 8;
-      if (interior) {
-#pragma unroll 4
+      const int tile = p.tile0 + (int)blockIdx.x + it * (int)gridDim.x;
+      if constexpr (!STEM) {
+        const uint32_t dst_lane = s_a + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)((lane & 7) * SLAB + (lane >> 3)) * 16u;
+        const int n_it = (slab_rows + 3) / 4;
+        long long grow = (long long)tile * TILE_M - halo + (lane >> 3);
+        const __nv_bfloat16* src = p.in + grow * CH + (lane & 7) * 8;
+        // position of this lane's first row inside its board, then advanced incrementally (4 rows per step, 4 < Wp)
+        const long long q0 = grow - range_lo;
+        int pos = (int)(((q0 % p.P) + p.P) % p.P);
+        int col = pos % p.Wp;
         for (int i = 0; i < n_it; ++i) {
-          if ((lane >> 3) + 4 * i < slab_rows) cp_async16(dst_lane + (uint32_t)i * 64u, src_lane + (long long)i * 4 * CH, 16u);
+          if ((lane >> 3) + 4 * i < slab_rows) {
+            // pad rows / pad columns / rows outside this launch's boards are zero by construction: zero-fill, no read
+            const bool ok = grow >= range_lo && grow < range_hi && pos < valid_pos && col < p.W;
+            cp_async16(dst_lane + (uint32_t)i * 64u, ok ? (const void*)src : (const void*)p.in, ok ? 16u : 0u);
+          }
+          grow += 4;
+          src += 4 * CH;
+          pos += 4;
+          if (pos >= p.P) pos -= p.P;
+          col += 4;
+          if (col >= p.Wp) col -= p.Wp;
         }
+        cp_async_commit();
+        cp_async_wait<0>();
       } else {
-        for (int i = 0; i < n_it; ++i) {
-          const int r = (lane >> 3) + 4 * i;
+        // Build k-chunk 0 of the slab from the observation planes: [lrelu(bn1(x))_0..3 | x_0..3] per cell.
+        uint8_t* dst = smem + SmemLayout::A_OFF + stage * A_STAGE_BYTES;
+        const uint2* obs = reinterpret_cast<const uint2*>(p.in);
+        const int cells = p.H * p.W;
+        const long long row0 = (long long)tile * TILE_M - halo;
+        constexpr int PER_LANE = (SLAB + 31) / 32;
+        float bs[4], bt[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          bs[i] = p.stem_st[i];
+          bt[i] = p.stem_st[4 + i];
+        }
+        uint2 raw[PER_LANE];
+        bool okv[PER_LANE];
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+          const int r = lane + 32 * i;
+          const long long grow = row0 + r;
+          bool ok = r < slab_rows && grow >= range_lo && grow < range_hi;
+          long long cell_index = 0;
+          if (ok) {
+            const long long q = grow - p.lead;
+            const int b = (int)(q / p.P), pos = (int)(q % p.P);
+            const int rr = pos / p.Wp, cc = pos % p.Wp;
+            ok = pos < valid_pos && cc < p.W;
+            cell_index = (long long)b * cells + rr * p.W + cc;
+          }
+          okv[i] = ok;
+          raw[i] = ok ? obs[cell_index] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+          const int r = lane + 32 * i;
           if (r < slab_rows) {
-            const long long grow = row0 + r;
-            const bool ok = grow >= 0 && grow < p.rows_alloc;
-            cp_async16(dst_lane + (uint32_t)i * 64u, ok ? (const void*)(src_lane + (long long)i * 4 * CH) : (const void*)p.in,
-                       ok ? 16u : 0u);
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (okv[i]) {
+              const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&raw[i].x);
+              const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&raw[i].y);
+              const float x0 = __bfloat162float(x01.x), x1 = __bfloat162float(x01.y);
+              const float x2 = __bfloat162float(x23.x), x3 = __bfloat162float(x23.y);
+              o.x = pack_bf16(lrelu(bs[0] * x0 + bt[0]), lrelu(bs[1] * x1 + bt[1]));
+              o.y = pack_bf16(lrelu(bs[2] * x2 + bt[2]), lrelu(bs[3] * x3 + bt[3]));
+              o.z = raw[i].x;
+              o.w = raw[i].y;
+            }
+            *reinterpret_cast<uint4*>(dst + r * 16) = o;
           }
         }
       }
-      cp_async_commit();
-      cp_async_wait<0>();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full(stage));
     }
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = umma_idesc_bf16_m128_n64();
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)N_MMA);
     // Operand descriptors differ only in their 14-bit start-address field (units of 16 B): precompute the bases and the
     // nine tap offsets so that the issue loop is two integer adds per tcgen05.mma (the single issuing thread is
     // latency-bound on whatever address arithmetic sits between two MMAs).
-    const uint64_t wdesc0 = umma_desc(s_w, 1024u, 128u);
+    const uint64_t wdesc0 = umma_desc(s_w, (uint32_t)W_N * 16u, 128u);
     const uint64_t adesc0 = umma_desc(s_a + (uint32_t)halo * 16u, SLAB * 16u, 128u);
     long long dlt[9];
 #pragma unroll
@@ -247,14 +332,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) 
       // uniform registers instead of wrapping every tcgen05.mma in an ELECT / BRA.U.ANY serialisation loop.
       if (elect_one()) {
         const uint64_t ab = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES / 16));
-        const uint32_t d = tmem_base + (uint32_t)acc * CH;
+        const uint32_t d = tmem_base + (uint32_t)(acc * N_MMA);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const uint64_t at = ab + (uint64_t)dlt[tap];
-          const uint64_t bt = wdesc0 + (uint64_t)(tap * 512);
+          const uint64_t bt = wdesc0 + (uint64_t)(tap * (W_TAP_BYTES / 16));
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            umma_bf16(d, at + (uint64_t)(j * 2 * SLAB), bt + (uint64_t)(j * 128), idesc, (tap | j) != 0 ? 1u : 0u);
+          for (int j = 0; j < K_STEPS; ++j)
+            umma_bf16(d, at + (uint64_t)(j * 2 * SLAB), bt + (uint64_t)(j * 2 * W_N), idesc, (tap | j) != 0 ? 1u : 0u);
         }
         umma_commit(bar_empty(stage));  // smem stage reusable once these MMAs have read it
         umma_commit(bar_tfull(acc));    // accumulator ready for the epilogue
@@ -269,15 +354,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) 
     const int e = warp - 5;
     const int q = warp & 3;     // TMEM lane quarter this warp may access
     const int half = e >> 2;    // channels [32*half, 32*half+32)
-    {  // weights (72 KB) + epilogue vectors -> smem, asynchronously to the producers' first slabs
+    {  // weights + epilogue vectors -> smem, asynchronously to the producers' first slabs
       const int et = e * 32 + lane;
-      for (int i = et; i < W_BYTES / 16; i += EPI_WARPS * 32)
+      for (int i = et; i < W_TOTAL / 16; i += EPI_WARPS * 32)
         cp_async16(s_w + (uint32_t)i * 16u, reinterpret_cast<const uint4*>(p.wpack) + i, 16u);
       cp_async_commit();
       if (et < CH) {
         s_bias[et] = p.bias[et];
-        s_s2[et] = p.out2 ? p.s2[et] : 0.f;
-        s_t2[et] = p.out2 ? p.t2[et] : 0.f;
+        s_s2[et] = (p.out2 && p.s2) ? p.s2[et] : 0.f;
+        s_t2[et] = (p.out2 && p.t2) ? p.t2[et] : 0.f;
       }
       cp_async_wait<0>();
       fence_proxy_async();
@@ -290,37 +375,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) 
     uint8_t* stg_out2 = stg + 64 * SmemLayout::STG_ROW;
     const int crow = lane >> 2, cch = lane & 3;  // cooperative copy: lane -> (row within group of 8, 16-byte chunk)
     const int col0 = half * 32;
-    for (int it = 0; it < my_tiles; ++it) {
-      const int acc = it & 1;
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      const long long m_warp = (long long)tile * TILE_M + q * 32;
-      const long long m = m_warp + lane;
-      // validity of this thread's row: inside the board area, not a pad row / pad column
-      const long long qrow = m - p.lead;
-      bool valid = qrow >= 0 && qrow < (long long)p.boards * p.P;
-      if (valid) {
+    const bool has_res = !STEM && p.res != nullptr;
+
+    auto row_valid = [&](long long m) {
+      const long long qrow = m - range_lo;
+      bool v = qrow >= 0 && qrow < range_hi - range_lo;
+      if (v) {
         const int pos = (int)(qrow % p.P);
-        valid = pos < p.H * p.Wp && (pos % p.Wp) < p.W;
+        v = pos < valid_pos && (pos % p.Wp) < p.W;
       }
-      if (p.res != nullptr) {  // coalesced residual load -> staging (before waiting for the accumulator)
+      return v;
+    };
+    // residual rows of the NEXT tile are prefetched into registers while the current tile is processed
+    uint4 rnext[4];
+    uint32_t vmask_next = 0;
+    auto prefetch = [&](int it) {
+      const int tile = p.tile0 + (int)blockIdx.x + it * (int)gridDim.x;
+      const long long m_warp = (long long)tile * TILE_M + q * 32;
+      vmask_next = __ballot_sync(0xffffffffu, row_valid(m_warp + lane));
+      if (has_res) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.res + m_warp * CH + col0);
-        uint4 tmp[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tmp[i] = rp[(i * 8 + crow) * 8 + cch];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(stg_res + (i * 8 + crow) * SmemLayout::STG_ROW + cch * 16) = tmp[i];
+          rnext[i] = ((vmask_next >> (i * 8 + crow)) & 1u) ? rp[(i * 8 + crow) * 8 + cch] : make_uint4(0u, 0u, 0u, 0u);
       }
+    };
+    if (my_tiles > 0) prefetch(0);
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int acc = it & 1;
+      const int tile = p.tile0 + (int)blockIdx.x + it * (int)gridDim.x;
+      const long long m_warp = (long long)tile * TILE_M + q * 32;
+      // Invalid rows (pads, other launches' boards) are never loaded or stored.
+      const uint32_t vmask = vmask_next;
+      if (has_res) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(stg_res + (i * 8 + crow) * SmemLayout::STG_ROW + cch * 16) = rnext[i];
+      }
+      if (it + 1 < my_tiles) prefetch(it + 1);
       __syncwarp();
       mbar_wait(bar_tfull(acc), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       uint32_t v[32];
+      uint32_t w[STEM ? 32 : 1];
       {
-        uint32_t (&v0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[0]);
-        uint32_t (&v1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[16]);
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * CH + col0);
-        tmem_ld16(taddr, v0);
-        tmem_ld16(taddr + 16u, v1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_MMA + col0);
+        tmem_ld16(taddr, &v[0]);
+        tmem_ld16(taddr + 16u, &v[16]);
+        if constexpr (STEM) {
+          tmem_ld16(taddr + 64u, &w[0]);
+          tmem_ld16(taddr + 80u, &w[16]);
+        }
         tmem_ld_wait();
       }
       // accumulator read -> hand the TMEM stage back to the MMA warp before the math and the global stores
@@ -335,7 +441,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) 
           f[i] = __uint_as_float(v[cb * 16 + i]) + s_bias[col0 + cb * 16 + i];
           if (p.lrelu) f[i] = lrelu(f[i]);
         }
-        if (p.res != nullptr) {
+        if (has_res) {
           const uint4 r0 = *reinterpret_cast<const uint4*>(stg_res + lane * SmemLayout::STG_ROW + cb * 32);
           const uint4 r1 = *reinterpret_cast<const uint4*>(stg_res + lane * SmemLayout::STG_ROW + cb * 32 + 16);
           const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -346,44 +452,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) 
             f[2 * i + 1] += __bfloat162float(r2.y);
           }
         }
-        if (!valid) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = 0.f;
-        }
-        uint4 o0, o1;
-        o0.x = pack_bf16(f[0], f[1]);   o0.y = pack_bf16(f[2], f[3]);
-        o0.z = pack_bf16(f[4], f[5]);   o0.w = pack_bf16(f[6], f[7]);
-        o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]);
-        o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
-        *reinterpret_cast<uint4*>(stg_out + lane * SmemLayout::STG_ROW + cb * 32) = o0;
-        *reinterpret_cast<uint4*>(stg_out + lane * SmemLayout::STG_ROW + cb * 32 + 16) = o1;
+        *reinterpret_cast<uint4*>(stg_out + lane * SmemLayout::STG_ROW + cb * 32) = pack8(&f[0]);
+        *reinterpret_cast<uint4*>(stg_out + lane * SmemLayout::STG_ROW + cb * 32 + 16) = pack8(&f[8]);
         if (p.out2 != nullptr) {
           float g[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            g[i] = valid ? lrelu(s_s2[col0 + cb * 16 + i] * f[i] + s_t2[col0 + cb * 16 + i]) : 0.f;
-          o0.x = pack_bf16(g[0], g[1]);   o0.y = pack_bf16(g[2], g[3]);
-          o0.z = pack_bf16(g[4], g[5]);   o0.w = pack_bf16(g[6], g[7]);
-          o1.x = pack_bf16(g[8], g[9]);   o1.y = pack_bf16(g[10], g[11]);
-          o1.z = pack_bf16(g[12], g[13]); o1.w = pack_bf16(g[14], g[15]);
-          *reinterpret_cast<uint4*>(stg_out2 + lane * SmemLayout::STG_ROW + cb * 32) = o0;
-          *reinterpret_cast<uint4*>(stg_out2 + lane * SmemLayout::STG_ROW + cb * 32 + 16) = o1;
+          for (int i = 0; i < 16; ++i) {
+            if constexpr (STEM) g[i] = __uint_as_float(w[cb * 16 + i]) + s_t2[col0 + cb * 16 + i];
+            else g[i] = lrelu(s_s2[col0 + cb * 16 + i] * f[i] + s_t2[col0 + cb * 16 + i]);
+          }
+          *reinterpret_cast<uint4*>(stg_out2 + lane * SmemLayout::STG_ROW + cb * 32) = pack8(&g[0]);
+          *reinterpret_cast<uint4*>(stg_out2 + lane * SmemLayout::STG_ROW + cb * 32 + 16) = pack8(&g[8]);
         }
       }
       __syncwarp();
-      {  // coalesced copy-out
+      {  // coalesced copy-out of the valid rows
         uint4* op = reinterpret_cast<uint4*>(p.out + m_warp * CH + col0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = i * 8 + crow;
-          op[r * 8 + cch] = *reinterpret_cast<const uint4*>(stg_out + r * SmemLayout::STG_ROW + cch * 16);
+          if ((vmask >> r) & 1u)
+            op[r * 8 + cch] = *reinterpret_cast<const uint4*>(stg_out + r * SmemLayout::STG_ROW + cch * 16);
         }
         if (p.out2 != nullptr) {
           uint4* op2 = reinterpret_cast<uint4*>(p.out2 + m_warp * CH + col0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = i * 8 + crow;
-            op2[r * 8 + cch] = *reinterpret_cast<const uint4*>(stg_out2 + r * SmemLayout::STG_ROW + cch * 16);
+            if ((vmask >> r) & 1u)
+              op2[r * 8 + cch] = *reinterpret_cast<const uint4*>(stg_out2 + r * SmemLayout::STG_ROW + cch * 16);
           }
         }
       }
@@ -395,114 +492,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv3x3(const ConvParams p) 
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
-  }
-}
-
-// ---------------------------------------------------------------- stem (4 input planes) on CUDA cores
-struct StemParams {
-  const __nv_bfloat16* obs;  // [boards][H][W][4]
-  const float* w1;           // [9][4][64]  conv1 (bn2 folded), tap-major
-  const float* b1;           // [64]
-  const float* w3;           // [4][64]     1x1 skip projection
-  const float* b3;           // [64]
-  const float* s1;           // [4] bn1 scale
-  const float* t1;           // [4] bn1 shift
-  __nv_bfloat16* u;          // padded rows: lrelu(conv1(lrelu(bn1(x))))
-  __nv_bfloat16* r;          // padded rows: conv3(x)
-  int boards, H, W, Wp, P, lead;
-};
-
-__global__ void __launch_bounds__(256) k_stem(const StemParams p) {
-  // One board per block iteration: the 4-plane board goes to smem once (raw x and t = lrelu(bn1(x)) with a zero border),
-  // then thread (cell, 16-channel part) accumulates the 9 taps without bounds checks.
-  __shared__ __align__(16) float s_w1[9 * 4 * 64];
-  __shared__ __align__(16) float s_w3[4 * 64];
-  __shared__ float s_b1[64], s_b3[64], s_s1[4], s_t1[4];
-  __shared__ float4 s_t[10 * 10];  // (H+2) x (W+2), H,W <= 8
-  __shared__ float4 s_x[64];
-  for (int i = threadIdx.x; i < 9 * 4 * 64; i += blockDim.x) s_w1[i] = p.w1[i];
-  for (int i = threadIdx.x; i < 4 * 64; i += blockDim.x) s_w3[i] = p.w3[i];
-  if (threadIdx.x < 64) {
-    s_b1[threadIdx.x] = p.b1[threadIdx.x];
-    s_b3[threadIdx.x] = p.b3[threadIdx.x];
-  }
-  if (threadIdx.x < 4) {
-    s_s1[threadIdx.x] = p.s1[threadIdx.x];
-    s_t1[threadIdx.x] = p.t1[threadIdx.x];
-  }
-  if (threadIdx.x < 100) s_t[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-  const int cells = p.H * p.W, W2 = p.W + 2;
-  const int cell = threadIdx.x >> 2, part = threadIdx.x & 3;
-  const int r = cell / p.W, c = cell % p.W;
-  for (int b = blockIdx.x; b < p.boards; b += gridDim.x) {
-    if ((int)threadIdx.x < cells) {
-      const int rr = threadIdx.x / p.W, cc = threadIdx.x % p.W;
-      const uint2 raw = reinterpret_cast<const uint2*>(p.obs)[(long long)b * cells + threadIdx.x];
-      const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-      const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-      const float4 x = make_float4(__bfloat162float(x01.x), __bfloat162float(x01.y), __bfloat162float(x23.x),
-                                   __bfloat162float(x23.y));
-      s_x[threadIdx.x] = x;
-      s_t[(rr + 1) * W2 + cc + 1] = make_float4(lrelu(s_s1[0] * x.x + s_t1[0]), lrelu(s_s1[1] * x.y + s_t1[1]),
-                                                lrelu(s_s1[2] * x.z + s_t1[2]), lrelu(s_s1[3] * x.w + s_t1[3]));
-    }
-    __syncthreads();
-    if (cell < cells) {
-      float a1[16], a3[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        a1[i] = s_b1[part * 16 + i];
-        a3[i] = s_b3[part * 16 + i];
-      }
-      {
-        const float4 x = s_x[cell];
-        const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const float4* w4 = reinterpret_cast<const float4*>(s_w3 + ci * 64 + part * 16);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 wv = w4[i];
-            a3[4 * i] += xs[ci] * wv.x; a3[4 * i + 1] += xs[ci] * wv.y;
-            a3[4 * i + 2] += xs[ci] * wv.z; a3[4 * i + 3] += xs[ci] * wv.w;
-          }
-        }
-      }
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const float4 t = s_t[(r + tap / 3) * W2 + c + tap % 3];
-        const float ts[4] = {t.x, t.y, t.z, t.w};
-        const float* w = s_w1 + tap * 4 * 64 + part * 16;
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-          const float4* w4 = reinterpret_cast<const float4*>(w + ci * 64);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 wv = w4[i];
-            a1[4 * i] += ts[ci] * wv.x; a1[4 * i + 1] += ts[ci] * wv.y;
-            a1[4 * i + 2] += ts[ci] * wv.z; a1[4 * i + 3] += ts[ci] * wv.w;
-          }
-        }
-      }
-      const long long row = p.lead + (long long)b * p.P + r * p.Wp + c;
-      uint4 o[2], o3[2];
-      uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-      uint32_t* ow3 = reinterpret_cast<uint32_t*>(o3);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        ow[i] = pack_bf16(lrelu(a1[2 * i]), lrelu(a1[2 * i + 1]));
-        ow3[i] = pack_bf16(a3[2 * i], a3[2 * i + 1]);
-      }
-      uint4* up = reinterpret_cast<uint4*>(p.u + row * CH + part * 16);
-      uint4* rp = reinterpret_cast<uint4*>(p.r + row * CH + part * 16);
-      up[0] = o[0];
-      up[1] = o[1];
-      rp[0] = o3[0];
-      rp[1] = o3[1];
-    }
-    __syncthreads();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -519,15 +509,55 @@ static int nn_fail(int code, const char* what, cudaError_t e) {
   return code;
 }
 
+static int fill_geometry(aznn::ConvParams& p, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead,
+                         int32_t rows_alloc, const char* who) {
+  using namespace aznn;
+  p.Wp = W + 1;
+  p.P = (H + 1) * p.Wp;
+  p.H = H;
+  p.W = W;
+  p.lead = lead;
+  p.boards = boards;
+  p.board0 = board0;
+  p.rows_alloc = rows_alloc;
+  if (rows_alloc % TILE_M != 0 || p.Wp + 1 > MAX_HALO || TILE_M + 2 * (p.Wp + 1) > SLAB || lead < p.Wp + 1 || board0 < 0 ||
+      boards <= 0 || (long long)lead + (long long)(board0 + boards) * p.P > rows_alloc) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "%s: bad geometry (rows_alloc %% 128, lead >= W+2, capacity)", who);
+    return -1;
+  }
+  const long long lo = (long long)lead + (long long)board0 * p.P, hi = lo + (long long)boards * p.P;
+  p.tile0 = (int)(lo / TILE_M);
+  p.n_tiles = (int)((hi + TILE_M - 1) / TILE_M) - p.tile0;
+  return 0;
+}
+
+template <bool STEM>
+static int launch_conv(const aznn::ConvParams& p, int n_ctas, void* stream) {
+  using namespace aznn;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv<STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::TOTAL);
+    if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
+    attr_set = true;
+  }
+  int grid = n_ctas > 0 ? n_ctas : 148;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  k_conv<STEM><<<grid, NUM_THREADS, SmemLayout::TOTAL, (cudaStream_t)stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nn_fail(-2, "k_conv launch", e);
+  return 0;
+}
+
 extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                             const float* s2, const float* t2, int32_t boards, int32_t H, int32_t W, int32_t lead,
-                             int32_t rows_alloc, int32_t lrelu, int32_t n_ctas, void* stream) {
+                             const float* s2, const float* t2, int32_t board0, int32_t boards, int32_t H, int32_t W,
+                             int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t n_ctas, void* stream) {
   using namespace aznn;
   if (!in || !wpack || !bias || !out) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: null argument");
     return -1;
   }
   ConvParams p;
+  memset(&p, 0, sizeof(p));
   p.in = (const __nv_bfloat16*)in;
   p.wpack = (const __nv_bfloat16*)wpack;
   p.bias = bias;
@@ -536,62 +566,29 @@ extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bia
   p.out2 = (__nv_bfloat16*)out2;
   p.s2 = s2;
   p.t2 = t2;
-  p.Wp = W + 1;
-  p.P = (H + 1) * p.Wp;
-  p.H = H;
-  p.W = W;
-  p.lead = lead;
-  p.boards = boards;
-  p.rows_alloc = rows_alloc;
-  if (rows_alloc % TILE_M != 0 || p.Wp + 1 > MAX_HALO || lead < p.Wp + 1 ||
-      (long long)lead + (long long)boards * p.P > rows_alloc) {
-    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: bad geometry (rows_alloc %% 128, lead >= W+2, capacity)");
-    return -1;
-  }
-  p.n_tiles = rows_alloc / TILE_M;
   p.lrelu = lrelu;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::TOTAL);
-    if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
-    attr_set = true;
-  }
-  int grid = n_ctas > 0 ? n_ctas : 148;
-  if (grid > p.n_tiles) grid = p.n_tiles;
-  k_conv3x3<<<grid, NUM_THREADS, SmemLayout::TOTAL, (cudaStream_t)stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return nn_fail(-2, "k_conv3x3 launch", e);
-  return 0;
+  if (fill_geometry(p, board0, boards, H, W, lead, rows_alloc, "az_nn_conv3x3")) return -1;
+  return launch_conv<false>(p, n_ctas, stream);
 }
 
-extern "C" int az_nn_stem(const void* obs, const float* w1, const float* b1, const float* w3, const float* b3,
-                          const float* s1, const float* t1, void* u, void* r, int32_t boards, int32_t H, int32_t W,
-                          int32_t lead, void* stream) {
+extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st,
+                          void* u, void* r, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead,
+                          int32_t rows_alloc, int32_t n_ctas, void* stream) {
   using namespace aznn;
-  StemParams p;
-  p.obs = (const __nv_bfloat16*)obs;
-  p.w1 = w1;
-  p.b1 = b1;
-  p.w3 = w3;
-  p.b3 = b3;
-  p.s1 = s1;
-  p.t1 = t1;
-  p.u = (__nv_bfloat16*)u;
-  p.r = (__nv_bfloat16*)r;
-  p.boards = boards;
-  p.H = H;
-  p.W = W;
-  p.Wp = W + 1;
-  p.P = (H + 1) * p.Wp;
-  p.lead = lead;
-  if (H > 8 || W > 8) {
-    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_stem: board larger than 8x8");
+  if (!obs || !wpack || !b1 || !b3 || !bn_st || !u || !r) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_stem: null argument");
     return -1;
   }
-  const int block = (H * W * 4 + 31) / 32 * 32;  // 4 threads per cell (16 output channels each)
-  int grid = boards < 148 * 8 ? boards : 148 * 8;
-  k_stem<<<grid, block, 0, (cudaStream_t)stream>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return nn_fail(-2, "k_stem launch", e);
-  return 0;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = (const __nv_bfloat16*)obs;
+  p.wpack = (const __nv_bfloat16*)wpack;
+  p.bias = b1;
+  p.out = (__nv_bfloat16*)u;
+  p.out2 = (__nv_bfloat16*)r;
+  p.t2 = b3;
+  p.lrelu = 1;
+  p.stem_st = bn_st;
+  if (fill_geometry(p, board0, boards, H, W, lead, rows_alloc, "az_nn_stem")) return -1;
+  return launch_conv<true>(p, n_ctas, stream);
 }

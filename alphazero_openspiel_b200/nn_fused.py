@@ -33,7 +33,7 @@ def pack_conv3x3(w):
 
 
 class FusedEvaluator:
-    def __init__(self, net, batch, device, n_ctas=0):
+    def __init__(self, net, batch, device, n_ctas=0, slice_boards=0):
         self.lib = L.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -43,6 +43,9 @@ class FusedEvaluator:
         self.Wp = self.w + 1
         self.P = (self.h + 1) * self.Wp
         self.n_ctas = n_ctas
+        # optional board slices (measured: per-launch overhead outweighs L2 residency, so the default is one slice)
+        slice_boards = batch if slice_boards <= 0 else slice_boards
+        self.slices = [(b0, min(slice_boards, batch - b0)) for b0 in range(0, batch, slice_boards)]
         rows = LEAD + batch * self.P + self.Wp + 1
         self.rows_alloc = (rows + 127) // 128 * 128
         dev = self.device
@@ -82,14 +85,15 @@ class FusedEvaluator:
             if k == 0:
                 cin = blk.conv1.in_channels
                 assert cin == 4 and blk.use_1x1conv
-                sw1 = torch.zeros((9, 4, CH), dtype=torch.float64)
-                sw1[:, :, :N_FILTERS] = w1.permute(2, 3, 1, 0).reshape(9, 4, N_FILTERS)
-                sw3 = torch.zeros((4, CH), dtype=torch.float64)
-                sw3[:, :N_FILTERS] = blk.conv3.weight.double().cpu().reshape(N_FILTERS, 4).t()
+                # stem operand image [9 taps][2 k-chunks][128 n][8]: n<64 conv1 on k 0-3 (input lrelu(bn1(x))),
+                # n>=64 the 1x1 skip projection on k 4-7 (raw x) of the centre tap
+                sw = torch.zeros((9, 2, 128, 8), dtype=torch.float64)
+                sw[:, 0, :N_FILTERS, 0:4] = w1.permute(2, 3, 0, 1).reshape(9, N_FILTERS, 4)
+                sw[4, 0, CH:CH + N_FILTERS, 4:8] = blk.conv3.weight.double().cpu().reshape(N_FILTERS, 4)
                 sb3 = torch.zeros(CH, dtype=torch.float64)
                 sb3[:N_FILTERS] = blk.conv3.bias.double().cpu()
-                new["stem_w1"], new["stem_w3"], new["stem_b3"] = sw1.float(), sw3.float(), sb3.float()
-                new["stem_s1"], new["stem_t1"] = a1.float(), b1.float()
+                new["stem_w"], new["stem_b3"] = sw.to(torch.bfloat16), sb3.float()
+                new["stem_st"] = torch.cat([a1, b1]).float()
             else:
                 w1p = torch.zeros((CH, CH, 3, 3), dtype=torch.float64)
                 w1p[:N_FILTERS, :N_FILTERS] = w1
@@ -113,9 +117,9 @@ class FusedEvaluator:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu):
+    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, b0, nb):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
-        rc = self.lib.az_nn_conv3x3(p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), self.batch, self.h,
+        rc = self.lib.az_nn_conv3x3(p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), b0, nb, self.h,
                                     self.w, LEAD, self.rows_alloc, 1 if lrelu else 0, self.n_ctas, self._stream())
         if rc:
             raise RuntimeError("az_nn_conv3x3: " + self.lib.az_nn_last_error().decode())
@@ -125,22 +129,24 @@ class FusedEvaluator:
         """Evaluate self.obs into self.priors / self.values on the current stream (graph-capturable)."""
         P_ = self.par
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-        rc = self.lib.az_nn_stem(p(self.obs), p(P_["stem_w1"]), p(P_["b1_0"]), p(P_["stem_w3"]), p(P_["stem_b3"]),
-                                 p(P_["stem_s1"]), p(P_["stem_t1"]), p(self.U), p(self.X), self.batch, self.h, self.w,
-                                 LEAD, self._stream())
-        if rc:
-            raise RuntimeError("az_nn_stem: " + self.lib.az_nn_last_error().decode())
-        # block 1, second conv: X = conv(U) + X ; T = lrelu(bn1_2(X))
-        self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False)
-        for k in range(1, 5):
-            self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True)
-            last = k == 4
-            self._conv(self.U, P_["w2_%d" % k], P_["b2_%d" % k], self.X, self.X, None if last else self.T,
-                       None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False)
-        flat = self.X.view(-1)[LEAD * CH:(LEAD + self.batch * self.P) * CH].view(self.batch, self.P * CH)
-        out = F.linear(flat, P_["fw"]).float() + P_["fb"]
-        torch.softmax(out[:, :self.A], dim=1, out=self.priors)
-        torch.tanh(out[:, self.A], out=self.values)
+        for b0, nb in self.slices:
+            rc = self.lib.az_nn_stem(p(self.obs), p(P_["stem_w"]), p(P_["b1_0"]), p(P_["stem_b3"]), p(P_["stem_st"]),
+                                     p(self.U), p(self.X), b0, nb, self.h, self.w, LEAD, self.rows_alloc, self.n_ctas,
+                                     self._stream())
+            if rc:
+                raise RuntimeError("az_nn_stem: " + self.lib.az_nn_last_error().decode())
+            # block 1, second conv: X = conv(U) + X ; T = lrelu(bn1_2(X))
+            self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False, b0, nb)
+            for k in range(1, 5):
+                self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True, b0, nb)
+                last = k == 4
+                self._conv(self.U, P_["w2_%d" % k], P_["b2_%d" % k], self.X, self.X, None if last else self.T,
+                           None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False, b0, nb)
+            lo = (LEAD + b0 * self.P) * CH
+            flat = self.X.view(-1)[lo:lo + nb * self.P * CH].view(nb, self.P * CH)
+            out = F.linear(flat, P_["fw"]).float() + P_["fb"]
+            torch.softmax(out[:, :self.A], dim=1, out=self.priors[b0:b0 + nb])
+            torch.tanh(out[:, self.A], out=self.values[b0:b0 + nb])
         return self.priors, self.values
 
     @torch.no_grad()

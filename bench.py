@@ -178,7 +178,7 @@ def run_ours(args):
     runner = SelfPlayRunner(net, game, dev, args.trees, n_playouts=args.playouts, c_puct=2.5, use_dirichlet=True,
                             dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", seed=0xC4 + rank,
                             auto_restart=True, random_start_mod=21, max_sims_per_step=args.sim_cap, records=True,
-                            use_graph=not args.no_graph, evaluator=args.evaluator)
+                            use_graph=not args.no_graph, evaluator=args.evaluator, nn_slice=args.nn_slice)
     # ---- warm-up (untimed): builds the first searches so trees are in steady state
     runner.round(args.warmup)
     runner.drain()
@@ -325,6 +325,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--ref-repeat", action="store_true")
     ap.add_argument("--evaluator", default="fused", choices=["fused", "torch"])
+    ap.add_argument("--nn-slice", type=int, default=0)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -227,15 +227,19 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  * az_nn_conv3x3: out = conv3x3(in) + bias, optional LeakyReLU, optional + res; optional second output
  *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  wpack is [9 taps][8][64][8] bf16
  *   (tap = ky*3+kx, k-chunk, out-channel, in-channel%8).  tcgen05 implicit GEMM; n_ctas <= 0 -> one CTA per SM.
- * az_nn_stem: the 4-plane first block input: u = LeakyReLU(conv1(LeakyReLU(s1*x+t1)) + b1) with w1 [9][4][64] fp32
- *   (BatchNorm folded), r = conv1x1(x) + b3 with w3 [4][64] (network.py:99-103 for resblock1); obs is the az_step
- *   AZ_OBS_BF16_NHWC batch [boards][H][W][4]. */
+ * az_nn_stem: the 4-plane first block on the same tcgen05 kernel (the slab is built from the az_step
+ *   AZ_OBS_BF16_NHWC batch [boards][H][W][4]): u = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1), r = conv1x1(x) + b3
+ *   (network.py:99-103 for resblock1).  wpack is [9 taps][2][128][8] bf16: rows 0-63 = conv1 (BatchNorm folded) on
+ *   k 0-3, rows 64-127 = the 1x1 skip projection on k 4-7 of the centre tap.  bn_st = device [8]: scale[4], shift[4].
+ *   Both kernels work on boards [board0, board0+boards) of the full buffers and never read or write pad rows or rows of
+ *   other boards (pads must be zero from allocation). */
 const char* az_nn_last_error(void);
 int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                  const float* s2, const float* t2, int32_t boards, int32_t H, int32_t W, int32_t lead,
+                  const float* s2, const float* t2, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead,
                   int32_t rows_alloc, int32_t lrelu, int32_t n_ctas, void* stream);
-int az_nn_stem(const void* obs, const float* w1, const float* b1, const float* w3, const float* b3, const float* s1,
-               const float* t1, void* u, void* r, int32_t boards, int32_t H, int32_t W, int32_t lead, void* stream);
+int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st, void* u,
+               void* r, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc,
+               int32_t n_ctas, void* stream);
 
 #ifdef __cplusplus
 }
