@@ -24,14 +24,18 @@
 //               (next block's BatchNorm + LeakyReLU, or the skip projection for STEM), bf16 stores coalesced through smem.
 // The layer's weights (72 KB / 36 KB, BatchNorm folded) are resident in smem for the whole launch.
 //
-// Measured limiter (profiles/r01_summary.md): the shared-memory operand fetch of SS-mode MMAs at N=64 -- the slab is
-// re-read once per tap and tap-shifted core matrices straddle 128-byte lines -- about 78 cycles per MMA vs 32 of math.
+// Operand layouts: STEM=false uses SWIZZLE_128B K-major (one activation row = one 128-byte line, so tap shifts never
+// straddle lines); STEM=true keeps the no-swizzle layout (its K is a single 16-channel step).
+// Measured limiter (profiles/r01_summary.md, scripts/conv_microbench.py): shared-memory bandwidth.  Every tile moves
+// ~216 KB of MMA operands (the slab is re-read once per tap, the 72 KB of weights once per tile) plus producer writes
+// and epilogue staging through the SM's 128 B/clk smem datapath; the MMAs alone take ~67 cycles each vs 32 of math.
 
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/az_b200.h"
 
@@ -42,7 +46,7 @@ constexpr int TILE_M = 128;       // output rows per MMA tile
 constexpr int SLAB = 153;         // smem rows per A stage (>= 128 + 2*HALO; odd => conflict-free scatter)
 constexpr int MAX_HALO = 12;
 constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = 8 * SLAB * 16;        // 19,584
+constexpr int A_STAGE_BYTES = 160 * 128;            // 20,480: 160 rows x 128 B (SW128, 1024-aligned) >= 2 * SLAB * 16 (stem)
 constexpr int W_BYTES = 9 * CH * CH * 2;            // 73,728 (STEM: 9 x 128 x 16 x 2 = 36,864)
 constexpr int NUM_THREADS = 416;                    // 13 warps: 4 producers, 1 MMA issuer, 8 epilogue
 constexpr int EPI_WARPS = 8;
@@ -64,6 +68,7 @@ struct ConvParams {
   int board0;                 // this launch handles boards [board0, board0 + boards)
   int tile0;                  // first 128-row tile of that range
   int lrelu;                  // apply LeakyReLU to (acc + bias)
+  int debug;                  // experiments: 1 = producers skip loads, 2 = epilogue skips math+stores, 4 = no MMAs
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -106,6 +111,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
   return d;
 }
+// SWIZZLE_128B, K-major: rows are 128 B (64 bf16) wide, 8-row atoms of 1024 B (SBO), 16-byte chunks XOR-swizzled with
+// the row index; LBO unused.  Measured on B200: the XOR is applied to absolute smem address bits, so a start address
+// shifted by whole rows works with base_offset = 0 (base_offset = row & 7 gives wrong results).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;            // SBO = 1024 B
+  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
 __device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
@@ -137,7 +154,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : LRELU_SLOPE * x; }
+__device__ __forceinline__ float lrelu(float x) { return fmaxf(x, LRELU_SLOPE * x); }  // slope < 1
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 o;
   o.x = pack_bf16(f[0], f[1]);
@@ -233,8 +250,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     for (int it = stage, round = 0; it < my_tiles; it += STAGES, ++round) {
       mbar_wait(bar_empty(stage), ((uint32_t)round & 1u) ^ 1u);
       const int tile = p.tile0 + (int)blockIdx.x + it * (int)gridDim.x;
-      if constexpr (!STEM) {
-        const uint32_t dst_lane = s_a + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)((lane & 7) * SLAB + (lane >> 3)) * 16u;
+      if (p.debug & 1) {
+        // (experiment) no loads
+      } else if constexpr (!STEM) {
+        // SW128 layout: smem row r (128 B) holds the 8 chunks of one activation row, chunk c at ((c ^ (r & 7)) * 16)
+        const uint32_t dst_stage = s_a + (uint32_t)stage * A_STAGE_BYTES;
         const int n_it = (slab_rows + 3) / 4;
         long long grow = (long long)tile * TILE_M - halo + (lane >> 3);
         const __nv_bfloat16* src = p.in + grow * CH + (lane & 7) * 8;
@@ -246,7 +266,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
           if ((lane >> 3) + 4 * i < slab_rows) {
             // pad rows / pad columns / rows outside this launch's boards are zero by construction: zero-fill, no read
             const bool ok = grow >= range_lo && grow < range_hi && pos < valid_pos && col < p.W;
-            cp_async16(dst_lane + (uint32_t)i * 64u, ok ? (const void*)src : (const void*)p.in, ok ? 16u : 0u);
+            const uint32_t r = (uint32_t)((lane >> 3) + 4 * i);
+            cp_async16(dst_stage + r * 128u + ((((uint32_t)lane & 7u) ^ (r & 7u)) << 4),
+                       ok ? (const void*)src : (const void*)p.in, ok ? 16u : 0u);
           }
           grow += 4;
           src += 4 * CH;
@@ -317,8 +339,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     // Operand descriptors differ only in their 14-bit start-address field (units of 16 B): precompute the bases and the
     // nine tap offsets so that the issue loop is two integer adds per tcgen05.mma (the single issuing thread is
     // latency-bound on whatever address arithmetic sits between two MMAs).
-    const uint64_t wdesc0 = umma_desc(s_w, (uint32_t)W_N * 16u, 128u);
-    const uint64_t adesc0 = umma_desc(s_a + (uint32_t)halo * 16u, SLAB * 16u, 128u);
     long long dlt[9];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) dlt[tap] = (long long)((tap / 3 - 1) * p.Wp + (tap % 3 - 1));
@@ -331,15 +351,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       // elect.sync (not `lane == 0`): the compiler then knows exactly one lane issues and keeps the descriptors in
       // uniform registers instead of wrapping every tcgen05.mma in an ELECT / BRA.U.ANY serialisation loop.
       if (elect_one()) {
-        const uint64_t ab = adesc0 + (uint64_t)(stage * (A_STAGE_BYTES / 16));
         const uint32_t d = tmem_base + (uint32_t)(acc * N_MMA);
+        if (p.debug & 4) {
+          // (experiment) no MMAs
+        } else if constexpr (STEM) {
+          const uint64_t wdesc0 = umma_desc(s_w, (uint32_t)W_N * 16u, 128u);
+          const uint64_t ab = umma_desc(s_a + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)halo * 16u, SLAB * 16u, 128u);
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint64_t at = ab + (uint64_t)dlt[tap];
-          const uint64_t bt = wdesc0 + (uint64_t)(tap * (W_TAP_BYTES / 16));
+          for (int tap = 0; tap < 9; ++tap)
+            umma_bf16(d, ab + (uint64_t)dlt[tap], wdesc0 + (uint64_t)(tap * (W_TAP_BYTES / 16)), idesc, tap != 0 ? 1u : 0u);
+        } else {
+          // SW128: every activation row is its own 128-byte line, so a tap shift of delta rows never straddles lines.
+          const uint32_t a_stage = s_a + (uint32_t)stage * A_STAGE_BYTES;
 #pragma unroll
-          for (int j = 0; j < K_STEPS; ++j)
-            umma_bf16(d, at + (uint64_t)(j * 2 * SLAB), bt + (uint64_t)(j * 2 * W_N), idesc, (tap | j) != 0 ? 1u : 0u);
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t at = umma_desc_sw128(a_stage + (uint32_t)(halo + (int)dlt[tap]) * 128u);
+            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)tap * 8192u);
+#pragma unroll
+            for (int j = 0; j < K_STEPS; ++j)
+              umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (tap | j) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(bar_empty(stage));  // smem stage reusable once these MMAs have read it
         umma_commit(bar_tfull(acc));    // accumulator ready for the epilogue
@@ -377,22 +408,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     const int col0 = half * 32;
     const bool has_res = !STEM && p.res != nullptr;
 
-    auto row_valid = [&](long long m) {
-      const long long qrow = m - range_lo;
-      bool v = qrow >= 0 && qrow < range_hi - range_lo;
-      if (v) {
-        const int pos = (int)(qrow % p.P);
-        v = pos < valid_pos && (pos % p.Wp) < p.W;
-      }
-      return v;
-    };
+    // Row validity without per-tile divisions: this thread's row advances by gridDim.x * 128 rows per tile, so its
+    // position inside the board advances by a constant (mod P).  32-bit arithmetic throughout.
+    const int range_len = (int)(range_hi - range_lo);
+    const int step_rows = (int)gridDim.x * TILE_M;
+    const int step_pos = step_rows % p.P;
+    int qrow_next = (int)((long long)(p.tile0 + (int)blockIdx.x) * TILE_M + q * 32 + lane - range_lo);  // may be < 0
+    int pos_next = ((qrow_next % p.P) + p.P) % p.P;
+    float bias_r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias_r[i] = s_bias[col0 + i];
     // residual rows of the NEXT tile are prefetched into registers while the current tile is processed
     uint4 rnext[4];
     uint32_t vmask_next = 0;
     auto prefetch = [&](int it) {
       const int tile = p.tile0 + (int)blockIdx.x + it * (int)gridDim.x;
       const long long m_warp = (long long)tile * TILE_M + q * 32;
-      vmask_next = __ballot_sync(0xffffffffu, row_valid(m_warp + lane));
+      const bool v = qrow_next >= 0 && qrow_next < range_len && pos_next < valid_pos && (pos_next % p.Wp) < p.W;
+      vmask_next = __ballot_sync(0xffffffffu, v);
+      qrow_next += step_rows;
+      pos_next += step_pos;
+      if (pos_next >= p.P) pos_next -= p.P;
       if (has_res) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.res + m_warp * CH + col0);
 #pragma unroll
@@ -433,12 +469,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty(acc));
+      if (p.debug & 2) continue;
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {  // 16 columns at a time
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          f[i] = __uint_as_float(v[cb * 16 + i]) + s_bias[col0 + cb * 16 + i];
+          f[i] = __uint_as_float(v[cb * 16 + i]) + bias_r[cb * 16 + i];
           if (p.lrelu) f[i] = lrelu(f[i]);
         }
         if (has_res) {
@@ -567,6 +604,14 @@ extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bia
   p.s2 = s2;
   p.t2 = t2;
   p.lrelu = lrelu;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("AZ_NN_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   if (fill_geometry(p, board0, boards, H, W, lead, rows_alloc, "az_nn_conv3x3")) return -1;
   return launch_conv<false>(p, n_ctas, stream);
 }

@@ -24,12 +24,16 @@ LEAD = 16
 
 
 def pack_conv3x3(w):
-    """[64 out][64 in][3][3] (any float dtype, already zero-padded) -> bf16 [9][8][64][8] UMMA operand image."""
+    """[64 out][64 in][3][3] (any float dtype, already zero-padded) -> bf16 [9][64 n][8 chunks][8] UMMA operand image
+    in the SWIZZLE_128B K-major layout: row n is 128 B, its 16-byte chunk c is stored at chunk position c ^ (n & 7)."""
     co, ci = w.shape[0], w.shape[1]
     assert co == CH and ci == CH
-    t = w.permute(2, 3, 1, 0).reshape(9, ci, co)          # [tap][k][n]
-    t = t.reshape(9, 8, 8, co).permute(0, 1, 3, 2)          # [tap][kc][n][k%8]
-    return t.contiguous().to(torch.bfloat16)
+    t = w.permute(2, 3, 0, 1).reshape(9, co, 8, 8)           # [tap][n][chunk][k%8]
+    n = torch.arange(co).view(1, co, 1)
+    c = torch.arange(8).view(1, 1, 8)
+    src_chunk = (c ^ (n & 7)).expand(9, co, 8)               # position p holds chunk p ^ (n & 7)
+    out = torch.gather(t, 2, src_chunk.unsqueeze(-1).expand(9, co, 8, 8).to(t.device))
+    return out.contiguous().to(torch.bfloat16)
 
 
 class FusedEvaluator:

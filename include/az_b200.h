@@ -225,8 +225,9 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  * pad rows/columns hold zeros; 50 filters are zero-padded to 64.  All pointers are device pointers.
  *
  * az_nn_conv3x3: out = conv3x3(in) + bias, optional LeakyReLU, optional + res; optional second output
- *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  wpack is [9 taps][8][64][8] bf16
- *   (tap = ky*3+kx, k-chunk, out-channel, in-channel%8).  tcgen05 implicit GEMM; n_ctas <= 0 -> one CTA per SM.
+ *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  wpack is [9 taps][64 n][8][8] bf16,
+ *   the SWIZZLE_128B K-major operand image (tap = ky*3+kx; 16-byte chunk c of row n stored at position c ^ (n & 7)).
+ *   tcgen05 implicit GEMM; n_ctas <= 0 -> one CTA per SM.
  * az_nn_stem: the 4-plane first block on the same tcgen05 kernel (the slab is built from the az_step
  *   AZ_OBS_BF16_NHWC batch [boards][H][W][4]): u = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1), r = conv1x1(x) + b3
  *   (network.py:99-103 for resblock1).  wpack is [9 taps][2][128][8] bf16: rows 0-63 = conv1 (BatchNorm folded) on
