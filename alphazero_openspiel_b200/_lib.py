@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(HERE, "libaz_b200.so")
 GAME_CONNECT_FOUR, GAME_BREAKTHROUGH = 0, 1
 F_KEEP_TREE, F_AUTO_RESTART, F_MANUAL, F_SAMPLE_MOVES = 1 << 0, 1 << 1, 1 << 2, 1 << 3
 F_RECORDS, F_OFFPOLICY, F_PRIORS_F64, F_RANDOM_START = 1 << 4, 1 << 5, 1 << 6, 1 << 7
+F_ASYNC_COMPACT = 1 << 8
 NOISE_NONE, NOISE_DIRICHLET, NOISE_HOST, NOISE_COUNTER = 0, 1, 2, 3
 EVAL_EXTERNAL, EVAL_UNIFORM, EVAL_HASH = 0, 1, 2
 OBS_NONE, OBS_F32_NCHW, OBS_BF16_NHWC = 0, 1, 2
@@ -58,6 +59,7 @@ SIGNATURES = {
     "az_set_positions": (C.c_int, [C.c_void_p, _I32P, _I32P, C.c_int32, _VP]),
     "az_command": (C.c_int, [C.c_void_p, _I32P, _I32P, _I32P, _VP]),
     "az_step": (C.c_int, [C.c_void_p, _VP, _VP, _F64P, _VP, C.c_int32, _VP]),
+    "az_compact": (C.c_int, [C.c_void_p, _VP]),
     "az_status": (C.c_int, [C.c_void_p, _I32P, _I32P, _I32P, _I32P, _VP]),
     "az_request_info": (C.c_int, [C.c_void_p, _U64P, _I32P, _I32P, _I32P, C.c_int32, _VP]),
     "az_root_stats": (C.c_int, [C.c_void_p, _I32P, _F64P, _I32P, _I32P, _I32P, _F64P, _F64P, _F64P, _F64P, _VP]),

@@ -41,6 +41,7 @@
 namespace az {
 
 constexpr int PH_BEGIN = 6;  // internal: a search must be started (root eval request or first simulation)
+constexpr int PH_COMPACT = 7;  // internal: waiting for k_compact to re-root (pend_node = the child to promote)
 constexpr int BLOCK = 128;
 
 struct __align__(16) TreeHdr {
@@ -69,6 +70,8 @@ struct Params {
   unsigned long long* rec_count;
   unsigned long long* ctr;
   int* games_started;
+  int* compact_list;   // trees waiting for re-root compaction (k_compact work list)
+  int* compact_count;  // [0] = entries, [1] = CTAs done
   long long rec_cap;
   int max_games;
   int rec_stride;
@@ -616,12 +619,14 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
   h.root_b1 = s2.b1;
   h.root_ply = s2.ply;
   if ((p.flags & AZ_F_KEEP_TREE) && nc > 0) {
-    unsigned long long copied = 0;
-    reroot_compact<GM, G>(p, h, tree, fc + k, lane, gm, copied);
-    if (lane == 0) ctr_add(s_ctr, AZ_CTR_COMPACT_NODES, copied);
-  } else {
-    fresh_tree<G>(p, h, tree, lane, gm);
+    // Re-rooting copies the kept subtree (hundreds of dependent loads): done by k_compact, off this kernel's critical
+    // path, so that one moving tree does not set the duration of the whole lock-step launch.
+    h.pend_node = fc + k;
+    h.phase = PH_COMPACT;
+    if (lane == 0) p.compact_list[atomicAdd(p.compact_count, 1)] = tree;
+    return;
   }
+  fresh_tree<G>(p, h, tree, lane, gm);
   h.phase = PH_BEGIN;
 }
 
@@ -806,6 +811,83 @@ __global__ void __launch_bounds__(BLOCK) k_step(const Params p, const StepIO io)
   if (threadIdx.x < AZ_CTR_COUNT && s_ctr[threadIdx.x]) atomicAdd(&p.ctr[threadIdx.x], s_ctr[threadIdx.x]);
 }
 
+// ---------------------------------------------------------------- re-root compaction, one CTA per moving tree
+// MCTS.update_root (mcts.py:192-203) for the trees queued by finish_move.  Runs on its own stream next to the evaluator.
+// Same BFS copy as reroot_compact (the new arena is its own queue) but 256 queue nodes per iteration: the copy is a chain
+// of dependent global loads, so its duration is the number of iterations, not the number of nodes.
+constexpr int COMPACT_BLOCK = 256;
+__global__ void __launch_bounds__(COMPACT_BLOCK) k_compact(const Params p) {
+  __shared__ int s_warp_sum[COMPACT_BLOCK / 32];
+  __shared__ unsigned long long s_copied;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_copied = 0ULL;
+  const int count = *p.compact_count;
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    const int tree = p.compact_list[i];
+    TreeHdr h = p.hdr[tree];
+    const Arena src = arena_of(p, tree, h.half);
+    const Arena dst = arena_of(p, tree, h.half ^ 1);
+    if (tid == 0) {
+      dst.NL[0] = src.NL[h.pend_node];
+      dst.Q[0] = src.Q[h.pend_node];
+      dst.P[0] = src.P[h.pend_node];
+    }
+    __syncthreads();
+    int head = 0, tail = 1;
+    while (head < tail) {
+      const int nb = min(COMPACT_BLOCK, tail - head);
+      const int idx = head + tid;
+      int mync = 0, oldfc = 0;
+      if (tid < nb) {
+        const uint2 nl = dst.NL[idx];
+        mync = (int)(nl.y & 0xffu);
+        oldfc = (int)(nl.y >> 8);
+      }
+      const int incl = gscan_incl<32>(0xffffffffu, mync, lane);
+      if (lane == 31) s_warp_sum[warp] = incl;
+      __syncthreads();
+      int off = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < COMPACT_BLOCK / 32; ++w) {
+        const int v = s_warp_sum[w];
+        if (w < warp) off += v;
+        total += v;
+      }
+      if (mync > 0) {
+        const int newfc = tail + off + incl - mync;
+        dst.NL[idx].y = ((unsigned)newfc << 8) | (unsigned)mync;
+        for (int j = 0; j < mync; ++j) {
+          dst.NL[newfc + j] = src.NL[oldfc + j];
+          dst.Q[newfc + j] = src.Q[oldfc + j];
+          dst.P[newfc + j] = src.P[oldfc + j];
+        }
+      }
+      __syncthreads();
+      tail += total;
+      head += nb;
+    }
+    if (tid == 0) {
+      h.half ^= 1;
+      h.root_node = 0;
+      h.alloc = tail;
+      h.phase = PH_BEGIN;
+      p.hdr[tree] = h;
+      s_copied += (unsigned long long)tail;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (s_copied) atomicAdd(&p.ctr[AZ_CTR_COMPACT_NODES], s_copied);
+    __threadfence();
+    const int done = atomicAdd(p.compact_count + 1, 1);
+    if (done == (int)gridDim.x - 1) {  // last CTA: reset the work list for the next k_step
+      p.compact_count[0] = 0;
+      p.compact_count[1] = 0;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- control kernels
 template <class GM>
 __global__ void k_reset(const Params p) {
@@ -910,7 +992,7 @@ __global__ void k_status(const Params p, int32_t* phase, int32_t* sims, int32_t*
   const int tree = blockIdx.x * blockDim.x + threadIdx.x;
   if (tree >= p.n_trees) return;
   const TreeHdr h = p.hdr[tree];
-  if (phase) phase[tree] = h.phase == PH_BEGIN ? AZ_PH_RUN : h.phase;
+  if (phase) phase[tree] = (h.phase == PH_BEGIN || h.phase == PH_COMPACT) ? AZ_PH_RUN : h.phase;
   if (sims) sims[tree] = h.sims_done;
   if (ply) ply[tree] = h.root_ply;
   if (req_legal) {
@@ -1155,6 +1237,10 @@ static int dispatch_game(int game_id, F&& f) {
   return f(BT());
 }
 
+static inline int compact_grid(int n_trees) {  // one CTA per moving tree; ~n_trees * e / n_playouts trees move per step
+  int grid = n_trees / 128 + 4;
+  return grid > 296 ? 296 : grid;
+}
 static inline int groups_grid(int n_trees, int G, int block) { return (int)(((long long)n_trees * G + block - 1) / block); }
 
 extern "C" {
@@ -1242,6 +1328,8 @@ int az_create(const az_config* cfg_in, az_engine** out) {
       (err = alloc((void**)&p.rec_count, sizeof(unsigned long long))) != cudaSuccess ||
       (err = alloc((void**)&p.ctr, sizeof(unsigned long long) * AZ_CTR_COUNT)) != cudaSuccess ||
       (err = alloc((void**)&p.games_started, sizeof(int))) != cudaSuccess ||
+      (err = alloc((void**)&p.compact_list, sizeof(int) * (size_t)cfg.n_trees)) != cudaSuccess ||
+      (err = alloc((void**)&p.compact_count, sizeof(int) * 2)) != cudaSuccess ||
       (err = alloc((void**)&e->d_cmd, sizeof(int32_t) * ((size_t)cfg.n_trees * 3))) != cudaSuccess ||
       (err = alloc((void**)&e->d_bad, sizeof(int32_t))) != cudaSuccess) {
     fail(-2, "cudaMalloc failed (%zu bytes requested so far): %s", bytes, cudaGetErrorString(err));
@@ -1252,6 +1340,7 @@ int az_create(const az_config* cfg_in, az_engine** out) {
   CK(cudaMemset(p.rec_count, 0, sizeof(unsigned long long)));
   CK(cudaMemset(p.ctr, 0, sizeof(unsigned long long) * AZ_CTR_COUNT));
   CK(cudaMemset(e->d_bad, 0, sizeof(int32_t)));
+  CK(cudaMemset(p.compact_count, 0, sizeof(int) * 2));
   *out = e;
   int rc = az_reset(e, nullptr);
   if (rc) return rc;
@@ -1271,6 +1360,8 @@ int az_destroy(az_engine* e) {
   cudaFree(p.rec_count);
   cudaFree(p.ctr);
   cudaFree(p.games_started);
+  cudaFree(p.compact_list);
+  cudaFree(p.compact_count);
   cudaFree(e->d_cmd);
   cudaFree(e->d_bad);
   delete e;
@@ -1292,6 +1383,7 @@ int az_reset(az_engine* e, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const Params p = e->p;
   CK(cudaMemcpyAsync(p.games_started, &e->cfg.n_trees, sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(p.compact_count, 0, sizeof(int) * 2, st));
   dispatch_game(e->cfg.game_id, [&](auto gm) {
     using GM = decltype(gm);
     k_reset<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p);
@@ -1368,11 +1460,23 @@ int az_step(az_engine* e, const void* priors_dev, const void* values_dev, const 
   io.obs = obs_dev;
   io.obs_format = obs_format;
   if (p.noise_mode == AZ_NOISE_HOST && !noise_dev) return fail(-1, "AZ_NOISE_HOST needs noise_dev");
+  if ((p.flags & AZ_F_KEEP_TREE) && !(p.flags & AZ_F_MANUAL) && !(p.flags & AZ_F_ASYNC_COMPACT)) {
+    k_compact<<<compact_grid(p.n_trees), 256, 0, st>>>(p);  // re-root the trees that moved in the previous step
+    CK(cudaGetLastError());
+  }
   dispatch_game(e->cfg.game_id, [&](auto gm) {
     using GM = decltype(gm);
     k_step<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
     return 0;
   });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int az_compact(az_engine* e, void* stream) {
+  if (!e) return fail(-1, "null engine");
+  const Params p = e->p;
+  k_compact<<<compact_grid(p.n_trees), 256, 0, (cudaStream_t)stream>>>(p);
   CK(cudaGetLastError());
   return 0;
 }

@@ -130,6 +130,11 @@ class Engine:
         L.check(self.lib.az_step(self.h, _ptr(priors), _ptr(values), _ptr(noise), _ptr(obs), obs_format,
                                  self._stream()))
 
+    def compact(self, stream=None):
+        """Re-root compaction of the trees that just moved (only needed with F_ASYNC_COMPACT)."""
+        st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)
+        L.check(self.lib.az_compact(self.h, st))
+
     def set_positions(self, histories):
         """histories: list (len n_trees) of action lists, or None entries to leave a tree untouched."""
         n = self.n_trees

@@ -127,7 +127,7 @@ class SelfPlayRunner:
         self.device = torch.device("cuda", dev_index)
         flags = L.F_SAMPLE_MOVES
         if keep_search_tree:
-            flags |= L.F_KEEP_TREE
+            flags |= L.F_KEEP_TREE | L.F_ASYNC_COMPACT   # re-root compaction on a side stream, next to the evaluator
         if auto_restart:
             flags |= L.F_AUTO_RESTART
         if records:
@@ -159,6 +159,10 @@ class SelfPlayRunner:
         self._graph = None
         self._first = True
         self.rounds = 0
+        self._async_compact = bool(keep_search_tree)
+        self._side = torch.cuda.Stream(self.device) if self._async_compact else None
+        self._ev_fork = torch.cuda.Event()
+        self._ev_join = torch.cuda.Event()
 
     def load_weights(self, net):
         """New generation's weights (host or device Net) into the captured evaluator, in place."""
@@ -168,7 +172,17 @@ class SelfPlayRunner:
     def _round_eager(self):
         ev = self.evaluator
         self.engine.step(ev.priors, ev.values, None, ev.obs, L.OBS_BF16_NHWC)
-        ev()
+        if self._async_compact:
+            # fork: k_compact (re-rooting of the trees that just moved) runs next to the evaluator, join before next step
+            main = torch.cuda.current_stream(self.device)
+            self._ev_fork.record(main)
+            self._side.wait_event(self._ev_fork)
+            self.engine.compact(self._side)
+            self._ev_join.record(self._side)
+            ev()
+            main.wait_event(self._ev_join)
+        else:
+            ev()
 
     @torch.no_grad()
     def round(self, n=1):
@@ -177,6 +191,8 @@ class SelfPlayRunner:
             if self._first:
                 # first call: no evaluator outputs yet -- produce the initial requests, then evaluate them
                 self.engine.step(None, None, None, self.evaluator.obs, L.OBS_BF16_NHWC)
+                if self._async_compact:
+                    self.engine.compact()
                 self.evaluator()
                 self._first = False
             if self.use_graph and self._graph is None:

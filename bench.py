@@ -178,7 +178,8 @@ def run_ours(args):
     runner = SelfPlayRunner(net, game, dev, args.trees, n_playouts=args.playouts, c_puct=2.5, use_dirichlet=True,
                             dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", seed=0xC4 + rank,
                             auto_restart=True, random_start_mod=21, max_sims_per_step=args.sim_cap, records=True,
-                            use_graph=not args.no_graph, evaluator=args.evaluator, nn_slice=args.nn_slice)
+                            use_graph=not args.no_graph, evaluator=args.evaluator, nn_slice=args.nn_slice,
+                            keep_search_tree=not args.no_keep_tree)
     # ---- warm-up (untimed): builds the first searches so trees are in steady state
     runner.round(args.warmup)
     runner.drain()
@@ -236,6 +237,8 @@ def run_ours(args):
         a[0].record()
         runner.engine.step(ev.priors, ev.values, None, ev.obs, L.OBS_BF16_NHWC)
         a[1].record()
+        if runner._async_compact:
+            runner.engine.compact()
         ev()
         b.record()
     torch.cuda.synchronize(dev)
@@ -314,7 +317,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=1200)
+    ap.add_argument("--warmup", type=int, default=1500)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--game", default="connect_four")
     ap.add_argument("--trees", type=int, default=16384)
@@ -326,6 +329,7 @@ def main():
     ap.add_argument("--ref-repeat", action="store_true")
     ap.add_argument("--evaluator", default="fused", choices=["fused", "torch"])
     ap.add_argument("--nn-slice", type=int, default=0)
+    ap.add_argument("--no-keep-tree", action="store_true", help="experiment: fresh tree every move (no re-root compaction)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -57,6 +57,7 @@ extern "C" {
 #define AZ_F_OFFPOLICY      (1u << 5) /* also compute the A0GB off-policy target per ply (game_utils.py:182-194) */
 #define AZ_F_PRIORS_F64     (1u << 6) /* az_step priors/values are double (generic policy_fn), else float (Net outputs) */
 #define AZ_F_RANDOM_START   (1u << 7) /* (re)started games begin after counter%start_plies_mod random plies (bench synthetic positions) */
+#define AZ_F_ASYNC_COMPACT  (1u << 8) /* the caller runs az_compact() itself (e.g. on a side stream next to the evaluator) */
 
 /* root noise (mcts.py:182-190) */
 #define AZ_NOISE_NONE      0 /* use_dirichlet=False */
@@ -174,6 +175,12 @@ int az_command(az_engine* e, const int32_t* update_root_host, const int32_t* res
  * eval_batch(obs) -> (priors, values). */
 int az_step(az_engine* e, const void* priors_dev, const void* values_dev, const double* noise_dev,
             void* obs_dev, int32_t obs_format, void* stream);
+
+/* Re-root compaction (MCTS.update_root, mcts.py:192-203) of the trees that played a move in the last az_step: BFS-copies
+ * the kept subtree into the other arena half, one warp per tree.  az_step runs it first by itself unless
+ * AZ_F_ASYNC_COMPACT is set; then the caller must call it once between two az_step calls, on any stream ordered after
+ * the first and before the second (typically a side stream, overlapping the evaluator). */
+int az_compact(az_engine* e, void* stream);
 
 /* Per-tree status into device arrays (any may be NULL): phase (AZ_PH_*), sims done in the current search,
  * ply of the root position, legal-move count of the pending request's position. */
