@@ -60,6 +60,7 @@ class FusedEvaluator:
         self.priors = torch.zeros((batch, self.A), dtype=torch.float32, device=dev)
         self.values = torch.zeros((batch,), dtype=torch.float32, device=dev)
         self.par = None
+        self.timing = None   # set to a list to collect (kernel, start_event, end_event) per launch (bench.py roofline)
         self.load(net)
 
     @torch.no_grad()
@@ -121,10 +122,22 @@ class FusedEvaluator:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _timed(self, name, fn):
+        if self.timing is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn()
+        e1.record()
+        self.timing.append((name, e0, e1))
+        return rc
+
     def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, b0, nb):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
-        rc = self.lib.az_nn_conv3x3(p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), b0, nb, self.h,
-                                    self.w, LEAD, self.rows_alloc, 1 if lrelu else 0, self.n_ctas, self._stream())
+        name = "conv" + ("+res" if res is not None else "") + ("+out2" if out2 is not None else "")
+        rc = self._timed(name, lambda: self.lib.az_nn_conv3x3(
+            p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), b0, nb, self.h, self.w, LEAD, self.rows_alloc,
+            1 if lrelu else 0, self.n_ctas, self._stream()))
         if rc:
             raise RuntimeError("az_nn_conv3x3: " + self.lib.az_nn_last_error().decode())
 
@@ -134,9 +147,9 @@ class FusedEvaluator:
         P_ = self.par
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         for b0, nb in self.slices:
-            rc = self.lib.az_nn_stem(p(self.obs), p(P_["stem_w"]), p(P_["b1_0"]), p(P_["stem_b3"]), p(P_["stem_st"]),
-                                     p(self.U), p(self.X), b0, nb, self.h, self.w, LEAD, self.rows_alloc, self.n_ctas,
-                                     self._stream())
+            rc = self._timed("stem", lambda: self.lib.az_nn_stem(
+                p(self.obs), p(P_["stem_w"]), p(P_["b1_0"]), p(P_["stem_b3"]), p(P_["stem_st"]), p(self.U), p(self.X),
+                b0, nb, self.h, self.w, LEAD, self.rows_alloc, self.n_ctas, self._stream()))
             if rc:
                 raise RuntimeError("az_nn_stem: " + self.lib.az_nn_last_error().decode())
             # block 1, second conv: X = conv(U) + X ; T = lrelu(bn1_2(X))

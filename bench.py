@@ -133,7 +133,8 @@ def run_reference(args):
     v = sum(vals) / len(vals)
     base["value"] = v
     line = {"metric": "mcts_simulations_per_sec", "value": v, "unit": "sims/s", "impl": "reference",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(base["sample"].split(" sims in ")[1].split(" s")[0]) / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": workload_name(args), "trees_per_gpu": args.trees,
                                             "n_playouts": args.playouts, "game": game},
@@ -227,26 +228,39 @@ def run_ours(args):
     d2h = recs.nbytes + 8 * len(L.CTR_NAMES)
     e2e_sims = e1["sims"] - e0["sims"]
 
-    # ---- per-launch duration of the hand-written kernel (k_step), live, CUDA events around each az_step
+    # ---- per-launch durations of the hand-written kernels, live, CUDA events around each launch (un-graphed pass)
     n_probe = min(args.steps, 200)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
-    nn_evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_probe)]
+    nn_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
     p0 = runner.counters()
     ev = runner.evaluator
+    fused = hasattr(ev, "timing")
+    if fused:
+        ev.timing = []
     for a, b in zip(evs, nn_evs):
         a[0].record()
         runner.engine.step(ev.priors, ev.values, None, ev.obs, L.OBS_BF16_NHWC)
         a[1].record()
         if runner._async_compact:
             runner.engine.compact()
+        b[0].record()
         ev()
-        b.record()
+        b[1].record()
     torch.cuda.synchronize(dev)
     p1 = runner.counters()
     pd = {k: p1[k] - p0[k] for k in p1}
     step_ms = sum(a.elapsed_time(b) for a, b in evs) / n_probe
-    nn_ms = sum(a[1].elapsed_time(b) for a, b in zip(evs, nn_evs)) / n_probe
+    nn_ms = sum(a.elapsed_time(b) for a, b in nn_evs) / n_probe
     alg_bytes_per_launch = algorithmic_bytes(pd, rows * cols, n_actions) / n_probe
+    conv_ms, conv_n, stem_ms = 0.0, 0, 0.0
+    if fused:
+        for name, e0, e1 in ev.timing:
+            if name == "stem":
+                stem_ms += e0.elapsed_time(e1)
+            else:
+                conv_ms += e0.elapsed_time(e1)
+                conv_n += 1
+        ev.timing = None
 
     # ---- reduce over ranks
     stats = torch.tensor([ms, float(d["sims"]), float(d["moves"]), float(d["games"]), float(d["overflow"]),
@@ -272,6 +286,25 @@ def run_ours(args):
     flops = FLOPS_PER_EVAL.get(game, 0)
     hbm_ach = alg_bytes_per_launch / (step_ms / 1e3) / 1e9
     nn_tflops = args.trees * flops / (nn_ms / 1e3) / 1e12
+    tree_roofline = {"kernel": "k_step (select/expand/backup/advance/encode)", "bound": "hbm",
+                     "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+                     "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": step_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                     "share_of_step": step_ms / (step_ms + nn_ms)}
+    conv_roofline = None
+    if fused and conv_n:
+        # dominant kernel: k_conv<false> (3x3 conv, 50->50 filters).  Algorithmic FLOPs per launch = boards x 2*HW*50*50*9.
+        conv_flops = args.trees * 2.0 * rows * cols * 50 * 50 * 9
+        avg_conv_ms = conv_ms / conv_n
+        ach = conv_flops / (avg_conv_ms / 1e3) / 1e12
+        conv_roofline = {"kernel": "k_conv<false> (tcgen05 implicit-GEMM 3x3 conv + fused BN/LeakyReLU/residual epilogue)",
+                         "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": ach / peaks["bf16_tflops"], "traffic": 134.4e6, "peak_source": peaks["source"] + " (burst)",
+                         "avg_launch_ms": avg_conv_ms, "launches_per_step": conv_n / n_probe,
+                         "algorithmic_flops_per_launch": conv_flops, "stem_avg_launch_ms": stem_ms / n_probe,
+                         "share_of_step": conv_ms / n_probe / (step_ms + nn_ms),
+                         "note": "measured limiter is shared-memory bandwidth (SS-mode operand fetch at N=64), see DESIGN.md; "
+                                 "traffic = dram read+write of a conv1-type launch from profiles/r01_conv_full_raw.csv"}
     line = {
         "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -290,13 +323,11 @@ def run_ours(args):
         "e2e": {"value": e2e_sims / t_e2e, "unit": "sims/s", "h2d_bytes_per_step": h2d / args.steps,
                 "d2h_bytes_per_step": d2h / args.steps,
                 "what": "SelfPlayRunner.load_weights(host net) + round(K) + drain()/counters() to host, wall clock"},
-        "gpu_launches": args.steps * world,
-        "roofline": {"kernel": "k_step (select/expand/backup/advance/encode)", "bound": "hbm",
-                     "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
-                     "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": step_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                     "share_of_step": step_ms / (step_ms + nn_ms)},
-        "nn_roofline": {"kernel": "ResNet forward (%s)" % args.evaluator, "bound": "tensor",
+        # our kernels per round trip: k_step, k_compact, stem + 9 convs (the FC head / softmax / tanh are library calls)
+        "gpu_launches": args.steps * world * ((2 if not args.no_keep_tree else 1) + (10 if fused else 0)),
+        "roofline": conv_roofline if fused else tree_roofline,
+        "tree_roofline": tree_roofline,
+        "nn_roofline": {"kernel": "ResNet forward (%s): stem + 9 convs + FC head" % args.evaluator, "bound": "tensor",
                         "achieved": nn_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                         "frac": nn_tflops / peaks["bf16_tflops_sustained"], "avg_forward_ms": nn_ms,
                         "flops_per_eval": flops, "peak_source": peaks["source"]},
