@@ -116,3 +116,43 @@ def test_no_dirichlet_argmax_and_sim_cap():
             for r, g in zip(ref, plies):
                 assert list(g["counts"][:r["n_legal"]]) == r["counts"] and g["action"] == r["action"]
                 assert g["root_q"] == r["root_q"]
+
+
+def test_full_size_pool_matches_oracle_on_sampled_trees():
+    """BASELINE config 3 size (16,384 trees x 800 sims/move, tree reuse, random synthetic starts): trees are independent, so
+    a sample of them must still equal the oracle ply by ply, and every recorded search must satisfy the size-independent
+    invariants (visit counts sum to the root's visits gained, legal counts, arena never overflows)."""
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    game, n_trees, n_playouts, seed = "connect_four", 16384, 800, 0xC4
+    flags = L.F_RECORDS | L.F_KEEP_TREE | L.F_SAMPLE_MOVES | L.F_RANDOM_START | L.F_AUTO_RESTART
+    eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=L.NOISE_COUNTER, eval_mode=L.EVAL_HASH, flags=flags,
+                   seed=seed, start_plies_mod=21, max_sims_per_step=16)
+    for _ in range(2600):  # ~4 moves per tree
+        eng.step()
+    recs = eng.drain_records()
+    ctr = eng.counters()
+    eng.close()
+    assert ctr["overflow"] == 0 and ctr["moves"] > 3 * n_trees
+    plies = recs[recs["kind"] == 0]
+    assert len(plies) == ctr["moves"]
+    # invariants over ALL records: a search adds exactly n_playouts visits below the root
+    # (first search of a game: children sum == n_playouts; with reuse the root keeps inherited visits)
+    csum = plies["counts"].sum(axis=1)
+    # every playout of a Dirichlet-expanded root visits a child; a re-rooted node additionally carries the one visit
+    # in which it was itself the expanded leaf (mcts.py:145-152)
+    assert np.all((csum == plies["root_n"]) | (csum == plies["root_n"] - 1))
+    assert np.all(plies["root_n"] >= n_playouts)
+    assert np.all(plies["n_legal"] >= 1) and np.all(plies["n_legal"] <= 7)
+    assert np.all(np.abs(plies["root_q"]) <= 1.0)
+    cfg = ou.selfplay_cfg(game, n_playouts, use_dirichlet=2, sample_moves=1, keep_tree=1, seed=seed, start_mod=21, max_plies=3)
+    checked = 0
+    for t in list(range(0, 8)) + [4095, 8191, 16383]:
+        mine = plies[(plies["tree"] == t) & (plies["game_seq"] == 0)]
+        mine = mine[np.argsort(mine["ply"])]
+        ref, _, _ = ou.selfplay_game(cfg, t)
+        assert len(mine) >= min(len(ref), 3)
+        for r, g in zip(ref, mine):
+            assert g["ply"] == r["ply"] and list(g["counts"][:r["n_legal"]]) == r["counts"] and g["action"] == r["action"]
+            assert g["root_q"] == r["root_q"] and (int(g["bb"][0]), int(g["bb"][1])) == r["bb"]
+            checked += 1
+    assert checked >= 25
