@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // Programmatic dependent launch: let the next layer's CTAs start their own prologue as soon as SMs free up ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int halo = p.Wp + 1;
   const int slab_rows = TILE_M + 2 * halo;
@@ -247,6 +249,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     // slab, wait for ITS OWN copies only, make them visible to the tensor core's async proxy, signal `full`.
     // Four such warps keep four slabs in flight without any cross-tile dependency between load issue and hand-off.
     const int stage = warp;
+    // ... and do not touch the previous layer's output before that layer has completely finished.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int it = stage, round = 0; it < my_tiles; it += STAGES, ++round) {
       mbar_wait(bar_empty(stage), ((uint32_t)round & 1u) ^ 1u);
       const int tile = p.tile0 + (int)blockIdx.x + it * (int)gridDim.x;
@@ -436,6 +440,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
           rnext[i] = ((vmask_next >> (i * 8 + crow)) & 1u) ? rp[(i * 8 + crow) * 8 + cch] : make_uint4(0u, 0u, 0u, 0u);
       }
     };
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // residual reads / output writes depend on the previous layer
     if (my_tiles > 0) prefetch(0);
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -579,8 +584,25 @@ static int launch_conv(const aznn::ConvParams& p, int n_ctas, void* stream) {
   }
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  k_conv<STEM><<<grid, NUM_THREADS, SmemLayout::TOTAL, (cudaStream_t)stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* ev = getenv("AZ_NN_PDL");
+    use_pdl = ev ? atoi(ev) : 1;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SmemLayout::TOTAL;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<STEM>, p);
+  if (e != cudaSuccess) return nn_fail(-2, "k_conv launch", e);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_conv launch", e);
   return 0;
 }

@@ -71,6 +71,30 @@ def policy_target(counts, actions, n_legal, num_actions):
     return out
 
 
+def policy_targets_batch(counts, actions, n_legal, num_actions):
+    """Vectorised policy_target for many records: float64 [n, num_actions], bit-identical to the per-record expressions
+    (IEEE division is elementwise; the row sums run over the same contiguous vectors as np.sum on one record)."""
+    n = counts.shape[0]
+    maxc = counts.shape[1]
+    valid = np.arange(maxc)[None, :] < n_legal[:, None]
+    rows = np.repeat(np.arange(n), maxc).reshape(n, maxc)[valid]
+    cols = actions.astype(np.int64)[valid]
+    visits = np.zeros((n, num_actions), dtype=np.float64)
+    visits[rows, cols] = counts[valid]
+    total = counts.astype(np.int64).sum(axis=1).astype(np.float64) * valid.any(axis=1)
+    probs = visits / total[:, None]                      # float(v) / sum(visits)               mcts.py:161-162
+    s = np.array([np.sum(probs[i]) for i in range(n)]) if num_actions >= 8 else probs.sum(axis=1)
+    ok = s > 1e-6                                        # remove_illegal_actions               alphazerobot.py:12-17
+    out = np.zeros_like(probs)
+    out[ok] = probs[ok] / s[ok][:, None]
+    if not ok.all():
+        legal_mask = np.zeros((n, num_actions), dtype=bool)
+        legal_mask[rows, cols] = True
+        uni = legal_mask / np.maximum(n_legal, 1)[:, None].astype(np.float64)
+        out[~ok] = uni[~ok]
+    return out
+
+
 def records_to_games(records, game_name, backup="on-policy"):
     """Device training records -> list of games in the reference's example format (game_utils.py:168-204).
     Only games that have their closing (kind 1) record are returned."""
@@ -81,6 +105,10 @@ def records_to_games(records, game_name, backup="on-policy"):
     order = np.lexsort((records["kind"], records["ply"], records["game_seq"], records["tree"]))
     recs = records[order]
     boards = boards_from_bitboards(gid, rows, cols, recs["bb"], recs["ply"])
+    ply_mask = recs["kind"] == 0
+    pol_rows = np.full((len(recs),), -1, dtype=np.int64)
+    pol_rows[ply_mask] = np.arange(int(ply_mask.sum()))
+    pols = policy_targets_batch(recs["counts"][ply_mask], recs["actions"][ply_mask], recs["n_legal"][ply_mask], num_actions)
     key = recs["tree"].astype(np.int64) * (1 << 32) + recs["game_seq"].astype(np.int64)
     starts = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
     ends = np.r_[starts[1:], len(recs)]
@@ -92,7 +120,7 @@ def records_to_games(records, game_name, backup="on-policy"):
         game = []
         for i in range(s, e - 1):
             r = recs[i]
-            pol = policy_target(r["counts"], r["actions"], int(r["n_legal"]), num_actions)
+            pol = pols[pol_rows[i]].tolist()
             if backup == "soft-Z":
                 value = -float(r["root_q"])
             elif backup == "A0C":
@@ -118,7 +146,7 @@ class SelfPlayRunner:
     def __init__(self, net, game_name, device, n_trees, n_playouts=100, c_puct=2.5, use_dirichlet=True,
                  dirichlet_ratio=0.25, temperature=1.0, num_probabilistic_actions=1000, keep_search_tree=True,
                  backup="on-policy", seed=0, max_games=0, auto_restart=True, random_start_mod=0,
-                 max_sims_per_step=16, records=True, use_graph=True, noise_mode=None, node_capacity=0,
+                 max_sims_per_step=8, records=True, use_graph=True, noise_mode=None, node_capacity=0,
                  record_capacity=0, evaluator="fused", nn_slice=0, **_ignored):
         self.device = torch.device(device)
         if self.device.type != "cuda":

@@ -353,7 +353,7 @@ def main():
     ap.add_argument("--game", default="connect_four")
     ap.add_argument("--trees", type=int, default=16384)
     ap.add_argument("--playouts", type=int, default=800)
-    ap.add_argument("--sim-cap", type=int, default=16)
+    ap.add_argument("--sim-cap", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)

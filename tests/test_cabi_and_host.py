@@ -103,6 +103,20 @@ def test_remove_illegal_actions_and_policy_target_follow_the_reference_expressio
             assert np.array_equal(want, got)
             pol = policy_target(counts, np.array(legal), L_, A)
             assert pol == [want[a] if a in legal else 0.0 for a in range(A)]
+    # the vectorised batch version used by records_to_games is bit-identical to the per-record expressions
+    from alphazero_openspiel_b200.examplegenerator import policy_targets_batch
+    for A, maxc in [(7, 7), (432, 48), (768, 48)]:
+        n = 64
+        n_legal = rng.randint(1, min(maxc, A) + 1, size=n)
+        counts = np.zeros((n, maxc), dtype=np.int32)
+        actions = np.full((n, maxc), -1, dtype=np.int16)
+        for i in range(n):
+            actions[i, :n_legal[i]] = sorted(rng.choice(A, size=n_legal[i], replace=False).tolist())
+            counts[i, :n_legal[i]] = rng.randint(0, 900, size=n_legal[i])
+            counts[i, rng.randint(n_legal[i])] += 1
+        batch = policy_targets_batch(counts, actions, n_legal, A)
+        for i in range(n):
+            assert batch[i].tolist() == policy_target(counts[i], actions[i], int(n_legal[i]), A)
     # all-zero mass -> uniform over legal (alphazerobot.py:15-17)
     z = remove_illegal_actions(np.zeros(7), [1, 3])
     assert z.tolist() == [0, 0.5, 0, 0.5, 0, 0, 0]
