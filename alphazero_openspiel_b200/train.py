@@ -1,0 +1,179 @@
+"""Drop-in for the caller of the self-play path: the reference's Trainer (train.py:21-298) -- SURVEY 8(f) rank 1.
+
+Same hyper-parameter attributes and method names (generate_examples / train_network / net_step / remove_duplicates /
+update_buffer_size / run).  Self-play generation goes through the GPU ExampleGenerator; the optimisation step is plain
+PyTorch (MSE value loss + cross-entropy against the visit-count targets, Adam lr 1e-3, weight decay 1e-4, train.py:85-128).
+With torch.distributed initialised (one process per GPU): every rank plays its share of the games, the records are
+all-gathered, rank 0 trains and the new weights are broadcast over NCCL (parallel.broadcast_weights) -- the reference
+"broadcasts" by pickling a deepcopy of the net into every handler process (examplegenerator.py:121).
+Strength evaluation (test_agent, train.py:238-270) is the match-up harness, out of scope.
+"""
+import logging
+import time
+from datetime import datetime
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import parallel
+from .engine import game_shape
+from .examplegenerator import ExampleGenerator
+from .network import Net
+
+logger = logging.getLogger("alphazero")
+
+
+class Trainer:
+    def __init__(self, name="openspieltest", backup="on-policy", name_game="connect_four", device=None, **overrides):
+        # Experiment parameters (train.py:24-33)
+        self.name_game = name_game
+        self.name_run = name
+        self.model_path = "models/"
+        self.save = False
+        self.save_n_gens = 10
+        self.test_n_gens = 10
+        self.n_tests = 200
+        self.use_gpu = True
+        self.n_pools = 1
+        self.n_processes = 1
+        # Algorithm parameters (train.py:35-49)
+        self.n_games_per_generation = 500
+        self.n_batches_per_generation = 500
+        self.n_games_buffer_max = 20000
+        self.batch_size = 256
+        self.lr = 0.001
+        self.n_games_buffer = 4 * self.n_games_per_generation
+        self.temperature = 1.0
+        self.dirichlet_ratio = 0.25
+        self.uct_train = 2.5
+        self.uct_test = 2.5
+        self.n_playouts_train = 100
+        self.backup = backup
+        self.tree_strap = False
+        self.it = 0
+        self.n_generations = 201
+        for k, v in overrides.items():
+            if not hasattr(self, k):
+                raise TypeError("unknown Trainer setting %r" % k)
+            setattr(self, k, v)
+        if "n_games_buffer" not in overrides:
+            self.n_games_buffer = 4 * self.n_games_per_generation
+
+        self.generation = 0
+        self.buffer = []
+        self.state_shape, self.num_distinct_actions = game_shape(self.name_game)
+        self.games_played = 0
+        self.start_time = datetime.now().strftime("%Y-%m-%d-%H-%M-%S")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if (self.use_gpu and torch.cuda.is_available()) \
+                else torch.device("cpu")
+        self.device = torch.device(device)
+        self.current_net = Net(self.state_shape, self.num_distinct_actions, device=self.device)
+        self.current_net.to(self.device)
+        parallel.broadcast_weights(self.current_net, src=0, device=self.device)  # identical initial weights on every rank
+        self.optimizer = torch.optim.Adam(self.current_net.parameters(), lr=self.lr, weight_decay=0.0001)
+        self.criterion_value = nn.MSELoss()
+        self.current_net.eval()
+        self.last_generation_stats = {}
+
+    # ------------------------------------------------------------------ optimisation (train.py:95-154)
+    def net_step(self, flattened_buffer):
+        self.current_net.zero_grad()
+        sample_ids = np.random.randint(len(flattened_buffer), size=self.batch_size)
+        boards = [flattened_buffer[i][1] for i in sample_ids]
+        pol = [flattened_buffer[i][2] for i in sample_ids]
+        val = [flattened_buffer[i][3] for i in sample_ids]
+        x = torch.from_numpy(np.array(boards)).float().to(self.device)
+        p_t, v_t = self.current_net(x)
+        pol = [item if item else p_t[i, :].to("cpu").tolist() for i, item in enumerate(pol)]
+        p_r = torch.tensor(np.array(pol)).float().to(self.device)
+        v_r = torch.tensor(np.array(val)).float().to(self.device)
+        loss_v = self.criterion_value(v_t, v_r.unsqueeze(1))
+        loss_p = -torch.sum(p_r * torch.log(p_t)) / p_r.size()[0]
+        (loss_v + loss_p).backward()
+        self.optimizer.step()
+        self.it += 1
+        return loss_p, loss_v
+
+    def train_network(self):
+        rank, world = parallel.rank_world()
+        losses = []
+        if rank == 0:
+            self.current_net.train()
+            flat = self.remove_duplicates([sample for game in self.buffer for sample in game])
+            run_p = run_v = 0
+            for i in range(self.n_batches_per_generation):
+                loss_p, loss_v = self.net_step(flat)
+                run_p += loss_p
+                run_v += loss_v
+                if i % 100 == 99:
+                    logger.info("Batch: " + str(i) + "Loss policy: " + str(run_p / 100.) + "Loss value: " + str(run_v / 100.))
+                    losses.append((float(run_p) / 100., float(run_v) / 100.))
+                    run_p = run_v = 0
+            self.current_net.eval()
+        if world > 1:
+            parallel.broadcast_weights(self.current_net, src=0, device=self.device)
+        return losses
+
+    @staticmethod
+    def remove_duplicates(flattened_buffer):
+        """Merge examples with the same information-state key: policies and values are averaged (train.py:156-201).
+        Like the reference, the FIRST example of a key is the accumulator object and is mutated in place."""
+        start = time.time()
+        merged, n_val, n_pol = {}, {}, {}
+        for item in flattened_buffer:
+            key = item[0]
+            acc = merged.get(key)
+            if acc is None:
+                merged[key], n_val[key], n_pol[key] = item, 1, 1
+                continue
+            if item[2] and acc[2]:
+                acc[2] = [sum(pair) for pair in zip(acc[2], item[2])]
+                n_pol[key] += 1
+            elif item[2]:
+                acc[2] = item[2]
+            acc[3] += item[3]
+            n_val[key] += 1
+        for key, acc in merged.items():
+            if acc[2]:
+                acc[2] = [x / n_pol[key] for x in acc[2]]
+            acc[3] = acc[3] / n_val[key]
+        out = list(merged.values())
+        logger.info("Removing duplicates: %d -> %d samples in %.2f s" % (len(flattened_buffer), len(out), time.time() - start))
+        return out
+
+    # ------------------------------------------------------------------ generation (train.py:203-236)
+    def generate_examples(self, n_games, **engine_kwargs):
+        start = time.time()
+        generator = ExampleGenerator(self.current_net, self.name_game, self.device,
+                                     n_playouts=self.n_playouts_train, temperature=self.temperature,
+                                     dirichlet_ratio=self.dirichlet_ratio, c_puct=self.uct_train, backup=self.backup,
+                                     tree_strap=self.tree_strap, n_pools=self.n_pools, n_processes=self.n_processes,
+                                     **engine_kwargs)
+        games = generator.generate_examples(n_games)
+        self.games_played += self.n_games_per_generation
+        for examples in games:
+            self.buffer.append(examples)
+        self.last_generation_stats = dict(generator.last_stats, seconds=time.time() - start, games=len(games))
+        logger.info("Finished Generating Data. Took: " + str(time.time() - start) + " seconds")
+        self.update_buffer_size()
+        if len(self.buffer) > self.n_games_buffer:
+            del self.buffer[:len(self.buffer) - self.n_games_buffer]
+
+    def update_buffer_size(self):
+        if self.generation % 2 == 0 and self.n_games_buffer < self.n_games_buffer_max:
+            self.n_games_buffer += self.n_games_per_generation
+
+    def test_agent(self):
+        logger.info("test_agent: the strength-evaluation harness is out of scope of the self-play engine (SURVEY 8(f).2)")
+
+    def run(self, **engine_kwargs):
+        """Main loop (train.py:272-293): generate -> train -> (save)."""
+        rank, _ = parallel.rank_world()
+        while self.generation < self.n_generations:
+            self.generation += 1
+            self.generate_examples(self.n_games_per_generation, **engine_kwargs)
+            self.train_network()
+            if self.save and rank == 0 and self.generation % self.save_n_gens == 0:
+                torch.save(self.current_net.state_dict(), self.model_path + self.name_run + str(self.generation) + ".pth")

@@ -367,6 +367,49 @@ class PortGenerator:
         return games
 
 
+def dedupe_examples(flat):
+    """train.py:156-201 remove_duplicates, restated: per key, element-wise policy sum / count and value sum / count;
+    the first example of each key is the accumulator and is mutated in place (as in the reference)."""
+    first, vcount, pcount = {}, {}, {}
+    for ex in flat:
+        k = ex[0]
+        if k not in first:
+            first[k] = ex
+            vcount[k] = 1
+            pcount[k] = 1
+        else:
+            tgt = first[k]
+            if ex[2] and tgt[2]:
+                tgt[2] = [sum(x) for x in zip(tgt[2], ex[2])]
+                pcount[k] += 1
+            elif ex[2]:
+                tgt[2] = ex[2]
+            tgt[3] += ex[3]
+            vcount[k] += 1
+    for k in first:
+        if first[k][2]:
+            first[k][2] = [x / pcount[k] for x in first[k][2]]
+        first[k][3] = first[k][3] / vcount[k]
+    return list(first.values())
+
+
+def train_step(net, optimizer, flat, batch_size, device="cpu"):
+    """train.py:95-130 net_step restated for the fp32 reference net: returns (loss_policy, loss_value)."""
+    import torch
+    net.zero_grad()
+    ids = np.random.randint(len(flat), size=batch_size)
+    x = torch.from_numpy(np.array([flat[i][1] for i in ids])).float().to(device)
+    p_t, v_t = net(x)
+    p_r = [flat[i][2] if flat[i][2] else p_t[j, :].to("cpu").tolist() for j, i in enumerate(ids)]
+    p_r = torch.tensor(np.array(p_r)).float().to(device)
+    v_r = torch.tensor(np.array([flat[i][3] for i in ids])).float().to(device)
+    loss_v = torch.nn.MSELoss()(v_t, v_r.unsqueeze(1))
+    loss_p = -torch.sum(p_r * torch.log(p_t)) / p_r.size()[0]
+    (loss_v + loss_p).backward()
+    optimizer.step()
+    return loss_p, loss_v
+
+
 def time_selfplay(net, game_name, n_games, n_processes, **kwargs):
     """Wall-clock the multi-process generator; returns dict(sims_per_s, games_per_s, plies, cores, seconds)."""
     gen = PortGenerator(net, game_name, "cpu", n_pools=1, n_processes=n_processes, **kwargs)
