@@ -43,6 +43,9 @@ namespace az {
 constexpr int PH_BEGIN = 6;  // internal: a search must be started (root eval request or first simulation)
 constexpr int PH_COMPACT = 7;  // internal: waiting for k_compact to re-root (pend_node = the child to promote)
 constexpr int BLOCK = 128;
+#ifndef K_STEP_MIN_BLOCKS
+#define K_STEP_MIN_BLOCKS 7  // <= 73 registers: all 1024 CTAs of a 16,384-tree Connect Four launch are resident in one wave
+#endif
 
 struct __align__(16) TreeHdr {
   uint64_t root_b0, root_b1;
@@ -632,7 +635,7 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
 
 // ---------------------------------------------------------------- the step kernel
 template <class GM>
-__global__ void __launch_bounds__(BLOCK) k_step(const Params p, const StepIO io) {
+__global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params p, const StepIO io) {
   constexpr int G = GM::G;
   __shared__ int32_t s_path[BLOCK / G][GM::MAXD];
   __shared__ unsigned long long s_ctr[AZ_CTR_COUNT];
