@@ -133,6 +133,34 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// cta_group::2 pair (two CTAs of a cluster, M = 256): each CTA supplies its own 128 A rows and HALF of B (N/2 rows), so
+// the per-SM shared-memory fetch of B halves.  Issued by the leader CTA only; commits are multicast to both CTAs.
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -171,21 +199,23 @@ struct SmemLayout {
   static constexpr int BIAS_OFF = A_OFF + STAGES * A_STAGE_BYTES;
   static constexpr int S2_OFF = BIAS_OFF + 256;
   static constexpr int T2_OFF = S2_OFF + 256;
-  static constexpr int BAR_OFF = T2_OFF + 256;           // 13 mbarriers (8 B each), then the TMEM base address
-  static constexpr int STG_OFF = BAR_OFF + 16 * 8 + 16;  // per epilogue warp: res / out / out2 staging, 32 rows x 80 B
+  static constexpr int BAR_OFF = T2_OFF + 256;           // up to 24 mbarriers (8 B each), then the TMEM base address
+  static constexpr int STG_OFF = BAR_OFF + 24 * 8 + 16;  // per epilogue warp: res / out / out2 staging, 32 rows x 80 B
   static constexpr int STG_ROW = 80;                     // 64 B (half a row) + 16 B pad: conflict-free row-per-thread access
   static constexpr int STG_WARP = 3 * 32 * STG_ROW;
   static constexpr int TOTAL = STG_OFF + EPI_WARPS * STG_WARP;
 };
 
-template <bool STEM>
+template <bool STEM, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
+  static_assert(CG == 1 || (CG == 2 && !STEM), "the CTA-pair variant exists for the 64-channel convs only");
   constexpr int N_MMA = STEM ? 128 : 64;              // accumulator columns per tile
   constexpr int K_STEPS = STEM ? 1 : 4;               // 16-channel k-steps per tap
-  constexpr int W_N = STEM ? 128 : 64;                // rows of the B operand image
+  constexpr int W_N = STEM ? 128 : 64 / CG;           // rows of the B operand image held by THIS CTA
   constexpr int W_TAP_BYTES = W_N * 16 * 2 * K_STEPS; // bytes of one tap's weights
   constexpr int W_TOTAL = 9 * W_TAP_BYTES;
-  constexpr uint32_t TMEM_COLS = STEM ? 256u : 128u;
+  constexpr int ACC = STEM ? 2 : 4;                   // TMEM accumulator stages (the MMA warp may run ACC tiles ahead)
+  constexpr uint32_t TMEM_COLS = 256u;                // ACC * N_MMA
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -199,28 +229,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
   auto bar_full = [&](int s) { return s_bar + 8u * s; };
   auto bar_empty = [&](int s) { return s_bar + 8u * (STAGES + s); };
   auto bar_tfull = [&](int a) { return s_bar + 8u * (2 * STAGES + a); };
-  auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * STAGES + 2 + a); };
-  auto bar_w = [&]() { return s_bar + 8u * (2 * STAGES + 4); };
-  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::BAR_OFF + 16 * 8);
+  auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * STAGES + ACC + a); };
+  auto bar_w = [&]() { return s_bar + 8u * (2 * STAGES + 2 * ACC); };
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::BAR_OFF + 24 * 8);
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;  // rank 0 = leader: issues the MMAs for the pair
+  // all hand-offs TO the MMA issuer go to the leader's barriers
+  auto arrive_leader = [&](uint32_t bar) {
+    if (CG == 1 || cta_rank == 0) mbar_arrive(bar); else mbar_arrive_cluster(bar, 0u);
+  };
 
   // ---- one-time setup: barriers + TMEM (weights and epilogue vectors are loaded by the epilogue warps, see below)
   if (warp == 4 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full(s), 1);
+      mbar_init(bar_full(s), CG);  // one producer warp per CTA of the pair
       mbar_init(bar_empty(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < ACC; ++a) {
       mbar_init(bar_tfull(a), 1);
-      mbar_init(bar_tempty(a), EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(bar_tempty(a), EPI_WARPS * CG);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    mbar_init(bar_w(), 1);
+    mbar_init(bar_w(), CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (STEM) {  // k-chunk 1 (channels 8..15) of every stage is constant zero in stem mode
     for (int i = threadIdx.x; i < STAGES * SLAB; i += NUM_THREADS) {
@@ -231,6 +273,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   // Programmatic dependent launch: let the next layer's CTAs start their own prologue as soon as SMs free up ...
@@ -238,7 +281,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
 
   const int halo = p.Wp + 1;
   const int slab_rows = TILE_M + 2 * halo;
-  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // work units: CG == 1: one tile; CG == 2: a pair of adjacent tiles (2u, 2u+1), one per CTA of the cluster
+  const int n_units = (p.n_tiles + CG - 1) / CG;
+  const int unit0 = (int)blockIdx.x / CG, unit_stride = (int)gridDim.x / CG;
+  const int my_tiles = (n_units - unit0 + unit_stride - 1) / unit_stride;
+  auto tile_of = [&](int it) { return p.tile0 + (unit0 + it * unit_stride) * CG + (int)cta_rank; };
   const long long range_lo = (long long)p.lead + (long long)p.board0 * p.P;
   const long long range_hi = range_lo + (long long)p.boards * p.P;
   const int valid_pos = p.H * p.Wp;
@@ -253,7 +300,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int it = stage, round = 0; it < my_tiles; it += STAGES, ++round) {
       mbar_wait(bar_empty(stage), ((uint32_t)round & 1u) ^ 1u);
-      const int tile = p.tile0 + (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = tile_of(it);
       if (p.debug & 1) {
         // (experiment) no loads
       } else if constexpr (!STEM) {
@@ -335,22 +382,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full(stage));
+      if (lane == 0) arrive_leader(bar_full(stage));
     }
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)N_MMA);
+    // cta_group::2: M = 256 (m_dim field 16) across the pair
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)N_MMA) + (CG == 2 ? ((128u >> 4) << 24) : 0u);
     // Operand descriptors differ only in their 14-bit start-address field (units of 16 B): precompute the bases and the
     // nine tap offsets so that the issue loop is two integer adds per tcgen05.mma (the single issuing thread is
     // latency-bound on whatever address arithmetic sits between two MMAs).
     long long dlt[9];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) dlt[tap] = (long long)((tap / 3 - 1) * p.Wp + (tap % 3 - 1));
+    if (CG == 2 && cta_rank != 0) goto teardown;  // the peer CTA's tensor core is driven by the leader's instructions
     mbar_wait(bar_w(), 0u);  // weights resident (loaded by the epilogue warps while the first slabs were in flight)
     for (int it = 0; it < my_tiles; ++it) {
-      const int stage = it % STAGES, acc = it & 1;
+      const int stage = it % STAGES, acc = it % ACC;
       mbar_wait(bar_full(stage), (uint32_t)(it / STAGES) & 1u);
-      mbar_wait(bar_tempty(acc), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      mbar_wait(bar_tempty(acc), ((uint32_t)(it / ACC) & 1u) ^ 1u);
       tc_fence_after();
       // elect.sync (not `lane == 0`): the compiler then knows exactly one lane issues and keeps the descriptors in
       // uniform registers instead of wrapping every tcgen05.mma in an ELECT / BRA.U.ANY serialisation loop.
@@ -370,14 +419,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const uint64_t at = umma_desc_sw128(a_stage + (uint32_t)(halo + (int)dlt[tap]) * 128u);
-            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)tap * 8192u);
+            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)tap * (uint32_t)W_TAP_BYTES);
 #pragma unroll
-            for (int j = 0; j < K_STEPS; ++j)
-              umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (tap | j) != 0 ? 1u : 0u);
+            for (int j = 0; j < K_STEPS; ++j) {
+              if constexpr (CG == 2)
+                umma_bf16_2cta(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (tap | j) != 0 ? 1u : 0u);
+              else
+                umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (tap | j) != 0 ? 1u : 0u);
+            }
           }
         }
-        umma_commit(bar_empty(stage));  // smem stage reusable once these MMAs have read it
-        umma_commit(bar_tfull(acc));    // accumulator ready for the epilogue
+        if constexpr (CG == 2) {
+          umma_commit_2cta(bar_empty(stage));  // both CTAs' stages reusable / both accumulators ready
+          umma_commit_2cta(bar_tfull(acc));
+        } else {
+          umma_commit(bar_empty(stage));  // smem stage reusable once these MMAs have read it
+          umma_commit(bar_tfull(acc));    // accumulator ready for the epilogue
+        }
       }
       __syncwarp();
     }
@@ -391,8 +449,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     const int half = e >> 2;    // channels [32*half, 32*half+32)
     {  // weights + epilogue vectors -> smem, asynchronously to the producers' first slabs
       const int et = e * 32 + lane;
-      for (int i = et; i < W_TOTAL / 16; i += EPI_WARPS * 32)
-        cp_async16(s_w + (uint32_t)i * 16u, reinterpret_cast<const uint4*>(p.wpack) + i, 16u);
+      for (int i = et; i < W_TOTAL / 16; i += EPI_WARPS * 32) {
+        // global image: [tap][64 n][128 B]; this CTA keeps rows n = W_N*rank .. +W_N of every tap
+        const int tap = i / (W_TAP_BYTES / 16), off = i % (W_TAP_BYTES / 16);
+        const int gsrc = CG == 1 ? i : tap * (CG * W_TAP_BYTES / 16) + (int)cta_rank * (W_TAP_BYTES / 16) + off;
+        cp_async16(s_w + (uint32_t)i * 16u, reinterpret_cast<const uint4*>(p.wpack) + gsrc, 16u);
+      }
       cp_async_commit();
       if (et < CH) {
         s_bias[et] = p.bias[et];
@@ -402,7 +464,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       cp_async_wait<0>();
       fence_proxy_async();
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      if (et == 0) mbar_arrive(bar_w());
+      if (et == 0) arrive_leader(bar_w());
     }
     uint8_t* stg = smem + SmemLayout::STG_OFF + e * SmemLayout::STG_WARP;
     uint8_t* stg_res = stg;
@@ -426,7 +488,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     uint4 rnext[4];
     uint32_t vmask_next = 0;
     auto prefetch = [&](int it) {
-      const int tile = p.tile0 + (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = tile_of(it);
       const long long m_warp = (long long)tile * TILE_M + q * 32;
       const bool v = qrow_next >= 0 && qrow_next < range_len && pos_next < valid_pos && (pos_next % p.Wp) < p.W;
       vmask_next = __ballot_sync(0xffffffffu, v);
@@ -444,8 +506,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     if (my_tiles > 0) prefetch(0);
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int acc = it & 1;
-      const int tile = p.tile0 + (int)blockIdx.x + it * (int)gridDim.x;
+      const int acc = it % ACC;
+      const int tile = tile_of(it);
       const long long m_warp = (long long)tile * TILE_M + q * 32;
       // Invalid rows (pads, other launches' boards) are never loaded or stored.
       const uint32_t vmask = vmask_next;
@@ -456,7 +518,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       }
       if (it + 1 < my_tiles) prefetch(it + 1);
       __syncwarp();
-      mbar_wait(bar_tfull(acc), (uint32_t)(it >> 1) & 1u);
+      mbar_wait(bar_tfull(acc), (uint32_t)(it / ACC) & 1u);
       tc_fence_after();
       uint32_t v[32];
       uint32_t w[STEM ? 32 : 1];
@@ -473,7 +535,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       // accumulator read -> hand the TMEM stage back to the MMA warp before the math and the global stores
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(acc));
+      if (lane == 0) arrive_leader(bar_tempty(acc));
       if (p.debug & 2) continue;
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {  // 16 columns at a time
@@ -530,11 +592,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     }
   }
 
+teardown:
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer may still be arriving on / reading from this CTA
   if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -573,17 +640,18 @@ static int fill_geometry(aznn::ConvParams& p, int32_t board0, int32_t boards, in
   return 0;
 }
 
-template <bool STEM>
+template <bool STEM, int CG>
 static int launch_conv(const aznn::ConvParams& p, int n_ctas, void* stream) {
   using namespace aznn;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv<STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv<STEM, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::TOTAL);
     if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
     attr_set = true;
   }
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid > p.n_tiles) grid = p.n_tiles;
+  if (CG == 2) grid = grid < 2 ? 2 : (grid & ~1);
   static int use_pdl = -1;
   if (use_pdl < 0) {
     const char* ev = getenv("AZ_NN_PDL");
@@ -595,12 +663,23 @@ static int launch_conv(const aznn::ConvParams& p, int n_ctas, void* stream) {
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SmemLayout::TOTAL;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<STEM>, p);
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<STEM, CG>, p);
   if (e != cudaSuccess) return nn_fail(-2, "k_conv launch", e);
   e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_conv launch", e);
@@ -635,7 +714,13 @@ extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bia
     p.debug = dbg;
   }
   if (fill_geometry(p, board0, boards, H, W, lead, rows_alloc, "az_nn_conv3x3")) return -1;
-  return launch_conv<false>(p, n_ctas, stream);
+  static int use_pair = -1;
+  if (use_pair < 0) {
+    const char* ev = getenv("AZ_NN_PAIR");
+    use_pair = ev ? atoi(ev) : 0;  // measured on B200 (scripts/conv_microbench.py): the cta_group::2 pair halves the B
+                                   // fetch but couples two CTAs' pipelines: 76/97/122 us vs 70/78/93 us single-CTA
+  }
+  return use_pair ? launch_conv<false, 2>(p, n_ctas, stream) : launch_conv<false, 1>(p, n_ctas, stream);
 }
 
 extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st,
@@ -657,5 +742,5 @@ extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, c
   p.lrelu = 1;
   p.stem_st = bn_st;
   if (fill_geometry(p, board0, boards, H, W, lead, rows_alloc, "az_nn_stem")) return -1;
-  return launch_conv<true>(p, n_ctas, stream);
+  return launch_conv<true, 1>(p, n_ctas, stream);
 }
