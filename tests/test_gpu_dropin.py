@@ -168,3 +168,26 @@ def test_example_generator_contract(shim):
                             n_trees=8, seed=4)
     for game in gen2.generate_examples(8):
         assert all(-1.0 <= ex[3] <= 1.0 for ex in game)
+
+
+def test_baseline_config1_shipped_checkpoint_game(shim):
+    """BASELINE.json configs[0]: one Connect Four self-play game, 100 sims/move, the shipped example checkpoint, the
+    evaluator Net.predict on the CPU in fp32 -- through the drop-in (search on the GPU) and through the oracle's port of
+    the reference: identical examples for the same numpy seed."""
+    import os
+    import torch
+    from oracle import ref_port
+    from alphazero_openspiel_b200.game_utils import play_game_self
+    from alphazero_openspiel_b200.network import Net
+    ck = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example_model_connect_four.pth")
+    net = Net([3, 6, 7], 7)
+    net.load_state_dict(torch.load(ck, map_location="cpu", weights_only=True))  # reference key names load unchanged
+    net.eval()
+    kwargs = dict(n_playouts=100, c_puct=2.5, dirichlet_ratio=0.25, temperature=1.0, backup="on-policy")
+    np.random.seed(2024)
+    ours = play_game_self(net.predict, "connect_four", **kwargs)
+    np.random.seed(2024)
+    ref = ref_port.selfplay_game(net.predict, "connect_four", shim.load_game, **kwargs)
+    assert len(ours) == len(ref) >= 7
+    for a, b in zip(ours, ref):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and list(a[2]) == list(b[2]) and a[3] == b[3]
