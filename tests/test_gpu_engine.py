@@ -156,3 +156,66 @@ def test_full_size_pool_matches_oracle_on_sampled_trees():
             assert g["root_q"] == r["root_q"] and (int(g["bb"][0]), int(g["bb"][1])) == r["bb"]
             checked += 1
     assert checked >= 25
+
+
+def test_arena_overflow_is_counted_and_raised():
+    """A too-small node arena must never corrupt memory or pass silently: the engine counts it, the host raises."""
+    import torch
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    from alphazero_openspiel_b200.examplegenerator import ExampleGenerator
+    from alphazero_openspiel_b200.network import Net
+    eng = E.Engine("connect_four", 8, n_playouts=200, noise_mode=L.NOISE_COUNTER, eval_mode=L.EVAL_HASH,
+                   flags=L.F_KEEP_TREE | L.F_SAMPLE_MOVES, seed=1, node_capacity=64)
+    for _ in range(400):
+        eng.step()
+    assert eng.counters()["overflow"] > 0
+    eng.close()
+    net = Net([3, 6, 7], 7).eval()
+    gen = ExampleGenerator(net, "connect_four", torch.device("cuda:0"), n_playouts=200, n_trees=8, node_capacity=64, seed=2)
+    with pytest.raises(RuntimeError, match="overflow"):
+        gen.generate_examples(8)
+
+
+def test_device_dirichlet_noise_statistics():
+    """AZ_NOISE_DIRICHLET (throughput mode): P = 0.75*p + 0.25*eta with eta ~ Dirichlet(0.3 * 1_7) at the initial position
+    (uniform priors): recover eta from the root children and check simplex, mean 1/7 and the Dirichlet variance."""
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    n = 8192
+    eng = E.Engine("connect_four", n, n_playouts=50, noise_mode=L.NOISE_DIRICHLET, eval_mode=L.EVAL_UNIFORM,
+                   flags=L.F_KEEP_TREE, seed=77)
+    eng.step()   # root-eval requests
+    eng.step()   # consume: root expanded with noise, first simulation runs
+    st = eng.root_stats(offpolicy=False)
+    eng.close()
+    assert np.all(st["n_children"] == 7)
+    eta = (st["child_p"] - 0.75 / 7.0) / 0.25
+    assert np.all(eta > -1e-12) and np.allclose(eta.sum(axis=1), 1.0, atol=1e-9)
+    a, a0 = 0.3, 2.1
+    assert np.allclose(eta.mean(axis=0), 1.0 / 7, atol=0.01)
+    want_var = a * (a0 - a) / (a0 * a0 * (a0 + 1))
+    assert np.allclose(eta.var(axis=0), want_var, rtol=0.08)
+    # different trees draw different noise; the same seed reproduces the same noise
+    assert len(np.unique(np.round(eta[:, 0], 9))) > 0.99 * n
+
+
+@pytest.mark.parametrize("temperature", [1.0, 0.5])
+def test_device_move_sampling_follows_visit_counts(temperature):
+    """alphazerobot.py:78,84: moves are sampled with p ~ N^(1/T).  Uniform evaluator, no noise => every tree has the same
+    root visit counts at ply 0, so the empirical move frequencies over 8,192 trees must match (chi-square)."""
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    n, n_playouts = 8192, 60
+    eng = E.Engine("connect_four", n, n_playouts=n_playouts, noise_mode=L.NOISE_NONE, eval_mode=L.EVAL_UNIFORM,
+                   flags=L.F_KEEP_TREE | L.F_SAMPLE_MOVES | L.F_RECORDS, seed=5, temperature=temperature)
+    for _ in range(n_playouts + 4):
+        eng.step()
+    recs = eng.drain_records()
+    eng.close()
+    first = recs[(recs["kind"] == 0) & (recs["ply"] == 0)]
+    assert len(first) == n
+    counts = first["counts"][0, :7].astype(np.float64)
+    assert np.all(first["counts"][:, :7] == counts)          # identical searches
+    p = counts ** (1.0 / temperature)
+    p /= p.sum()
+    freq = np.bincount(first["action"], minlength=7).astype(np.float64)
+    chi2 = float((((freq - n * p) ** 2) / (n * p)).sum())
+    assert chi2 < 30.0, (chi2, freq, n * p)                  # 6 dof: P(chi2 > 30) ~ 4e-5
