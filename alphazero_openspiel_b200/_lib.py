@@ -60,6 +60,7 @@ SIGNATURES = {
     "az_command": (C.c_int, [C.c_void_p, _I32P, _I32P, _I32P, _VP]),
     "az_step": (C.c_int, [C.c_void_p, _VP, _VP, _F64P, _VP, C.c_int32, _VP]),
     "az_compact": (C.c_int, [C.c_void_p, _VP]),
+    "az_debug_timing": (C.c_int, [C.c_void_p, _VP]),
     "az_status": (C.c_int, [C.c_void_p, _I32P, _I32P, _I32P, _I32P, _VP]),
     "az_request_info": (C.c_int, [C.c_void_p, _U64P, _I32P, _I32P, _I32P, C.c_int32, _VP]),
     "az_root_stats": (C.c_int, [C.c_void_p, _I32P, _F64P, _I32P, _I32P, _I32P, _F64P, _F64P, _F64P, _F64P, _VP]),

@@ -13,9 +13,7 @@
 //
 // Data layout in HBM (per engine):
 //   hdr   [n_trees]            64-byte tree header (root/pending positions, phase, arena cursor)
-//   NL    [n_trees][2][cap]    uint2 {N, link}; link = first_child << 8 | n_children   (8 B / node)
-//   Q     [n_trees][2][cap]    double mean value                                      (8 B / node)
-//   P     [n_trees][2][cap]    double prior                                           (8 B / node)
+//   nodes [n_trees][2][cap]    24-byte records {uint2 {N, link}, double Q, double P}; link = first_child << 8 | n_children
 //   path  [n_trees][MAXD]      node indices root..leaf of the in-flight simulation
 // The children of a node are ONE contiguous block in legal (ascending action) order, so a lane group
 // reads a node's child statistics with three coalesced loads; the winning child's {N, link} comes back by
@@ -63,11 +61,10 @@ struct __align__(16) TreeHdr {
 };
 static_assert(sizeof(TreeHdr) == 80, "TreeHdr size");
 
+struct Node;
 struct Params {
   TreeHdr* hdr;
-  uint2* NL;
-  double* Q;
-  double* P;
+  Node* nodes;
   int32_t* path;
   uint8_t* rec;
   unsigned long long* rec_count;
@@ -75,6 +72,7 @@ struct Params {
   int* games_started;
   int* compact_list;   // trees waiting for re-root compaction (k_compact work list)
   int* compact_count;  // [0] = entries, [1] = CTAs done
+  long long* dbg;      // optional [n_trees][4]: cycles, phase in, sims this step, flags (az_debug_timing)
   long long rec_cap;
   int max_games;
   int rec_stride;
@@ -217,17 +215,23 @@ __device__ __forceinline__ void write_obs(const Params& p, const StepIO& io, int
 }
 
 // ---------------------------------------------------------------- tree primitives
+// One 24-byte record per node: {N, link, Q, P}.  The children of a node are one contiguous run of records, so the three
+// 8-byte fields that a lane group reads per child sit in the same one or two 128-byte lines (and the same DRAM page).
+struct __align__(8) Node {
+  uint2 nl;   // x = N (visit count), y = link = first_child << 8 | n_children
+  double q;   // mean value
+  double p;   // prior
+};
+static_assert(sizeof(Node) == 24, "Node size");
 struct Arena {
-  uint2* NL;
-  double* Q;
-  double* P;
+  Node* nd;
+  __device__ __forceinline__ uint2& nl(int i) const { return nd[i].nl; }
+  __device__ __forceinline__ double& q(int i) const { return nd[i].q; }
+  __device__ __forceinline__ double& p(int i) const { return nd[i].p; }
 };
 __device__ __forceinline__ Arena arena_of(const Params& p, int tree, int half) {
-  const size_t base = ((size_t)tree * 2 + half) * (size_t)p.cap;
   Arena a;
-  a.NL = p.NL + base;
-  a.Q = p.Q + base;
-  a.P = p.P + base;
+  a.nd = p.nodes + ((size_t)tree * 2 + half) * (size_t)p.cap;
   return a;
 }
 
@@ -237,10 +241,10 @@ __device__ __forceinline__ void backup_path(const Arena& a, const int32_t* path,
   for (int j = lane; j <= depth; j += G) {
     const int node = path[j];
     const double v = ((depth - j) & 1) ? -v_leaf : v_leaf;
-    const uint2 nl = a.NL[node];
-    const double q = a.Q[node];
-    a.Q[node] = __ddiv_rn(__dadd_rn(__dmul_rn((double)nl.x, q), v), (double)(nl.x + 1u));
-    a.NL[node].x = nl.x + 1u;
+    const uint2 nl = a.nl(node);
+    const double q = a.q(node);
+    a.q(node) = __ddiv_rn(__dadd_rn(__dmul_rn((double)nl.x, q), v), (double)(nl.x + 1u));
+    a.nl(node).x = nl.x + 1u;
   }
 }
 
@@ -253,7 +257,7 @@ __device__ __forceinline__ bool expand_node(const Params& p, const StepIO& io, c
   const typename GM::Legal lg = GM::legal(s, p.geo);
   const int L = GM::count(lg);
   *L_out = L;
-  const uint2 nl = a.NL[node];
+  const uint2 nl = a.nl(node);
   int fc;
   bool fresh;
   if ((nl.y & 0xffu) != 0) {  // children exist (re-expanded root): overwrite P only
@@ -264,7 +268,7 @@ __device__ __forceinline__ bool expand_node(const Params& p, const StepIO& io, c
     fc = h.alloc;
     h.alloc += L;
     fresh = true;
-    if (lane == 0) a.NL[node].y = ((unsigned)fc << 8) | (unsigned)L;
+    if (lane == 0) a.nl(node).y = ((unsigned)fc << 8) | (unsigned)L;
   }
   const EvalKey ek = eval_key(p, s);
 #pragma unroll
@@ -274,10 +278,10 @@ __device__ __forceinline__ bool expand_node(const Params& p, const StepIO& io, c
       const int act = GM::action_of(lg, s, p.geo, i);
       double pr = eval_prior(p, io, tree, ek, act);
       if (root_mix) pr = __dadd_rn(__dmul_rn(p.keep, pr), __dmul_rn(p.noise_w, eta_lane[sl]));
-      a.P[fc + i] = pr;
+      a.p(fc + i) = pr;
       if (fresh) {
-        a.NL[fc + i] = make_uint2(0u, 0u);
-        a.Q[fc + i] = 0.0;
+        a.nl(fc + i) = make_uint2(0u, 0u);
+        a.q(fc + i) = 0.0;
       }
     }
   }
@@ -293,7 +297,7 @@ __device__ __forceinline__ void sim_select(const Params& p, const Arena& a, int 
   node = root;
   depth = 0;
   if (lane == 0) spath[0] = root;
-  uint2 cur = a.NL[root];
+  uint2 cur = a.nl(root);
   for (;;) {
     const int nc = (int)(cur.y & 0xffu);
     if (nc == 0) break;
@@ -307,9 +311,9 @@ __device__ __forceinline__ void sim_select(const Params& p, const Arena& a, int 
     for (int sl = 0; sl < GM::SLOTS; ++sl) {
       const int i = lane + sl * G;
       if (i < nc) {
-        const uint2 nl = a.NL[fc + i];
-        const double q = a.Q[fc + i];
-        const double pp = a.P[fc + i];
+        const uint2 nl = a.nl(fc + i);
+        const double q = a.q(fc + i);
+        const double pp = a.p(fc + i);
         // Q + (((c_puct * P) * sqrt(N_parent)) / (N + 1))      mcts.py:78
         const double u = __ddiv_rn(__dmul_rn(__dmul_rn(p.c_puct, pp), sq), (double)(nl.x + 1u));
         const double sc = __dadd_rn(q, u);
@@ -335,13 +339,13 @@ __device__ __forceinline__ void sim_select(const Params& p, const Arena& a, int 
 template <class GM, int G>
 __device__ double offpolicy_value(const Arena& a, int root, int lane, unsigned gm) {
   int node = root;
-  uint2 cur = a.NL[root];
+  uint2 cur = a.nl(root);
   double value = 0.0, mult = 1.0;
   for (;;) {
     const int nc = (int)(cur.y & 0xffu);
     if (nc == 0) break;
     const int fc = (int)(cur.y >> 8);
-    value = a.Q[node];
+    value = a.q(node);
     double best = 0.0;
     int bi = 0x7fffffff;
     uint2 bnl = make_uint2(0u, 0u);
@@ -349,8 +353,8 @@ __device__ double offpolicy_value(const Arena& a, int root, int lane, unsigned g
     for (int sl = 0; sl < GM::SLOTS; ++sl) {
       const int i = lane + sl * G;
       if (i < nc) {
-        const uint2 nl = a.NL[fc + i];
-        const double sc = nl.x > 0 ? __dadd_rn((double)nl.x, a.P[fc + i]) : -99.0;
+        const uint2 nl = a.nl(fc + i);
+        const double sc = nl.x > 0 ? __dadd_rn((double)nl.x, a.p(fc + i)) : -99.0;
         if (bi == 0x7fffffff || sc > best) { best = sc; bi = i; bnl = nl; }
       }
     }
@@ -363,7 +367,7 @@ __device__ double offpolicy_value(const Arena& a, int root, int lane, unsigned g
     mult = -mult;
   }
   if (cur.x > 0) {
-    value = a.Q[node];
+    value = a.q(node);
     mult = -mult;
   }
   return value * mult;
@@ -376,9 +380,9 @@ __device__ void reroot_compact(const Params& p, TreeHdr& h, int tree, int child,
   const Arena src = arena_of(p, tree, h.half);
   const Arena dst = arena_of(p, tree, h.half ^ 1);
   if (lane == 0) {
-    dst.NL[0] = src.NL[child];
-    dst.Q[0] = src.Q[child];
-    dst.P[0] = src.P[child];
+    dst.nl(0) = src.nl(child);
+    dst.q(0) = src.q(child);
+    dst.p(0) = src.p(child);
   }
   __syncwarp(gm);
   int head = 0, tail = 1;
@@ -387,7 +391,7 @@ __device__ void reroot_compact(const Params& p, TreeHdr& h, int tree, int child,
     const int idx = head + lane;
     int mync = 0, oldfc = 0;
     if (lane < nb) {
-      const uint2 nl = dst.NL[idx];
+      const uint2 nl = dst.nl(idx);
       mync = (int)(nl.y & 0xffu);
       oldfc = (int)(nl.y >> 8);
     }
@@ -395,11 +399,11 @@ __device__ void reroot_compact(const Params& p, TreeHdr& h, int tree, int child,
     const int total = gshfl<G>(gm, incl, G - 1);
     if (mync > 0) {
       const int newfc = tail + incl - mync;
-      dst.NL[idx].y = ((unsigned)newfc << 8) | (unsigned)mync;
+      dst.nl(idx).y = ((unsigned)newfc << 8) | (unsigned)mync;
       for (int j = 0; j < mync; ++j) {
-        dst.NL[newfc + j] = src.NL[oldfc + j];
-        dst.Q[newfc + j] = src.Q[oldfc + j];
-        dst.P[newfc + j] = src.P[oldfc + j];
+        dst.nl(newfc + j) = src.nl(oldfc + j);
+        dst.q(newfc + j) = src.q(oldfc + j);
+        dst.p(newfc + j) = src.p(oldfc + j);
       }
     }
     __syncwarp(gm);
@@ -416,9 +420,9 @@ template <int G>
 __device__ __forceinline__ void fresh_tree(const Params& p, TreeHdr& h, int tree, int lane, unsigned gm) {
   const Arena a = arena_of(p, tree, h.half);
   if (lane == 0) {
-    a.NL[0] = make_uint2(0u, 0u);  // Node(None, 0.0)  mcts.py:122
-    a.Q[0] = 0.0;
-    a.P[0] = 0.0;
+    a.nl(0) = make_uint2(0u, 0u);  // Node(None, 0.0)  mcts.py:122
+    a.q(0) = 0.0;
+    a.p(0) = 0.0;
   }
   h.root_node = 0;
   h.alloc = 1;
@@ -498,7 +502,7 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
   s.ply = h.root_ply;
   const typename GM::Legal lg = GM::legal(s, p.geo);
   const int L = GM::count(lg);
-  const uint2 rnl = a.NL[h.root_node];
+  const uint2 rnl = a.nl(h.root_node);
   const int fc = (int)(rnl.y >> 8);
   const int nc = (int)(rnl.y & 0xffu);  // == L once expanded
   int cnt[GM::SLOTS];
@@ -512,8 +516,8 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
     cnt[sl] = 0;
     qv[sl] = 0.0;
     if (i < nc) {
-      cnt[sl] = (int)a.NL[fc + i].x;
-      qv[sl] = a.Q[fc + i];
+      cnt[sl] = (int)a.nl(fc + i).x;
+      qv[sl] = a.q(fc + i);
       const double v = cnt[sl] > 0 ? qv[sl] : -99.0;
       if (a0c_i == 0x7fffffff || v > a0c) { a0c = v; a0c_i = i; }
     }
@@ -521,7 +525,7 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
   }
   total = gsum<G>(gm, total);
   gargmax<G>(gm, a0c, a0c_i);
-  const double root_q = a.Q[h.root_node];
+  const double root_q = a.q(h.root_node);
   double v_off = 0.0;
   if ((p.flags & AZ_F_RECORDS) && (p.flags & AZ_F_OFFPOLICY)) v_off = offpolicy_value<GM, G>(a, h.root_node, lane, gm);
 
@@ -647,7 +651,10 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
     const unsigned gm = group_mask<G>();
     int32_t* spath = s_path[threadIdx.x / G];
     int32_t* gpath = p.path + (size_t)tree * GM::MAXD;
+    const long long t_start = p.dbg ? clock64() : 0;
     TreeHdr h = p.hdr[tree];
+    const int phase_in = h.phase;
+    long long t_consume = 0;
     unsigned long long c_sims = 0, c_depth = 0, c_children = 0, c_exp = 0, c_legal = 0, c_term = 0;
 
     // ---------------- 1. consume the evaluator outputs of the pending request
@@ -722,6 +729,7 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
       if (lane == 0) ctr_add(s_ctr, AZ_CTR_ROOT_EVALS, 1);
     }
 
+    if (p.dbg) t_consume = clock64() - t_start;
     // ---------------- 2. run until the next evaluator request
     int sims_this_step = 0;
     bool advanced = false;
@@ -802,6 +810,12 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
 
     if (lane == 0) {
       p.hdr[tree] = h;
+      if (p.dbg) {
+        p.dbg[4 * tree + 0] = clock64() - t_start;
+        p.dbg[4 * tree + 1] = phase_in;
+        p.dbg[4 * tree + 2] = sims_this_step;
+        p.dbg[4 * tree + 3] = t_consume * 2 + (advanced ? 1 : 0);
+      }
       ctr_add(s_ctr, AZ_CTR_SIMS, c_sims);
       ctr_add(s_ctr, AZ_CTR_DEPTH, c_depth);
       ctr_add(s_ctr, AZ_CTR_CHILDREN, c_children);
@@ -831,9 +845,9 @@ __global__ void __launch_bounds__(COMPACT_BLOCK) k_compact(const Params p) {
     const Arena src = arena_of(p, tree, h.half);
     const Arena dst = arena_of(p, tree, h.half ^ 1);
     if (tid == 0) {
-      dst.NL[0] = src.NL[h.pend_node];
-      dst.Q[0] = src.Q[h.pend_node];
-      dst.P[0] = src.P[h.pend_node];
+      dst.nl(0) = src.nl(h.pend_node);
+      dst.q(0) = src.q(h.pend_node);
+      dst.p(0) = src.p(h.pend_node);
     }
     __syncthreads();
     int head = 0, tail = 1;
@@ -842,7 +856,7 @@ __global__ void __launch_bounds__(COMPACT_BLOCK) k_compact(const Params p) {
       const int idx = head + tid;
       int mync = 0, oldfc = 0;
       if (tid < nb) {
-        const uint2 nl = dst.NL[idx];
+        const uint2 nl = dst.nl(idx);
         mync = (int)(nl.y & 0xffu);
         oldfc = (int)(nl.y >> 8);
       }
@@ -858,11 +872,11 @@ __global__ void __launch_bounds__(COMPACT_BLOCK) k_compact(const Params p) {
       }
       if (mync > 0) {
         const int newfc = tail + off + incl - mync;
-        dst.NL[idx].y = ((unsigned)newfc << 8) | (unsigned)mync;
+        dst.nl(idx).y = ((unsigned)newfc << 8) | (unsigned)mync;
         for (int j = 0; j < mync; ++j) {
-          dst.NL[newfc + j] = src.NL[oldfc + j];
-          dst.Q[newfc + j] = src.Q[oldfc + j];
-          dst.P[newfc + j] = src.P[oldfc + j];
+          dst.nl(newfc + j) = src.nl(oldfc + j);
+          dst.q(newfc + j) = src.q(oldfc + j);
+          dst.p(newfc + j) = src.p(oldfc + j);
         }
       }
       __syncthreads();
@@ -960,7 +974,7 @@ __global__ void k_command(const Params p, const int32_t* upd, const int32_t* rst
       s.ply = h.root_ply;
       const typename GM::Legal lg = GM::legal(s, p.geo);
       const int k = GM::outcome(s, p.geo) >= 0 ? -1 : GM::rank_of(lg, s, p.geo, action);
-      const uint2 rnl = a.NL[h.root_node];
+      const uint2 rnl = a.nl(h.root_node);
       if ((rnl.y & 0xffu) == 0) {
         fresh_tree<G>(p, h, tree, lane, gm);  // root is a leaf -> Node(None, 0.0)   mcts.py:198-199
       } else if (k < 0) {
@@ -1033,7 +1047,7 @@ __global__ void k_request_info(const Params p, uint64_t* bb, int32_t* ply, int32
     s.b1 = h.root_b1;
     s.ply = h.root_ply;
     for (int j = 0; j < depth && j < max_depth; ++j) {
-      const int fc = (int)(a.NL[gpath[j]].y >> 8);
+      const int fc = (int)(a.nl(gpath[j]).y >> 8);
       const int k = gpath[j + 1] - fc;
       const typename GM::Legal lg = GM::legal(s, p.geo);
       const int act = GM::action_of(lg, s, p.geo, k);
@@ -1053,7 +1067,7 @@ __global__ void k_root_stats(const Params p, int32_t* root_n, double* root_q, in
   const unsigned gm = group_mask<G>();
   const TreeHdr h = p.hdr[tree];
   const Arena a = arena_of(p, tree, h.half);
-  const uint2 rnl = a.NL[h.root_node];
+  const uint2 rnl = a.nl(h.root_node);
   const int nc = (int)(rnl.y & 0xffu), fc = (int)(rnl.y >> 8);
   St s;
   s.b0 = h.root_b0;
@@ -1062,7 +1076,7 @@ __global__ void k_root_stats(const Params p, int32_t* root_n, double* root_q, in
   const typename GM::Legal lg = GM::legal(s, p.geo);
   if (lane == 0) {
     if (root_n) root_n[tree] = (int)rnl.x;
-    if (root_q) root_q[tree] = a.Q[h.root_node];
+    if (root_q) root_q[tree] = a.q(h.root_node);
     if (n_children) n_children[tree] = nc;
   }
   double a0c = -99.0;
@@ -1073,12 +1087,12 @@ __global__ void k_root_stats(const Params p, int32_t* root_n, double* root_q, in
     if (i < GM::MAXC) {
       const size_t o = (size_t)tree * GM::MAXC + i;
       const bool have = i < nc;
-      const uint2 nl = have ? a.NL[fc + i] : make_uint2(0u, 0u);
-      const double q = have ? a.Q[fc + i] : 0.0;
+      const uint2 nl = have ? a.nl(fc + i) : make_uint2(0u, 0u);
+      const double q = have ? a.q(fc + i) : 0.0;
       if (child_action) child_action[o] = have ? GM::action_of(lg, s, p.geo, i) : -1;
       if (child_n) child_n[o] = have ? (int)nl.x : 0;
       if (child_q) child_q[o] = q;
-      if (child_p) child_p[o] = have ? a.P[fc + i] : 0.0;
+      if (child_p) child_p[o] = have ? a.p(fc + i) : 0.0;
       if (have) {
         const double v = nl.x > 0 ? q : -99.0;
         if (a0c_i == 0x7fffffff || v > a0c) { a0c = v; a0c_i = i; }
@@ -1323,9 +1337,7 @@ int az_create(const az_config* cfg_in, az_engine** out) {
   };
   cudaError_t err = cudaSuccess;
   if ((err = alloc((void**)&p.hdr, sizeof(TreeHdr) * (size_t)cfg.n_trees)) != cudaSuccess ||
-      (err = alloc((void**)&p.NL, sizeof(uint2) * nodes)) != cudaSuccess ||
-      (err = alloc((void**)&p.Q, sizeof(double) * nodes)) != cudaSuccess ||
-      (err = alloc((void**)&p.P, sizeof(double) * nodes)) != cudaSuccess ||
+      (err = alloc((void**)&p.nodes, sizeof(Node) * nodes)) != cudaSuccess ||
       (err = alloc((void**)&p.path, sizeof(int32_t) * (size_t)cfg.n_trees * maxd)) != cudaSuccess ||
       (err = alloc((void**)&p.rec, (size_t)p.rec_stride * (size_t)p.rec_cap)) != cudaSuccess ||
       (err = alloc((void**)&p.rec_count, sizeof(unsigned long long))) != cudaSuccess ||
@@ -1355,9 +1367,7 @@ int az_destroy(az_engine* e) {
   if (!e) return 0;
   Params& p = e->p;
   cudaFree(p.hdr);
-  cudaFree(p.NL);
-  cudaFree(p.Q);
-  cudaFree(p.P);
+  cudaFree(p.nodes);
   cudaFree(p.path);
   cudaFree(p.rec);
   cudaFree(p.rec_count);
@@ -1365,6 +1375,7 @@ int az_destroy(az_engine* e) {
   cudaFree(p.games_started);
   cudaFree(p.compact_list);
   cudaFree(p.compact_count);
+  if (p.dbg) cudaFree(p.dbg);
   cudaFree(e->d_cmd);
   cudaFree(e->d_bad);
   delete e;
@@ -1481,6 +1492,19 @@ int az_compact(az_engine* e, void* stream) {
   const Params p = e->p;
   k_compact<<<compact_grid(p.n_trees), 256, 0, (cudaStream_t)stream>>>(p);
   CK(cudaGetLastError());
+  return 0;
+}
+
+int az_debug_timing(az_engine* e, long long* out_host) {
+  /* Development aid: per-tree SM cycle counts of the LAST k_step ([n_trees][4]: total cycles, phase on entry, simulations
+   * run, 2*consume_cycles + moved).  The first call only arms the instrumentation. */
+  if (!e || !out_host) return fail(-1, "null argument");
+  const size_t bytes = sizeof(long long) * 4 * (size_t)e->p.n_trees;
+  if (!e->p.dbg) {
+    CK(cudaMalloc((void**)&e->p.dbg, bytes));
+    CK(cudaMemset(e->p.dbg, 0, bytes));
+  }
+  CK(cudaMemcpy(out_host, e->p.dbg, bytes, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -182,6 +182,10 @@ int az_step(az_engine* e, const void* priors_dev, const void* values_dev, const 
  * the first and before the second (typically a side stream, overlapping the evaluator). */
 int az_compact(az_engine* e, void* stream);
 
+/* Development aid: per-tree SM cycle counts of the last az_step into host memory [n_trees][4] (total cycles, phase on
+ * entry, simulations run, 2*consume_cycles + moved).  The first call arms the instrumentation (returns zeros). */
+int az_debug_timing(az_engine* e, long long* out_host);
+
 /* Per-tree status into device arrays (any may be NULL): phase (AZ_PH_*), sims done in the current search,
  * ply of the root position, legal-move count of the pending request's position. */
 int az_status(az_engine* e, int32_t* phase_dev, int32_t* sims_dev, int32_t* ply_dev, int32_t* req_legal_dev,
