@@ -116,8 +116,24 @@ def cpu_baseline(game, n_playouts, seconds_budget=20.0, max_plies=None):
                                  dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", max_plies=max_plies)
     sample = ("%d games x first %d plies, %d sims/move, %d worker processes + 1 evaluator process (fp32 CPU ResNet), "
               "%d sims in %.1f s" % (res["n_games"], max_plies, n_playouts, workers, res["sims"], res["seconds"]))
+    # BASELINE config 1 shape: one process, in-process Net.predict, 100 sims/move (first 8 plies, bounded)
+    torch.set_num_threads(1)
+    np_state = None
+    try:
+        import numpy as np
+        np_state = np.random.get_state()
+        np.random.seed(0)
+        t0 = time.time()
+        st = {}
+        ref_port.selfplay_game(net.predict, game, pyspiel_shim.load_game, stats=st, n_playouts=100, c_puct=2.5,
+                               dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", max_plies=8)
+        single = st.get("sims", 0) / max(time.time() - t0, 1e-9)
+    finally:
+        if np_state is not None:
+            np.random.set_state(np_state)
     return {"value": res["sims_per_s"], "unit": "sims/s", "cores": workers + 1, "kind": "port", "sample": sample,
-            "host_cpus": cores, "games_per_s_equiv": res["sims_per_s"] / (n_playouts * 25.0)}
+            "host_cpus": cores, "games_per_s_equiv": res["sims_per_s"] / (n_playouts * 25.0),
+            "single_process_100sims_sims_per_s": single}
 
 
 def run_reference(args):
