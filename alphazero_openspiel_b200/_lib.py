@@ -14,7 +14,7 @@ EVAL_EXTERNAL, EVAL_UNIFORM, EVAL_HASH = 0, 1, 2
 OBS_NONE, OBS_F32_NCHW, OBS_BF16_NHWC = 0, 1, 2
 PH_IDLE, PH_ROOT_EVAL, PH_LEAF_EVAL, PH_SEARCH_DONE, PH_RUN, PH_ERROR = 0, 1, 2, 3, 4, 5
 CTR_NAMES = ["sims", "depth", "children", "expansions", "legal", "terminal", "root_evals", "moves", "games",
-             "compact_nodes", "overflow", "idle_slots"]
+             "compact_nodes", "overflow", "idle_slots", "peak_nodes"]
 
 
 class AzConfig(C.Structure):

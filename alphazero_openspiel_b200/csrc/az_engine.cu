@@ -816,6 +816,7 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
         p.dbg[4 * tree + 2] = sims_this_step;
         p.dbg[4 * tree + 3] = t_consume * 2 + (advanced ? 1 : 0);
       }
+      atomicMax(&s_ctr[AZ_CTR_PEAK_NODES], (unsigned long long)h.alloc);
       ctr_add(s_ctr, AZ_CTR_SIMS, c_sims);
       ctr_add(s_ctr, AZ_CTR_DEPTH, c_depth);
       ctr_add(s_ctr, AZ_CTR_CHILDREN, c_children);
@@ -825,7 +826,10 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
     }
   }
   __syncthreads();
-  if (threadIdx.x < AZ_CTR_COUNT && s_ctr[threadIdx.x]) atomicAdd(&p.ctr[threadIdx.x], s_ctr[threadIdx.x]);
+  if (threadIdx.x < AZ_CTR_COUNT && s_ctr[threadIdx.x]) {
+    if (threadIdx.x == AZ_CTR_PEAK_NODES) atomicMax(&p.ctr[threadIdx.x], s_ctr[threadIdx.x]);
+    else atomicAdd(&p.ctr[threadIdx.x], s_ctr[threadIdx.x]);
+  }
 }
 
 // ---------------------------------------------------------------- re-root compaction, one CTA per moving tree
@@ -1285,9 +1289,11 @@ int az_create(const az_config* cfg_in, az_engine** out) {
   const int maxd = cfg.game_id == AZ_GAME_CONNECT_FOUR ? C4::MAXD : BT::MAXD;
   const int group = cfg.game_id == AZ_GAME_CONNECT_FOUR ? C4::G : BT::G;
   if (cfg.node_capacity <= 0) {
-    // every playout expands at most one leaf (<= maxc children); a kept subtree is at most the previous arena
+    // Every playout expands at most one leaf (<= branch children) and a re-rooted tree keeps at most what it had, so the
+    // worst case grows by (n_playouts+1)*branch per ply.  Measured high-water marks (AZ_CTR_PEAK_NODES, 25k-step soaks):
+    // Connect Four @800: 26.7k nodes = 4.7 searches' worth -> default 8 searches' worth.  Overflow is counted and raised.
     const int branch = cfg.game_id == AZ_GAME_CONNECT_FOUR ? 7 : 3 * cfg.cols + 8;
-    long long c = (long long)(cfg.n_playouts + 2) * branch * 3 + 64;
+    long long c = (long long)(cfg.n_playouts + 2) * branch * 8 + 64;
     if (c > (1 << 24) - 1) c = (1 << 24) - 1;
     cfg.node_capacity = (int)c;
   }

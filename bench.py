@@ -196,7 +196,7 @@ def run_ours(args):
                             dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", seed=0xC4 + rank,
                             auto_restart=True, random_start_mod=21, max_sims_per_step=args.sim_cap, records=True,
                             use_graph=not args.no_graph, evaluator=args.evaluator, nn_slice=args.nn_slice,
-                            keep_search_tree=not args.no_keep_tree)
+                            keep_search_tree=not args.no_keep_tree, node_capacity=args.node_capacity)
     # ---- warm-up (untimed): builds the first searches so trees are in steady state
     runner.round(args.warmup)
     runner.drain()
@@ -336,6 +336,7 @@ def run_ours(args):
                                 % (runner.engine.device_bytes / 1e9, args.trees * rows * cols * 64 * 2 * 3 / 1e6)},
         "games_per_sec": games / (ms / 1e3), "moves_per_sec": moves / (ms / 1e3), "evals_per_sec": evals_per_s,
         "sims_per_eval_slot": sims / (args.trees * world * args.steps), "overflow": overflow,
+        "peak_nodes_per_tree": c1.get("peak_nodes"), "node_capacity": int(runner.engine.cfg.node_capacity),
         "e2e": {"value": e2e_sims / t_e2e, "unit": "sims/s", "h2d_bytes_per_step": h2d / args.steps,
                 "d2h_bytes_per_step": d2h / args.steps,
                 "what": "SelfPlayRunner.load_weights(host net) + round(K) + drain()/counters() to host, wall clock"},
@@ -355,6 +356,8 @@ def run_ours(args):
         except Exception as e:  # the baseline must never hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "sims/s", "cores": 0, "kind": "port",
                                     "sample": "failed: %r" % (e,)}
+    if overflow:
+        sys.stderr.write("WARNING: %d arena/record overflows in the timed region -- raise --node-capacity\n" % overflow)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -376,6 +379,7 @@ def main():
     ap.add_argument("--ref-repeat", action="store_true")
     ap.add_argument("--evaluator", default="fused", choices=["fused", "torch"])
     ap.add_argument("--nn-slice", type=int, default=0)
+    ap.add_argument("--node-capacity", type=int, default=0)
     ap.add_argument("--no-keep-tree", action="store_true", help="experiment: fresh tree every move (no re-root compaction)")
     args = ap.parse_args()
     if args.warmup < 3:

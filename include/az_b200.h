@@ -135,6 +135,7 @@ enum {
   AZ_CTR_COMPACT_NODES,   /* nodes copied by re-root compaction */
   AZ_CTR_OVERFLOW,        /* arena/depth/record overflows -- must stay 0 */
   AZ_CTR_IDLE_SLOTS,      /* evaluator rows wasted (no request from that tree this step) */
+  AZ_CTR_PEAK_NODES,      /* high-water mark of nodes in use in one tree's arena half (size node_capacity from it) */
   AZ_CTR_COUNT
 };
 
