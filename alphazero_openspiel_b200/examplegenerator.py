@@ -300,13 +300,20 @@ class ExampleGenerator:
         runner = SelfPlayRunner(self.net, self.game_name, self.device, n_trees, seed=seed, max_games=n_games,
                                 auto_restart=True, records=True, **kw)
         chunks = []
+        # drain the device record buffer before it can fill: ~1.5 * n_trees / n_playouts records arrive per round
+        n_playouts = max(1, int(kw.get("n_playouts", 100)))
+        capacity = int(runner.engine.cfg.record_capacity)
+        drain_every = max(64, int(capacity * n_playouts / (4.0 * n_trees)) // 64 * 64)
+        since_drain = 0
         try:
             while True:
                 runner.round(64)
+                since_drain += 64
                 if runner.all_idle():
                     break
-                if runner.rounds % 4096 < 64:
+                if since_drain >= drain_every:
                     chunks.append(runner.drain())
+                    since_drain = 0
             chunks.append(runner.drain())
             stats = runner.counters()
             stats["rounds"] = runner.rounds

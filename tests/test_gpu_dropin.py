@@ -191,3 +191,16 @@ def test_baseline_config1_shipped_checkpoint_game(shim):
     assert len(ours) == len(ref) >= 7
     for a, b in zip(ours, ref):
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and list(a[2]) == list(b[2]) and a[3] == b[3]
+
+
+def test_example_generator_many_short_searches_never_overflows_records(shim):
+    """More training records than the device buffer holds (1 M): the generator must drain in time, not overflow."""
+    import torch
+    from alphazero_openspiel_b200.examplegenerator import ExampleGenerator
+    from alphazero_openspiel_b200.network import Net
+    torch.manual_seed(0)
+    net = Net([3, 6, 7], 7).eval()
+    gen = ExampleGenerator(net, "connect_four", torch.device("cuda:0"), n_playouts=3, n_trees=4096, seed=9)
+    games = gen.generate_examples(70000)
+    assert len(games) == 70000 and gen.last_stats["overflow"] == 0
+    assert sum(len(g) for g in games) == gen.last_stats["moves"] > (1 << 20)
