@@ -126,13 +126,22 @@ def test_full_size_pool_matches_oracle_on_sampled_trees():
     game, n_trees, n_playouts, seed = "connect_four", 16384, 800, 0xC4
     flags = L.F_RECORDS | L.F_KEEP_TREE | L.F_SAMPLE_MOVES | L.F_RANDOM_START | L.F_AUTO_RESTART
     eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=L.NOISE_COUNTER, eval_mode=L.EVAL_HASH, flags=flags,
-                   seed=seed, start_plies_mod=21, max_sims_per_step=16)
-    for _ in range(2600):  # ~4 moves per tree
-        eng.step()
-    recs = eng.drain_records()
+                   seed=seed, start_plies_mod=21, max_sims_per_step=16, record_capacity=4 << 20)
+    sample = list(range(0, 8)) + [4095, 8191, 16383]
+    recs_all = []
+    for chunk in range(60):  # up to 30,000 steps: until the sampled trees have finished their first game
+        for _ in range(500):
+            eng.step()
+        recs_all.append(eng.drain_records())
+        r = np.concatenate(recs_all)
+        ends = r[(r["kind"] == 1) & (r["game_seq"] == 0)]
+        if all((ends["tree"] == t).any() for t in sample):
+            break
+    recs = np.concatenate(recs_all)
     ctr = eng.counters()
     eng.close()
     assert ctr["overflow"] == 0 and ctr["moves"] > 3 * n_trees
+    assert ctr["peak_nodes"] > 2 * 7 * n_playouts   # trees really carried several searches' worth of nodes across re-roots
     plies = recs[recs["kind"] == 0]
     assert len(plies) == ctr["moves"]
     # invariants over ALL records: a search adds exactly n_playouts visits below the root
@@ -144,18 +153,21 @@ def test_full_size_pool_matches_oracle_on_sampled_trees():
     assert np.all(plies["root_n"] >= n_playouts)
     assert np.all(plies["n_legal"] >= 1) and np.all(plies["n_legal"] <= 7)
     assert np.all(np.abs(plies["root_q"]) <= 1.0)
-    cfg = ou.selfplay_cfg(game, n_playouts, use_dirichlet=2, sample_moves=1, keep_tree=1, seed=seed, start_mod=21, max_plies=3)
+    cfg = ou.selfplay_cfg(game, n_playouts, use_dirichlet=2, sample_moves=1, keep_tree=1, seed=seed, start_mod=21)
     checked = 0
-    for t in list(range(0, 8)) + [4095, 8191, 16383]:
+    for t in sample:
         mine = plies[(plies["tree"] == t) & (plies["game_seq"] == 0)]
         mine = mine[np.argsort(mine["ply"])]
-        ref, _, _ = ou.selfplay_game(cfg, t)
-        assert len(mine) >= min(len(ref), 3)
+        ref, ret, _ = ou.selfplay_game(cfg, t)
+        assert len(mine) == len(ref)                      # the WHOLE first game, every ply, with tree reuse
         for r, g in zip(ref, mine):
             assert g["ply"] == r["ply"] and list(g["counts"][:r["n_legal"]]) == r["counts"] and g["action"] == r["action"]
             assert g["root_q"] == r["root_q"] and (int(g["bb"][0]), int(g["bb"][1])) == r["bb"]
+            assert g["root_n"] == r["root_n"]
             checked += 1
-    assert checked >= 25
+        end = recs[(recs["kind"] == 1) & (recs["tree"] == t) & (recs["game_seq"] == 0)]
+        assert len(end) == 1 and end[0]["root_q"] == ret[0]
+    assert checked >= 100
 
 
 def test_arena_overflow_is_counted_and_raised():
@@ -219,3 +231,39 @@ def test_device_move_sampling_follows_visit_counts(temperature):
     freq = np.bincount(first["action"], minlength=7).astype(np.float64)
     chi2 = float((((freq - n * p) ** 2) / (n * p)).sum())
     assert chi2 < 30.0, (chi2, freq, n * p)                  # 6 dof: P(chi2 > 30) ~ 4e-5
+
+
+def test_async_compaction_on_side_stream_is_bit_exact():
+    """AZ_F_ASYNC_COMPACT: the caller runs az_compact on a side stream between two az_step calls (what SelfPlayRunner does
+    next to the evaluator).  Results must equal the oracle exactly, like the synchronous mode."""
+    import torch
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    game, n_trees, n_playouts, seed = "connect_four", 64, 100, 4321
+    flags = L.F_RECORDS | L.F_OFFPOLICY | L.F_KEEP_TREE | L.F_SAMPLE_MOVES | L.F_ASYNC_COMPACT
+    eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=L.NOISE_COUNTER, eval_mode=L.EVAL_HASH, flags=flags,
+                   seed=seed)
+    side = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+    for it in range(200000):
+        eng.step()
+        ev_fork.record(main)
+        side.wait_event(ev_fork)
+        eng.compact(side)
+        ev_join.record(side)
+        main.wait_event(ev_join)
+        if it % 256 == 255 and int((eng.phases() != L.PH_IDLE).sum()) == 0:
+            break
+    recs = eng.drain_records()
+    ctr = eng.counters()
+    eng.close()
+    assert ctr["overflow"] == 0 and ctr["compact_nodes"] > 0
+    cfg = ou.selfplay_cfg(game, n_playouts, use_dirichlet=2, sample_moves=1, keep_tree=1, seed=seed)
+    for t in range(0, n_trees, 4):
+        plies = recs[(recs["tree"] == t) & (recs["kind"] == 0)]
+        plies = plies[np.argsort(plies["ply"])]
+        ref, _, _ = ou.selfplay_game(cfg, t)
+        assert len(plies) == len(ref)
+        for r, g in zip(ref, plies):
+            assert list(g["counts"][:r["n_legal"]]) == r["counts"] and g["action"] == r["action"]
+            assert g["root_q"] == r["root_q"] and g["v_offpolicy"] == r["v_offpolicy"] and g["root_n"] == r["root_n"]
