@@ -204,3 +204,25 @@ def test_example_generator_many_short_searches_never_overflows_records(shim):
     games = gen.generate_examples(70000)
     assert len(games) == 70000 and gen.last_stats["overflow"] == 0
     assert sum(len(g) for g in games) == gen.last_stats["moves"] > (1 << 20)
+
+
+def test_shipped_checkpoint_beats_random_through_the_whole_stack(shim):
+    """End-to-end behavioural pin of the UNPINNED game restatement (SURVEY B.4 / tournament.py:19-27 in spirit): the
+    reference's trained Connect Four checkpoint + 100-playout search on the device kernels + the tcgen05 evaluator must
+    crush a uniform-random opponent from both sides.  A wrong plane order, row orientation, action id or value sign
+    anywhere between az_step's observation encode and the policy/value head would turn this into coin flips."""
+    import os
+    import torch
+    from alphazero_openspiel_b200.evaluate import zero_vs_random
+    from alphazero_openspiel_b200.network import Net
+    ck = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example_model_connect_four.pth")
+    net = Net([3, 6, 7], 7)
+    net.load_state_dict(torch.load(ck, map_location="cpu", weights_only=True))
+    net.eval()
+    s_first, s_second = zero_vs_random(net, "connect_four", n_pairs=48, n_playouts=100, seed=3)
+    assert s_first >= 0.9 and s_second >= 0.85, (s_first, s_second)
+    # control: the same search with an untrained network is far weaker than that
+    torch.manual_seed(0)
+    blank = Net([3, 6, 7], 7).eval()
+    b_first, b_second = zero_vs_random(blank, "connect_four", n_pairs=48, n_playouts=100, seed=3)
+    assert (s_first + s_second) > (b_first + b_second)
