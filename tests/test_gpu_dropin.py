@@ -219,10 +219,12 @@ def test_shipped_checkpoint_beats_random_through_the_whole_stack(shim):
     net = Net([3, 6, 7], 7)
     net.load_state_dict(torch.load(ck, map_location="cpu", weights_only=True))
     net.eval()
-    s_first, s_second = zero_vs_random(net, "connect_four", n_pairs=48, n_playouts=100, seed=3)
-    assert s_first >= 0.9 and s_second >= 0.85, (s_first, s_second)
-    # control: the same search with an untrained network is far weaker than that
+    # 8 playouts: the result is decided by the network's policy / value, not by brute-force search
+    # (measured, 256 pairs: shipped checkpoint (1.0, 1.0); untrained network (0.48, 0.60); at 100 playouts even the
+    #  untrained network scores 0.97 against random, so that setting would not discriminate)
+    s_first, s_second = zero_vs_random(net, "connect_four", n_pairs=64, n_playouts=8, seed=3)
+    assert s_first >= 0.95 and s_second >= 0.95, (s_first, s_second)
     torch.manual_seed(0)
     blank = Net([3, 6, 7], 7).eval()
-    b_first, b_second = zero_vs_random(blank, "connect_four", n_pairs=48, n_playouts=100, seed=3)
-    assert (s_first + s_second) > (b_first + b_second)
+    b_first, b_second = zero_vs_random(blank, "connect_four", n_pairs=64, n_playouts=8, seed=3)
+    assert b_first <= 0.85 and b_second <= 0.85, (b_first, b_second)
