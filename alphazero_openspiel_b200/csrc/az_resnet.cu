@@ -62,6 +62,8 @@ struct ConvParams {
   const float* s2;
   const float* t2;
   const float* stem_st;       // STEM: device [8]: bn1 scale[4], shift[4] of the input planes
+  const uint2* skip_obs;      // optional: observation planes [boards][H][W][4]; the epilogue adds the 1x1 skip projection
+  const float* skip_w;        //   skip_w [64][4] of the raw planes (network.py:101-103) instead of reading a residual tensor
   int rows_alloc;             // multiple of 128
   int n_tiles;
   int lead, boards, P, Wp, H, W;
@@ -199,7 +201,8 @@ struct SmemLayout {
   static constexpr int BIAS_OFF = A_OFF + STAGES * A_STAGE_BYTES;
   static constexpr int S2_OFF = BIAS_OFF + 256;
   static constexpr int T2_OFF = S2_OFF + 256;
-  static constexpr int BAR_OFF = T2_OFF + 256;           // up to 24 mbarriers (8 B each), then the TMEM base address
+  static constexpr int SKIPW_OFF = T2_OFF + 256;         // [64][4] fp32 skip-projection weights
+  static constexpr int BAR_OFF = SKIPW_OFF + 1024;       // up to 24 mbarriers (8 B each), then the TMEM base address
   static constexpr int STG_OFF = BAR_OFF + 24 * 8 + 16;  // per epilogue warp: res / out / out2 staging, 32 rows x 80 B
   static constexpr int STG_ROW = 80;                     // 64 B (half a row) + 16 B pad: conflict-free row-per-thread access
   static constexpr int STG_WARP = 3 * 32 * STG_ROW;
@@ -460,6 +463,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
         s_bias[et] = p.bias[et];
         s_s2[et] = (p.out2 && p.s2) ? p.s2[et] : 0.f;
         s_t2[et] = (p.out2 && p.t2) ? p.t2[et] : 0.f;
+        reinterpret_cast<float4*>(smem + SmemLayout::SKIPW_OFF)[et] =
+            p.skip_obs ? reinterpret_cast<const float4*>(p.skip_w)[et] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       cp_async_wait<0>();
       fence_proxy_async();
@@ -473,6 +478,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     const int crow = lane >> 2, cch = lane & 3;  // cooperative copy: lane -> (row within group of 8, 16-byte chunk)
     const int col0 = half * 32;
     const bool has_res = !STEM && p.res != nullptr;
+    const bool has_skip = !STEM && p.skip_obs != nullptr;
+    const float4* s_skipw = reinterpret_cast<const float4*>(smem + SmemLayout::SKIPW_OFF);
+    const int cells = p.H * p.W;
+    uint2 xnext = make_uint2(0u, 0u);
 
     // Row validity without per-tile divisions: this thread's row advances by gridDim.x * 128 rows per tile, so its
     // position inside the board advances by a constant (mod P).  32-bit arithmetic throughout.
@@ -492,6 +501,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       const long long m_warp = (long long)tile * TILE_M + q * 32;
       const bool v = qrow_next >= 0 && qrow_next < range_len && pos_next < valid_pos && (pos_next % p.Wp) < p.W;
       vmask_next = __ballot_sync(0xffffffffu, v);
+      if (has_skip) {  // this row's 4 observation planes (for the 1x1 skip projection)
+        xnext = make_uint2(0u, 0u);
+        if (v) {
+          const int b = qrow_next / p.P;
+          xnext = p.skip_obs[(long long)(p.board0 + b) * cells + (pos_next / p.Wp) * p.W + pos_next % p.Wp];
+        }
+      }
       qrow_next += step_rows;
       pos_next += step_pos;
       if (pos_next >= p.P) pos_next -= p.P;
@@ -511,6 +527,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       const long long m_warp = (long long)tile * TILE_M + q * 32;
       // Invalid rows (pads, other launches' boards) are never loaded or stored.
       const uint32_t vmask = vmask_next;
+      const uint2 xrow = xnext;
       if (has_res) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -544,6 +561,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
         for (int i = 0; i < 16; ++i) {
           f[i] = __uint_as_float(v[cb * 16 + i]) + bias_r[cb * 16 + i];
           if (p.lrelu) f[i] = lrelu(f[i]);
+        }
+        if (has_skip) {
+          const float x0 = __uint_as_float(xrow.x << 16), x1 = __uint_as_float(xrow.x & 0xffff0000u);
+          const float x2 = __uint_as_float(xrow.y << 16), x3 = __uint_as_float(xrow.y & 0xffff0000u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 wv = s_skipw[col0 + cb * 16 + i];
+            f[i] += x0 * wv.x + x1 * wv.y + x2 * wv.z + x3 * wv.w;
+          }
         }
         if (has_res) {
           const uint4 r0 = *reinterpret_cast<const uint4*>(stg_res + lane * SmemLayout::STG_ROW + cb * 32);
@@ -602,6 +628,84 @@ teardown:
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FC head for small action spaces (fc1 of network.py:48, 61-66 with A + 1 <= 8 outputs, i.e. Connect Four): a skinny
+// [boards][K = P*64] x [K][8] product is pure streaming of the activations (K*2 bytes per board, HBM/L2-bound).  One warp
+// takes 8 boards; mma.sync m16n8k16 (rows 8-15 of A left zero, N = 8 outputs) keeps the arithmetic off the issue slots so
+// the warp only issues 16-byte loads, HEAD_UNROLL of them in flight per lane.  The k index inside a 64-byte segment is
+// permuted identically for both operands (lane t of a quad owns bytes [16t, 16t+16) of the segment in A and in B), which a
+// dot product does not care about, so every load is a plain 16-byte one.  The bf16 weight image [8][K] sits in shared
+// memory (rows padded by 64 B: conflict-free).  Softmax over the A logits and tanh of the value logit finish in the quad
+// that holds the board's 8 sums (fp32 out, no bf16 rounding of the logits).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int HEAD_OUT = 8;
+constexpr int HEAD_BOARDS = 8;      // boards per warp
+constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_UNROLL = 8;
+constexpr int HEAD_WPAD = 4;        // uint4 of padding per weight row in shared memory
+
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                  uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(HEAD_THREADS, 2)
+k_head(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __restrict__ bias, float* __restrict__ priors,
+       float* __restrict__ values, int board0, int boards, int chunks /* K/8 per board */, int A) {
+  extern __shared__ __align__(16) uint8_t hsmem[];
+  uint4* s_w = reinterpret_cast<uint4*>(hsmem);  // [HEAD_OUT][chunks + HEAD_WPAD]
+  const int wstride = chunks + HEAD_WPAD;
+  for (int i = threadIdx.x; i < HEAD_OUT * chunks; i += HEAD_THREADS) s_w[(i / chunks) * wstride + i % chunks] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;              // mma fragment coordinates: board row / output row g, quad lane t
+  const int warp_global = blockIdx.x * (HEAD_THREADS / 32) + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * (HEAD_THREADS / 32);
+  const int n_groups = (boards + HEAD_BOARDS - 1) / HEAD_BOARDS;
+  const int n_it = chunks >> 2;                       // 64-byte segments per board
+  const float bias0 = bias[2 * t], bias1 = bias[2 * t + 1];
+  for (int grp = warp_global; grp < n_groups; grp += n_warps) {
+    const int b = grp * HEAD_BOARDS + g;
+    const int bc = b < boards ? b : boards - 1;       // ragged tail: recompute the last board, never stored
+    const uint4* xr = x + (long long)(board0 + bc) * chunks + t;
+    const uint4* wr = s_w + g * wstride + t;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int it0 = 0; it0 < n_it; it0 += HEAD_UNROLL) {
+      uint4 xa[HEAD_UNROLL];
+#pragma unroll
+      for (int u = 0; u < HEAD_UNROLL; ++u)
+        xa[u] = it0 + u < n_it ? __ldg(xr + (it0 + u) * 4) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < HEAD_UNROLL; ++u) {
+        if (it0 + u < n_it) {
+          const uint4 wv = wr[(it0 + u) * 4];
+          mma_bf16_m16n8k16(c, xa[u].x, 0u, xa[u].y, 0u, wv.x, wv.y);
+          mma_bf16_m16n8k16(c, xa[u].z, 0u, xa[u].w, 0u, wv.z, wv.w);
+        }
+      }
+    }
+    // c[0], c[1] = sums of board g for outputs 2t, 2t+1; the quad holds all 8
+    const float l0 = c[0] + bias0, l1 = c[1] + bias1;
+    const bool v0 = 2 * t < A, v1 = 2 * t + 1 < A;
+    float mx = fmaxf(v0 ? l0 : -3.0e38f, v1 ? l1 : -3.0e38f);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float e0 = v0 ? expf(l0 - mx) : 0.f, e1 = v1 ? expf(l1 - mx) : 0.f;
+    float den = e0 + e1;
+    den += __shfl_xor_sync(0xffffffffu, den, 1);
+    den += __shfl_xor_sync(0xffffffffu, den, 2);
+    if (b < boards) {
+      const long long bb = board0 + b;
+      if (v0) priors[bb * A + 2 * t] = e0 / den;
+      if (v1) priors[bb * A + 2 * t + 1] = e1 / den;
+      if (2 * t == A) values[bb] = tanhf(l0);
+      if (2 * t + 1 == A) values[bb] = tanhf(l1);
+    }
   }
 }
 
@@ -687,8 +791,9 @@ static int launch_conv(const aznn::ConvParams& p, int n_ctas, void* stream) {
 }
 
 extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                             const float* s2, const float* t2, int32_t board0, int32_t boards, int32_t H, int32_t W,
-                             int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t n_ctas, void* stream) {
+                             const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
+                             int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu,
+                             int32_t n_ctas, void* stream) {
   using namespace aznn;
   if (!in || !wpack || !bias || !out) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: null argument");
@@ -704,6 +809,12 @@ extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bia
   p.out2 = (__nv_bfloat16*)out2;
   p.s2 = s2;
   p.t2 = t2;
+  p.skip_obs = (const uint2*)skip_obs;
+  p.skip_w = skip_obs ? skip_w : nullptr;
+  if (skip_obs && !skip_w) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: skip_obs needs skip_w");
+    return -1;
+  }
   p.lrelu = lrelu;
   {
     static int dbg = -1;
@@ -727,7 +838,7 @@ extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, c
                           void* u, void* r, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead,
                           int32_t rows_alloc, int32_t n_ctas, void* stream) {
   using namespace aznn;
-  if (!obs || !wpack || !b1 || !b3 || !bn_st || !u || !r) {
+  if (!obs || !wpack || !b1 || !b3 || !bn_st || !u) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_stem: null argument");
     return -1;
   }
@@ -743,4 +854,41 @@ extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, c
   p.stem_st = bn_st;
   if (fill_geometry(p, board0, boards, H, W, lead, rows_alloc, "az_nn_stem")) return -1;
   return launch_conv<true, 1>(p, n_ctas, stream);
+}
+
+extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t board0,
+                          int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t n_actions,
+                          int32_t n_ctas, void* stream) {
+  using namespace aznn;
+  if (!x || !w || !bias || !priors || !values) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head: null argument");
+    return -1;
+  }
+  const int P = (H + 1) * (W + 1);
+  const int chunks = P * CH / 8;
+  const size_t smem = (size_t)HEAD_OUT * (chunks + HEAD_WPAD) * 16;
+  if (n_actions < 1 || n_actions + 1 > HEAD_OUT || smem > 100 * 1024 || board0 < 0 || boards <= 0 || (lead * CH) % 8 != 0 ||
+      (long long)lead + (long long)(board0 + boards) * P > rows_alloc) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head: needs n_actions + 1 <= %d, (H+1)*(W+1)*1024 <= 100 KB, boards in range",
+             HEAD_OUT);
+    return -1;
+  }
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
+    smem_set = smem;
+  }
+  const int n_groups = (boards + HEAD_BOARDS - 1) / HEAD_BOARDS;
+  int grid = n_ctas > 0 ? n_ctas : 2 * 148;
+  const int need = (n_groups + HEAD_THREADS / 32 - 1) / (HEAD_THREADS / 32);
+  if (grid > need) grid = need;
+  // plain launch: measured on B200, letting k_head start under programmatic dependent launch behind the last conv costs
+  // ~2% of the step (its CTAs take the SM slots the conv's tail and the concurrent k_compact want)
+  const uint4* xp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)x + (long long)lead * CH);
+  k_head<<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>(xp, (const uint4*)w, bias, priors, values, (int)board0, (int)boards,
+                                                             chunks, (int)n_actions);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nn_fail(-2, "k_head launch", e);
+  return 0;
 }

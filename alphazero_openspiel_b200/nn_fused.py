@@ -3,15 +3,17 @@
 Same contract as network.BatchedEvaluator -- obs bf16 [B,H,W,4] (written by az_step) -> priors fp32 [B,A], values
 fp32 [B] -- but the ten 3x3 convolutions run as tcgen05 implicit GEMMs with BatchNorm / LeakyReLU / bias / residual
 fused into their epilogues (11 launches instead of ~45 PyTorch kernels), on bf16 "padded rows" activations
-(see az_resnet.cu).  Host code here only folds/packs weights and sequences the launches; the FC head (a plain
-[B, P*64] x [P*64, A+1] GEMM) stays a cuBLAS call through torch, as does the softmax/tanh on its tiny output.
+(see az_resnet.cu).  Host code here only folds/packs weights and sequences the launches.  The FC head is the streaming
+k_head kernel (FC + softmax + tanh in one launch, fp32 logits) when A + 1 <= 8 (Connect Four); for larger action spaces
+it is a plain [B, P*64] x [P*64, A+1] GEMM and stays a cuBLAS call through torch, with softmax/tanh on its output.
 
-Per evaluation:   stem(obs) -> U, X
-                  conv(U)+X -> X, T = lrelu(bn1_2(X))                  (block 1, conv2)
+Per evaluation:   stem(obs) -> U
+                  X = conv(U) + conv1x1(obs), T = lrelu(bn1_2(X))      (block 1, conv2; skip projection in its epilogue)
                   for k = 2..5:  U = lrelu(conv(T) + b)  ;  X = conv(U) + X, T = lrelu(bn1_{k+1}(X))
                   head: softmax / tanh (X_flat @ Wfc + b)
 """
 import ctypes as C
+import os
 
 import torch
 from torch.nn import functional as F
@@ -60,6 +62,9 @@ class FusedEvaluator:
         self.priors = torch.zeros((batch, self.A), dtype=torch.float32, device=dev)
         self.values = torch.zeros((batch,), dtype=torch.float32, device=dev)
         self.par = None
+        # small action spaces (Connect Four) finish with the streaming k_head kernel; larger ones with a cuBLAS GEMM
+        self.fused_head = self.A + 1 <= 8 and 8 * (self.P * 8 + 4) * 16 <= 100 * 1024 and os.environ.get("AZ_NN_HEAD", "1") != "0"
+        self.fuse_skip = os.environ.get("AZ_NN_SKIPFUSE", "1") != "0"
         self.timing = None   # set to a list to collect (kernel, start_event, end_event) per launch (bench.py roofline)
         self.load(net)
 
@@ -98,6 +103,10 @@ class FusedEvaluator:
                 sb3 = torch.zeros(CH, dtype=torch.float64)
                 sb3[:N_FILTERS] = blk.conv3.bias.double().cpu()
                 new["stem_w"], new["stem_b3"] = sw.to(torch.bfloat16), sb3.float()
+                skw = torch.zeros((CH, 4), dtype=torch.float64)        # 1x1 skip projection, added by block 1's conv2
+                skw[:N_FILTERS] = blk.conv3.weight.double().cpu().reshape(N_FILTERS, 4)
+                new["skip_w"] = skw.float()
+                new["b2skip_0"] = (bias2 + sb3).float()                 # conv2 bias + projection bias
                 new["stem_st"] = torch.cat([a1, b1]).float()
             else:
                 w1p = torch.zeros((CH, CH, 3, 3), dtype=torch.float64)
@@ -113,6 +122,12 @@ class FusedEvaluator:
         fwp[:, :self.h, :self.w, :N_FILTERS] = fw.permute(0, 2, 3, 1)
         new["fw"] = fwp.reshape(self.A + 1, -1).to(torch.bfloat16)
         new["fb"] = net.fc1.bias.double().cpu().float()
+        if self.fused_head:   # k_head operand: [8 outputs][P*64] bf16 (unused outputs zero), bias [8]
+            hw = torch.zeros((8, self.P * CH), dtype=torch.float64)
+            hw[:self.A + 1] = fwp.reshape(self.A + 1, -1)
+            hb = torch.zeros(8, dtype=torch.float64)
+            hb[:self.A + 1] = net.fc1.bias.double().cpu()
+            new["hw"], new["hb"] = hw.to(torch.bfloat16), hb.float()
         if self.par is None:
             self.par = {k: v.contiguous().to(dev) for k, v in new.items()}
         else:
@@ -132,12 +147,13 @@ class FusedEvaluator:
         self.timing.append((name, e0, e1))
         return rc
 
-    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, b0, nb):
+    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, b0, nb, skip_obs=None, skip_w=None):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
-        name = "conv" + ("+res" if res is not None else "") + ("+out2" if out2 is not None else "")
+        name = "conv" + ("+res" if res is not None else "") + ("+skip" if skip_obs is not None else "") + \
+            ("+out2" if out2 is not None else "")
         rc = self._timed(name, lambda: self.lib.az_nn_conv3x3(
-            p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), b0, nb, self.h, self.w, LEAD, self.rows_alloc,
-            1 if lrelu else 0, self.n_ctas, self._stream()))
+            p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), p(skip_obs), p(skip_w), b0, nb, self.h, self.w,
+            LEAD, self.rows_alloc, 1 if lrelu else 0, self.n_ctas, self._stream()))
         if rc:
             raise RuntimeError("az_nn_conv3x3: " + self.lib.az_nn_last_error().decode())
 
@@ -148,17 +164,29 @@ class FusedEvaluator:
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         for b0, nb in self.slices:
             rc = self._timed("stem", lambda: self.lib.az_nn_stem(
-                p(self.obs), p(P_["stem_w"]), p(P_["b1_0"]), p(P_["stem_b3"]), p(P_["stem_st"]), p(self.U), p(self.X),
+                p(self.obs), p(P_["stem_w"]), p(P_["b1_0"]), p(P_["stem_b3"]), p(P_["stem_st"]), p(self.U),
+                None if self.fuse_skip else p(self.X),
                 b0, nb, self.h, self.w, LEAD, self.rows_alloc, self.n_ctas, self._stream()))
             if rc:
                 raise RuntimeError("az_nn_stem: " + self.lib.az_nn_last_error().decode())
-            # block 1, second conv: X = conv(U) + X ; T = lrelu(bn1_2(X))
-            self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False, b0, nb)
+            if self.fuse_skip:
+                # block 1, second conv: X = conv(U) + conv1x1(obs) ; T = lrelu(bn1_2(X))   (skip projection in the epilogue)
+                self._conv(self.U, P_["w2_0"], P_["b2skip_0"], None, self.X, self.T, P_["s_1"], P_["t_1"], False, b0, nb,
+                           skip_obs=self.obs, skip_w=P_["skip_w"])
+            else:
+                self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False, b0, nb)
             for k in range(1, 5):
                 self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True, b0, nb)
                 last = k == 4
                 self._conv(self.U, P_["w2_%d" % k], P_["b2_%d" % k], self.X, self.X, None if last else self.T,
                            None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False, b0, nb)
+            if self.fused_head:
+                rc = self._timed("head", lambda: self.lib.az_nn_head(
+                    p(self.X), p(P_["hw"]), p(P_["hb"]), p(self.priors), p(self.values), b0, nb, self.h, self.w, LEAD,
+                    self.rows_alloc, self.A, self.n_ctas, self._stream()))
+                if rc:
+                    raise RuntimeError("az_nn_head: " + self.lib.az_nn_last_error().decode())
+                continue
             lo = (LEAD + b0 * self.P) * CH
             flat = self.X.view(-1)[lo:lo + nb * self.P * CH].view(nb, self.P * CH)
             out = F.linear(flat, P_["fw"]).float() + P_["fb"]

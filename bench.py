@@ -269,11 +269,15 @@ def run_ours(args):
     nn_ms = sum(a.elapsed_time(b) for a, b in nn_evs) / n_probe
     alg_bytes_per_launch = algorithmic_bytes(pd, rows * cols, n_actions) / n_probe
     conv_ms, conv_n, stem_ms = 0.0, 0, 0.0
+    by_name = {}
     if fused:
         for name, e0, e1 in ev.timing:
+            acc = by_name.setdefault(name, [0.0, 0])
+            acc[0] += e0.elapsed_time(e1)
+            acc[1] += 1
             if name == "stem":
                 stem_ms += e0.elapsed_time(e1)
-            else:
+            elif name.startswith("conv"):
                 conv_ms += e0.elapsed_time(e1)
                 conv_n += 1
         ev.timing = None
@@ -319,6 +323,7 @@ def run_ours(args):
                          "avg_launch_ms": avg_conv_ms, "launches_per_step": conv_n / n_probe,
                          "algorithmic_flops_per_launch": conv_flops, "stem_avg_launch_ms": stem_ms / n_probe,
                          "share_of_step": conv_ms / n_probe / (step_ms + nn_ms),
+                         "launch_ms_by_kind": {k: v[0] / v[1] for k, v in sorted(by_name.items())},
                          "note": "measured limiter is shared-memory bandwidth (SS-mode operand fetch at N=64), see DESIGN.md; "
                                  "traffic = dram read+write of a conv1-type launch from profiles/r01_conv_full_raw.csv"}
     line = {
@@ -341,7 +346,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h / args.steps,
                 "what": "SelfPlayRunner.load_weights(host net) + round(K) + drain()/counters() to host, wall clock"},
         # our kernels per round trip: k_step, k_compact, stem + 9 convs (the FC head / softmax / tanh are library calls)
-        "gpu_launches": args.steps * world * ((2 if not args.no_keep_tree else 1) + (10 if fused else 0)),
+        "gpu_launches": args.steps * world * ((2 if not args.no_keep_tree else 1) + ((11 if getattr(ev, 'fused_head', False) else 10) if fused else 0)),
         "roofline": conv_roofline if fused else tree_roofline,
         "tree_roofline": tree_roofline,
         "nn_roofline": {"kernel": "ResNet forward (%s): stem + 9 convs + FC head" % args.evaluator, "bound": "tensor",

@@ -239,20 +239,29 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  * az_nn_conv3x3: out = conv3x3(in) + bias, optional LeakyReLU, optional + res; optional second output
  *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  wpack is [9 taps][64 n][8][8] bf16,
  *   the SWIZZLE_128B K-major operand image (tap = ky*3+kx; 16-byte chunk c of row n stored at position c ^ (n & 7)).
- *   tcgen05 implicit GEMM; n_ctas <= 0 -> one CTA per SM.
+ *   tcgen05 implicit GEMM; n_ctas <= 0 -> one CTA per SM.  With skip_obs (the az_step observation batch) and skip_w
+ *   [64][4] fp32 the epilogue adds the 1x1 skip projection of the raw planes (resblock1.conv3, network.py:101-103) instead
+ *   of reading a residual tensor, so the stem never has to write one.
  * az_nn_stem: the 4-plane first block on the same tcgen05 kernel (the slab is built from the az_step
  *   AZ_OBS_BF16_NHWC batch [boards][H][W][4]): u = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1), r = conv1x1(x) + b3
- *   (network.py:99-103 for resblock1).  wpack is [9 taps][2][128][8] bf16: rows 0-63 = conv1 (BatchNorm folded) on
+ *   (network.py:99-103 for resblock1; r may be NULL when the next conv computes the projection itself).  wpack is [9 taps][2][128][8] bf16: rows 0-63 = conv1 (BatchNorm folded) on
  *   k 0-3, rows 64-127 = the 1x1 skip projection on k 4-7 of the centre tap.  bn_st = device [8]: scale[4], shift[4].
- *   Both kernels work on boards [board0, board0+boards) of the full buffers and never read or write pad rows or rows of
+ * az_nn_head: the FC head (fc1, network.py:48,61-66) for games with n_actions + 1 <= 8 outputs: priors [.][n_actions] =
+ *   softmax(x_flat @ w[0..A-1]^T + bias), values = tanh(x_flat @ w[A]^T + bias[A]), fp32.  w is bf16 [8][(H+1)*(W+1)*64]
+ *   over the padded-rows flatten of one board (zero on pad cells / pad channels / unused outputs), bias fp32 [8].
+ *   All kernels work on boards [board0, board0+boards) of the full buffers and never read or write pad rows or rows of
  *   other boards (pads must be zero from allocation). */
 const char* az_nn_last_error(void);
 int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                  const float* s2, const float* t2, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead,
-                  int32_t rows_alloc, int32_t lrelu, int32_t n_ctas, void* stream);
+                  const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
+                  int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t n_ctas,
+                  void* stream);
 int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st, void* u,
                void* r, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc,
                int32_t n_ctas, void* stream);
+int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t board0,
+               int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t n_actions, int32_t n_ctas,
+               void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,7 +55,7 @@ def test_conv3x3_tcgen05_matches_torch(H, W, B):
         out = torch.zeros((rows_alloc, 64), dtype=torch.bfloat16, device=dev)   # pads are zero from allocation
         out2 = torch.zeros((rows_alloc, 64), dtype=torch.bfloat16, device=dev) if use_out2 else None
         rc = lib.az_nn_conv3x3(ptr(xin), ptr(wp), ptr(bias), ptr(rin) if use_res else None, ptr(out), ptr(out2),
-                               ptr(s2) if use_out2 else None, ptr(t2) if use_out2 else None, 0, B, H, W, LEAD,
+                               ptr(s2) if use_out2 else None, ptr(t2) if use_out2 else None, None, None, 0, B, H, W, LEAD,
                                rows_alloc, lrelu, 0, st)
         assert rc == 0, lib.az_nn_last_error()
         torch.cuda.synchronize()
@@ -121,5 +121,8 @@ def test_fused_evaluator_matches_fp32_reference(game):
     assert torch.equal(p2.cpu(), p) and torch.equal(v2.cpu(), v)
     # evaluating in L2-sized board slices changes nothing (slices never touch each other's rows)
     p3, v3 = FusedEvaluator(net, B, "cuda:0", slice_boards=333).eval_batch(xbf)
-    # (the cuBLAS FC head may pick a different kernel for a different row count -> last-bit differences only)
-    assert (p3.cpu() - p).abs().max().item() < 2e-3 and (v3.cpu() - v).abs().max().item() < 5e-3
+    # (k_head is slice-independent; the cuBLAS FC head of the larger games rounds its logits to bf16 and may pick a
+    # different kernel for a different row count -> differences of one bf16 ulp of the logit, 2^-8 at |logit| ~ 1)
+    assert (p3.cpu() - p).abs().max().item() < 2e-3 and (v3.cpu() - v).abs().max().item() < 1e-2
+    if fe.fused_head:
+        assert torch.equal(p3.cpu(), p) and torch.equal(v3.cpu(), v)
