@@ -37,6 +37,8 @@
 #include <string.h>
 #include <stdlib.h>
 
+#include <cuda.h>
+
 #include "../../include/az_b200.h"
 
 namespace aznn {
@@ -209,16 +211,25 @@ struct SmemLayout {
   static constexpr int TOTAL = STG_OFF + EPI_WARPS * STG_WARP;
 };
 
-template <bool STEM, int CG>
+// MODE_CONV: nine row-shifted A views (one per tap), N = 64.  MODE_STEM: the 4-plane first block.  MODE_DX: boards whose
+// padded row pitch is exactly 8 (W = 7, Connect Four): the three dx taps of a kernel row share ONE A view and become the N
+// dimension, D[row][dx*64 + co] = sum_dy,k A[row + dy*8][k] W(dy,dx)[k][co] (12 MMAs of N = 192 instead of 36 of N = 64:
+// the slab is fetched from shared memory 3x instead of 9x per tile), and the epilogue adds the three column blocks of the
+// neighbouring rows, out[q] = D_-1[q-1] + D_0[q] + D_+1[q+1], with one-lane warp shuffles.  Rows q-1 / q+1 of a lane at a
+// 32-row boundary are pad-column cells (row % 8 == 7 / 0), whose partial sums are zero because their activations are.
+constexpr int MODE_CONV = 0, MODE_STEM = 1, MODE_DX = 2;
+
+template <int MODE, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
-  static_assert(CG == 1 || (CG == 2 && !STEM), "the CTA-pair variant exists for the 64-channel convs only");
-  constexpr int N_MMA = STEM ? 128 : 64;              // accumulator columns per tile
+  constexpr bool STEM = MODE == MODE_STEM, FDX = MODE == MODE_DX;
+  static_assert(CG == 1 || (CG == 2 && MODE == MODE_CONV), "the CTA-pair variant exists for the plain 64-channel convs only");
+  constexpr int N_MMA = STEM ? 128 : FDX ? 192 : 64;  // accumulator columns per tile
   constexpr int K_STEPS = STEM ? 1 : 4;               // 16-channel k-steps per tap
-  constexpr int W_N = STEM ? 128 : 64 / CG;           // rows of the B operand image held by THIS CTA
-  constexpr int W_TAP_BYTES = W_N * 16 * 2 * K_STEPS; // bytes of one tap's weights
-  constexpr int W_TOTAL = 9 * W_TAP_BYTES;
-  constexpr int ACC = STEM ? 2 : 4;                   // TMEM accumulator stages (the MMA warp may run ACC tiles ahead)
-  constexpr uint32_t TMEM_COLS = 256u;                // ACC * N_MMA
+  constexpr int W_N = STEM ? 128 : FDX ? 192 : 64 / CG;  // rows of the B operand image held by THIS CTA
+  constexpr int W_TAP_BYTES = W_N * 16 * 2 * K_STEPS; // bytes of one tap's (FDX: one kernel row's) weights
+  constexpr int W_TOTAL = (FDX ? 3 : 9) * W_TAP_BYTES;
+  constexpr int ACC = (STEM || FDX) ? 2 : 4;          // TMEM accumulator stages (the MMA warp may run ACC tiles ahead)
+  constexpr uint32_t TMEM_COLS = FDX ? 512u : 256u;   // >= ACC * N_MMA, power of two
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -282,7 +293,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
   // Programmatic dependent launch: let the next layer's CTAs start their own prologue as soon as SMs free up ...
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int halo = p.Wp + 1;
+  const int halo = FDX ? p.Wp : p.Wp + 1;
   const int slab_rows = TILE_M + 2 * halo;
   // work units: CG == 1: one tile; CG == 2: a pair of adjacent tiles (2u, 2u+1), one per CTA of the cluster
   const int n_units = (p.n_tiles + CG - 1) / CG;
@@ -416,6 +427,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap)
             umma_bf16(d, ab + (uint64_t)dlt[tap], wdesc0 + (uint64_t)(tap * (W_TAP_BYTES / 16)), idesc, tap != 0 ? 1u : 0u);
+        } else if constexpr (FDX) {
+          const uint32_t a_stage = s_a + (uint32_t)stage * A_STAGE_BYTES;
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t at = umma_desc_sw128(a_stage + (uint32_t)(halo + (dy - 1) * p.Wp) * 128u);
+            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)dy * (uint32_t)W_TAP_BYTES);
+#pragma unroll
+            for (int j = 0; j < K_STEPS; ++j)
+              umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (dy | j) != 0 ? 1u : 0u);
+          }
         } else {
           // SW128: every activation row is its own 128-byte line, so a tap shift of delta rows never straddles lines.
           const uint32_t a_stage = s_a + (uint32_t)stage * A_STAGE_BYTES;
@@ -539,7 +560,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       tc_fence_after();
       uint32_t v[32];
       uint32_t w[STEM ? 32 : 1];
-      {
+      if constexpr (FDX) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_MMA + col0);
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t dm[16], d0[16], dp[16];
+          tmem_ld16(taddr + (uint32_t)(cb * 16), dm);
+          tmem_ld16(taddr + (uint32_t)(64 + cb * 16), d0);
+          tmem_ld16(taddr + (uint32_t)(128 + cb * 16), dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(dm[i]), 1);
+            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(dp[i]), 1);
+            v[cb * 16 + i] = __float_as_uint(__uint_as_float(d0[i]) + (lane != 0 ? up : 0.f) + (lane != 31 ? dn : 0.f));
+          }
+        }
+      } else {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_MMA + col0);
         tmem_ld16(taddr, &v[0]);
         tmem_ld16(taddr + 16u, &v[16]);
@@ -629,6 +666,348 @@ teardown:
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_conv_tma: the 64-channel 3x3 conv with TMA on both sides of the tensor core.
+//   warp 0      one thread: bulk-copies the weight image, then one cp.async.bulk.tensor (SWIZZLE_128B box of
+//               128 + 2*halo activation rows) per tile into a ring of S smem stages
+//   warp 1      MMA issuer (tcgen05.mma, accumulators in TMEM), as in k_conv
+//   warps 2..   NE epilogue warps.  A work item is (tile, 32-row TMEM lane quarter, 32-channel half); the NE/4 warps of a
+//               quarter take items round-robin, so several tiles' epilogues are in flight per scheduler.  Residual rows
+//               arrive by TMA (SWIZZLE_64B box of 32 rows x 32 channels, one item ahead), the result is written in place
+//               and leaves by TMA store; every row of the tile is stored, pad rows as zeros, so no per-row predicates
+//               and no LDS/STG copy-out.  (Launches therefore own whole 128-row tiles: no board slices here.)
+// Pad cells of the activation buffers are zero in global memory (never written with anything else), so the loader needs
+// no zero-fill logic: a tap that leaves the board always lands on a pad cell.
+// ---------------------------------------------------------------------------------------------------------------------
+struct TmaConvParams {
+  const __nv_bfloat16* wpack;
+  const float* bias;
+  const float* s2;
+  const float* t2;
+  const uint2* skip_obs;
+  const float* skip_w;
+  int n_tiles, lead, boards, P, Wp, H, W, board0, tile0;
+  int lrelu, has_res, has_out2, debug;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <bool FDX, int NE, int S>
+struct TmaSmem {
+  static constexpr int A_ST = (FDX ? 144 : 152) * 128;   // one slab: 128 + 2*halo rows of 128 B
+  static constexpr int W_OFF = 0;
+  static constexpr int A_OFF = W_BYTES;
+  static constexpr int STG_OFF = A_OFF + S * A_ST;       // per epilogue warp: io[2] (residual in / result out), out2
+  static constexpr int STG_WARP = 3 * 2048;
+  static constexpr int BIAS_OFF = STG_OFF + NE * STG_WARP;
+  static constexpr int S2_OFF = BIAS_OFF + 256;
+  static constexpr int T2_OFF = S2_OFF + 256;
+  static constexpr int SKIPW_OFF = T2_OFF + 256;
+  static constexpr int BAR_OFF = SKIPW_OFF + 1024;       // full[S] empty[S] tfull[4] tempty[4] w resbar[NE][2]
+  static constexpr int N_BARS = 2 * S + 9 + 2 * NE;
+  static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+template <bool FDX, int NE, int S>
+__global__ void __launch_bounds__((2 + NE) * 32, 1)
+k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_res,
+           const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2, const TmaConvParams p) {
+  using L = TmaSmem<FDX, NE, S>;
+  constexpr int N_MMA = FDX ? 192 : 64;
+  constexpr int K_STEPS = 4;
+  constexpr int W_TAP_BYTES = N_MMA * 16 * 2 * K_STEPS;
+  constexpr int ACC = FDX ? 2 : 4;
+  constexpr uint32_t TMEM_COLS = FDX ? 512u : 256u;
+  constexpr int NEQ = NE / 4;                            // epilogue warps per TMEM lane quarter
+  static_assert(NE % 4 == 0, "whole quarters");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_w = s_base + L::W_OFF, s_a = s_base + L::A_OFF;
+  float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+  float* s_s2 = reinterpret_cast<float*>(smem + L::S2_OFF);
+  float* s_t2 = reinterpret_cast<float*>(smem + L::T2_OFF);
+  const uint32_t s_bar = s_base + L::BAR_OFF;
+  auto bar_full = [&](int s) { return s_bar + 8u * s; };
+  auto bar_empty = [&](int s) { return s_bar + 8u * (S + s); };
+  auto bar_tfull = [&](int a) { return s_bar + 8u * (2 * S + a); };
+  auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * S + 4 + a); };
+  auto bar_w = [&]() { return s_bar + 8u * (2 * S + 8); };
+  auto bar_res = [&](int e, int b) { return s_bar + 8u * (2 * S + 9 + 2 * e + b); };
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + L::N_BARS * 8);
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < ACC; ++a) {
+      mbar_init(bar_tfull(a), 1);
+      mbar_init(bar_tempty(a), 8);  // (4 quarters) x (2 channel halves)
+    }
+    mbar_init(bar_w(), 1);
+    for (int e = 0; e < NE; ++e) {
+      mbar_init(bar_res(e, 0), 1);
+      mbar_init(bar_res(e, 1), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int halo = FDX ? p.Wp : p.Wp + 1;
+  const int slab_rows = TILE_M + 2 * halo;
+  const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_of = [&](int it) { return p.tile0 + (int)blockIdx.x + it * (int)gridDim.x; };
+  const long long range_lo = (long long)p.lead + (long long)p.board0 * p.P;
+  const int range_len = p.boards * p.P;
+  const int valid_pos = p.H * p.Wp;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      mbar_expect_tx(bar_w(), (uint32_t)W_BYTES);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        bulk_g2s(s_w + (uint32_t)i * (W_BYTES / 3), reinterpret_cast<const uint8_t*>(p.wpack) + i * (W_BYTES / 3), W_BYTES / 3, bar_w());
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are the previous layer's output
+      for (int it = 0; it < my_tiles; ++it) {
+        const int stage = it % S;
+        mbar_wait(bar_empty(stage), ((uint32_t)(it / S) & 1u) ^ 1u);
+        if (p.debug & 1) {
+          mbar_arrive(bar_full(stage));
+        } else {
+          mbar_expect_tx(bar_full(stage), (uint32_t)slab_rows * 128u);
+          tma_load_2d(s_a + (uint32_t)stage * L::A_ST, &tm_in, 0, tile_of(it) * TILE_M - halo, bar_full(stage));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)N_MMA);
+    uint32_t dlt[9];  // byte offset of each tap's A view inside a stage
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) dlt[tap] = (uint32_t)(halo + (tap / 3 - 1) * p.Wp + (FDX ? 0 : tap % 3 - 1)) * 128u;
+    mbar_wait(bar_w(), 0u);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int stage = it % S, acc = it % ACC;
+      mbar_wait(bar_full(stage), (uint32_t)(it / S) & 1u);
+      mbar_wait(bar_tempty(acc), ((uint32_t)(it / ACC) & 1u) ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = tmem_base + (uint32_t)(acc * N_MMA);
+        const uint32_t a_stage = s_a + (uint32_t)stage * L::A_ST;
+        if (p.debug & 4) {
+          // (experiment) no MMAs
+        } else if constexpr (FDX) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t at = umma_desc_sw128(a_stage + dlt[dy * 3]);
+            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)dy * (uint32_t)W_TAP_BYTES);
+#pragma unroll
+            for (int j = 0; j < K_STEPS; ++j)
+              umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (dy | j) != 0 ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t at = umma_desc_sw128(a_stage + dlt[tap]);
+            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)tap * (uint32_t)W_TAP_BYTES);
+#pragma unroll
+            for (int j = 0; j < K_STEPS; ++j)
+              umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (tap | j) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_empty(stage));
+        umma_commit(bar_tfull(acc));
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int e = warp - 2;
+    const int q = warp & 3;      // TMEM lane quarter this warp may access
+    const int j0 = e >> 2;       // round-robin slot among the NEQ warps of this quarter
+    {
+      const int et = e * 32 + lane;
+      if (et < CH) {
+        s_bias[et] = p.bias[et];
+        s_s2[et] = (p.has_out2 && p.s2) ? p.s2[et] : 0.f;
+        s_t2[et] = (p.has_out2 && p.t2) ? p.t2[et] : 0.f;
+        reinterpret_cast<float4*>(smem + L::SKIPW_OFF)[et] =
+            p.skip_obs ? reinterpret_cast<const float4*>(p.skip_w)[et] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NE * 32) : "memory");
+    }
+    uint8_t* stg = smem + L::STG_OFF + e * L::STG_WARP;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const bool has_res = p.has_res != 0, has_out2 = p.has_out2 != 0, has_skip = p.skip_obs != nullptr;
+    const float4* s_skipw = reinterpret_cast<const float4*>(smem + L::SKIPW_OFF);
+    const int cells = p.H * p.W;
+    const int n_items = my_tiles * 2;
+    // this thread's row inside a 32-row x 64-byte SWIZZLE_64B box: chunk c lives at chunk position c ^ ((row >> 1) & 3)
+    const uint32_t row_off = (uint32_t)lane * 64u;
+    const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+    const bool skip_all = (p.debug & 2) != 0;
+
+    // validity + observation planes of this thread's row in item i
+    auto row_info = [&](int i, uint2& x) -> bool {
+      const int tile = tile_of(i >> 1);
+      const long long qr = (long long)tile * TILE_M + q * 32 + lane - range_lo;
+      bool v = qr >= 0 && qr < range_len;
+      x = make_uint2(0u, 0u);
+      if (v) {
+        const int b = (int)qr / p.P, pos = (int)qr - b * p.P;
+        const int rr = pos / p.Wp, cc = pos - rr * p.Wp;
+        v = pos < valid_pos && cc < p.W;
+        if (v && has_skip) x = p.skip_obs[(long long)(p.board0 + b) * cells + rr * p.W + cc];
+      }
+      return v;
+    };
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // residual reads / output writes depend on the previous layer
+    uint2 xnext = make_uint2(0u, 0u);
+    bool vnext = false;
+    if (j0 < n_items) {
+      vnext = row_info(j0, xnext);
+      if (has_res && !skip_all && lane == 0) {
+        mbar_expect_tx(bar_res(e, 0), 2048u);
+        tma_load_2d(stg_u32, &tm_res, (j0 & 1) * 32, tile_of(j0 >> 1) * TILE_M + q * 32, bar_res(e, 0));
+      }
+    }
+    for (int i = j0, n = 0; i < n_items; i += NEQ, ++n) {
+      const int it = i >> 1, half = i & 1, acc = it % ACC, b = n & 1;
+      const int col0 = half * 32;
+      const int row0 = tile_of(it) * TILE_M + q * 32;
+      const bool valid = vnext;
+      const uint2 xrow = xnext;
+      mbar_wait(bar_tfull(acc), (uint32_t)(it / ACC) & 1u);
+      tc_fence_after();
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_MMA + col0);
+      if constexpr (FDX) {
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t dm[16], d0[16], dp[16];
+          tmem_ld16(taddr + (uint32_t)(cb * 16), dm);
+          tmem_ld16(taddr + (uint32_t)(64 + cb * 16), d0);
+          tmem_ld16(taddr + (uint32_t)(128 + cb * 16), dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(dm[k]), 1);
+            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(dp[k]), 1);
+            v[cb * 16 + k] = __float_as_uint(__uint_as_float(d0[k]) + (lane != 0 ? up : 0.f) + (lane != 31 ? dn : 0.f));
+          }
+        }
+      } else {
+        tmem_ld16(taddr, &v[0]);
+        tmem_ld16(taddr + 16u, &v[16]);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(acc));
+      if (skip_all) continue;
+      // the previous item's stores have drained their staging buffers (io[b^1] and out2) before anything overwrites them
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      const int inext = i + NEQ;
+      if (inext < n_items) {
+        vnext = row_info(inext, xnext);
+        if (has_res && lane == 0) {
+          mbar_expect_tx(bar_res(e, b ^ 1), 2048u);
+          tma_load_2d(stg_u32 + (uint32_t)(b ^ 1) * 2048u, &tm_res, (inext & 1) * 32, tile_of(inext >> 1) * TILE_M + q * 32,
+                      bar_res(e, b ^ 1));
+        }
+      }
+      if (has_res) mbar_wait(bar_res(e, b), (uint32_t)(n >> 1) & 1u);
+      uint8_t* io = stg + b * 2048 + row_off;
+      uint8_t* o2 = stg + 4096 + row_off;
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {  // 16 columns = two 16-byte chunks at a time
+        const uint32_t c0 = (((uint32_t)(2 * cb)) ^ sw) * 16u, c1 = (((uint32_t)(2 * cb + 1)) ^ sw) * 16u;
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          f[k] = __uint_as_float(v[cb * 16 + k]) + s_bias[col0 + cb * 16 + k];
+          if (p.lrelu) f[k] = lrelu(f[k]);
+        }
+        if (has_skip) {
+          const float x0 = __uint_as_float(xrow.x << 16), x1 = __uint_as_float(xrow.x & 0xffff0000u);
+          const float x2 = __uint_as_float(xrow.y << 16), x3 = __uint_as_float(xrow.y & 0xffff0000u);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float4 wv = s_skipw[col0 + cb * 16 + k];
+            f[k] += x0 * wv.x + x1 * wv.y + x2 * wv.z + x3 * wv.w;
+          }
+        }
+        if (has_res) {
+          const uint4 r0 = *reinterpret_cast<const uint4*>(io + c0);
+          const uint4 r1 = *reinterpret_cast<const uint4*>(io + c1);
+          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            f[2 * k] += __uint_as_float(rw[k] << 16);
+            f[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+          }
+        }
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(io + c0) = valid ? pack8(&f[0]) : z;
+        *reinterpret_cast<uint4*>(io + c1) = valid ? pack8(&f[8]) : z;
+        if (has_out2) {
+          float g[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) g[k] = lrelu(s_s2[col0 + cb * 16 + k] * f[k] + s_t2[col0 + cb * 16 + k]);
+          *reinterpret_cast<uint4*>(o2 + c0) = valid ? pack8(&g[0]) : z;
+          *reinterpret_cast<uint4*>(o2 + c1) = valid ? pack8(&g[8]) : z;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tm_out, col0, row0, stg_u32 + (uint32_t)b * 2048u);
+        if (has_out2) tma_store_2d(&tm_out2, col0, row0, stg_u32 + 4096u);
+        bulk_commit();
+      }
+    }
+    if (lane == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -744,12 +1123,12 @@ static int fill_geometry(aznn::ConvParams& p, int32_t board0, int32_t boards, in
   return 0;
 }
 
-template <bool STEM, int CG>
+template <int MODE, int CG>
 static int launch_conv(const aznn::ConvParams& p, int n_ctas, void* stream) {
   using namespace aznn;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv<STEM, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::TOTAL);
     if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
     attr_set = true;
   }
@@ -783,17 +1162,106 @@ static int launch_conv(const aznn::ConvParams& p, int n_ctas, void* stream) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<STEM, CG>, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<MODE, CG>, p);
   if (e != cudaSuccess) return nn_fail(-2, "k_conv launch", e);
   e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_conv launch", e);
   return 0;
 }
 
-extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                             const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
-                             int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu,
-                             int32_t n_ctas, void* stream) {
+// ---- TMA path: tensor maps are encoded on the host per launch (pure CPU work; baked into a captured graph's parameters)
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tmap(CUtensorMap* m, const void* base, int rows_alloc, int box_c, int box_r, CUtensorMapSwizzle sw) {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !f) return nn_fail(-2, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)", e);
+    fn = (PFN_tmapEncodeTiled)f;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)aznn::CH, (cuuint64_t)rows_alloc};
+  const cuuint64_t gstr[1] = {(cuuint64_t)aznn::CH * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
+  const cuuint32_t est[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, est,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -2;
+  }
+  return 0;
+}
+
+template <bool FDX, int NE, int S>
+static int launch_conv_tma(const aznn::ConvParams& c, int n_ctas, void* stream) {
+  using namespace aznn;
+  using L = TmaSmem<FDX, NE, S>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tma<FDX, NE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
+    attr_set = true;
+  }
+  const int halo = FDX ? c.Wp : c.Wp + 1;
+  CUtensorMap tm_in, tm_res, tm_out, tm_out2;
+  if (make_tmap(&tm_in, c.in, c.rows_alloc, CH, TILE_M + 2 * halo, CU_TENSOR_MAP_SWIZZLE_128B)) return -2;
+  if (make_tmap(&tm_out, c.out, c.rows_alloc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
+  if (make_tmap(&tm_res, c.res ? c.res : c.out, c.rows_alloc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
+  if (make_tmap(&tm_out2, c.out2 ? c.out2 : c.out, c.rows_alloc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
+  TmaConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.wpack = c.wpack;
+  p.bias = c.bias;
+  p.s2 = c.s2;
+  p.t2 = c.t2;
+  p.skip_obs = c.skip_obs;
+  p.skip_w = c.skip_w;
+  p.n_tiles = c.n_tiles;
+  p.lead = c.lead;
+  p.boards = c.boards;
+  p.P = c.P;
+  p.Wp = c.Wp;
+  p.H = c.H;
+  p.W = c.W;
+  p.board0 = c.board0;
+  p.tile0 = c.tile0;
+  p.lrelu = c.lrelu;
+  p.has_res = c.res != nullptr;
+  p.has_out2 = c.out2 != nullptr;
+  p.debug = c.debug;
+  int grid = n_ctas > 0 ? n_ctas : 148;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((2 + NE) * 32);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv_tma<FDX, NE, S>, tm_in, tm_res, tm_out, tm_out2, p);
+  if (e != cudaSuccess) return nn_fail(-2, "k_conv_tma launch", e);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return nn_fail(-2, "k_conv_tma launch", e);
+  return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* ev = getenv(name);
+  return ev ? atoi(ev) : dflt;
+}
+
+static int conv_entry(bool dx_fused, const void* in, const void* wpack, const float* bias, const void* res, void* out,
+                      void* out2, const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
+                      int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t n_ctas,
+                      void* stream) {
   using namespace aznn;
   if (!in || !wpack || !bias || !out) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: null argument");
@@ -831,7 +1299,21 @@ extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bia
     use_pair = ev ? atoi(ev) : 0;  // measured on B200 (scripts/conv_microbench.py): the cta_group::2 pair halves the B
                                    // fetch but couples two CTAs' pipelines: 76/97/122 us vs 70/78/93 us single-CTA
   }
-  return use_pair ? launch_conv<false, 2>(p, n_ctas, stream) : launch_conv<false, 1>(p, n_ctas, stream);
+  if (dx_fused && (p.Wp != 8 || lead % 8 != 0)) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3_w7: needs W == 7 (row pitch 8) and lead %% 8 == 0");
+    return -1;
+  }
+  static int use_tma = -1, ne = 12;
+  if (use_tma < 0) {
+    use_tma = env_int("AZ_NN_TMA", 1);
+    ne = env_int("AZ_NN_NE", 12);
+  }
+  if (use_tma) {
+    if (dx_fused) return ne == 16 ? launch_conv_tma<true, 16, 3>(p, n_ctas, stream) : launch_conv_tma<true, 12, 4>(p, n_ctas, stream);
+    return launch_conv_tma<false, 12, 4>(p, n_ctas, stream);
+  }
+  if (dx_fused) return launch_conv<MODE_DX, 1>(p, n_ctas, stream);
+  return use_pair ? launch_conv<MODE_CONV, 2>(p, n_ctas, stream) : launch_conv<MODE_CONV, 1>(p, n_ctas, stream);
 }
 
 extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st,
@@ -853,7 +1335,7 @@ extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, c
   p.lrelu = 1;
   p.stem_st = bn_st;
   if (fill_geometry(p, board0, boards, H, W, lead, rows_alloc, "az_nn_stem")) return -1;
-  return launch_conv<true, 1>(p, n_ctas, stream);
+  return launch_conv<MODE_STEM, 1>(p, n_ctas, stream);
 }
 
 extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t board0,
@@ -891,4 +1373,20 @@ extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_head launch", e);
   return 0;
+}
+
+extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
+                             const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
+                             int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu,
+                             int32_t n_ctas, void* stream) {
+  return conv_entry(false, in, wpack, bias, res, out, out2, s2, t2, skip_obs, skip_w, board0, boards, H, W, lead, rows_alloc,
+                    lrelu, n_ctas, stream);
+}
+
+extern "C" int az_nn_conv3x3_w7(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
+                                const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
+                                int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu,
+                                int32_t n_ctas, void* stream) {
+  return conv_entry(true, in, wpack, bias, res, out, out2, s2, t2, skip_obs, skip_w, board0, boards, H, W, lead, rows_alloc,
+                    lrelu, n_ctas, stream);
 }

@@ -38,6 +38,18 @@ def pack_conv3x3(w):
     return out.contiguous().to(torch.bfloat16)
 
 
+def pack_conv3x3_w7(w):
+    """Same weights for az_nn_conv3x3_w7: bf16 [3 ky][192 = kx*64 + n][8 chunks][8], SWIZZLE_128B K-major per row."""
+    co, ci = w.shape[0], w.shape[1]
+    assert co == CH and ci == CH
+    t = w.permute(2, 3, 0, 1).reshape(3, 3 * co, 8, 8)       # [ky][kx*64 + n][chunk][k%8]
+    n = torch.arange(3 * co).view(1, 3 * co, 1)
+    c = torch.arange(8).view(1, 1, 8)
+    src_chunk = (c ^ (n & 7)).expand(3, 3 * co, 8)
+    out = torch.gather(t, 2, src_chunk.unsqueeze(-1).expand(3, 3 * co, 8, 8).to(t.device))
+    return out.contiguous().to(torch.bfloat16)
+
+
 class FusedEvaluator:
     def __init__(self, net, batch, device, n_ctas=0, slice_boards=0):
         self.lib = L.load()
@@ -64,6 +76,8 @@ class FusedEvaluator:
         self.par = None
         # small action spaces (Connect Four) finish with the streaming k_head kernel; larger ones with a cuBLAS GEMM
         self.fused_head = self.A + 1 <= 8 and 8 * (self.P * 8 + 4) * 16 <= 100 * 1024 and os.environ.get("AZ_NN_HEAD", "1") != "0"
+        # width-7 boards (row pitch 8) take the dx-fused N = 192 conv kernel
+        self.w7 = self.Wp == 8 and LEAD % 8 == 0 and os.environ.get("AZ_NN_W7", "1") != "0"
         self.fuse_skip = os.environ.get("AZ_NN_SKIPFUSE", "1") != "0"
         self.timing = None   # set to a list to collect (kernel, start_event, end_event) per launch (bench.py roofline)
         self.load(net)
@@ -89,7 +103,8 @@ class FusedEvaluator:
             bias2[:N_FILTERS] = c2b
             w2p = torch.zeros((CH, CH, 3, 3), dtype=torch.float64)
             w2p[:N_FILTERS, :N_FILTERS] = w2
-            new["w2_%d" % k] = pack_conv3x3(w2p)
+            pack = pack_conv3x3_w7 if self.w7 else pack_conv3x3
+            new["w2_%d" % k] = pack(w2p)
             new["b2_%d" % k] = bias2.float()
             new["b1_%d" % k] = bias1.float()
             if k == 0:
@@ -111,7 +126,7 @@ class FusedEvaluator:
             else:
                 w1p = torch.zeros((CH, CH, 3, 3), dtype=torch.float64)
                 w1p[:N_FILTERS, :N_FILTERS] = w1
-                new["w1_%d" % k] = pack_conv3x3(w1p)
+                new["w1_%d" % k] = pack(w1p)
                 s = torch.zeros(CH, dtype=torch.float64)
                 t = torch.zeros(CH, dtype=torch.float64)
                 s[:N_FILTERS], t[:N_FILTERS] = a1, b1
@@ -151,7 +166,8 @@ class FusedEvaluator:
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         name = "conv" + ("+res" if res is not None else "") + ("+skip" if skip_obs is not None else "") + \
             ("+out2" if out2 is not None else "")
-        rc = self._timed(name, lambda: self.lib.az_nn_conv3x3(
+        fn = self.lib.az_nn_conv3x3_w7 if self.w7 else self.lib.az_nn_conv3x3
+        rc = self._timed(name, lambda: fn(
             p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), p(skip_obs), p(skip_w), b0, nb, self.h, self.w,
             LEAD, self.rows_alloc, 1 if lrelu else 0, self.n_ctas, self._stream()))
         if rc:

@@ -242,6 +242,9 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  *   tcgen05 implicit GEMM; n_ctas <= 0 -> one CTA per SM.  With skip_obs (the az_step observation batch) and skip_w
  *   [64][4] fp32 the epilogue adds the 1x1 skip projection of the raw planes (resblock1.conv3, network.py:101-103) instead
  *   of reading a residual tensor, so the stem never has to write one.
+ * az_nn_conv3x3_w7: the same operator for boards of width 7 (padded row pitch 8, Connect Four; lead % 8 == 0): the three
+ *   dx taps of a kernel row are one MMA of N = 192 and are recombined by the epilogue, so the activation slab is fetched
+ *   from shared memory 3x instead of 9x per tile.  wpack is [3 ky][192 = kx*64 + n][8][8] bf16, SWIZZLE_128B as above.
  * az_nn_stem: the 4-plane first block on the same tcgen05 kernel (the slab is built from the az_step
  *   AZ_OBS_BF16_NHWC batch [boards][H][W][4]): u = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1), r = conv1x1(x) + b3
  *   (network.py:99-103 for resblock1; r may be NULL when the next conv computes the projection itself).  wpack is [9 taps][2][128][8] bf16: rows 0-63 = conv1 (BatchNorm folded) on
@@ -256,6 +259,10 @@ int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const vo
                   const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
                   int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t n_ctas,
                   void* stream);
+int az_nn_conv3x3_w7(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
+                     const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
+                     int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t n_ctas,
+                     void* stream);
 int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st, void* u,
                void* r, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc,
                int32_t n_ctas, void* stream);

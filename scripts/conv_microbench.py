@@ -2,7 +2,8 @@
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alphazero_openspiel_b200 import _lib as L
-from alphazero_openspiel_b200.nn_fused import pack_conv3x3, LEAD
+from alphazero_openspiel_b200.nn_fused import pack_conv3x3, pack_conv3x3_w7, LEAD
+W7 = os.environ.get("AZ_NN_W7", "1") != "0"
 lib = L.load()
 dev = torch.device("cuda:0")
 B, H, W = 16384, 6, 7
@@ -12,13 +13,14 @@ x = torch.randn((rows, 64), device=dev).to(torch.bfloat16)
 r = torch.randn((rows, 64), device=dev).to(torch.bfloat16)
 o = torch.zeros((rows, 64), dtype=torch.bfloat16, device=dev)
 o2 = torch.zeros((rows, 64), dtype=torch.bfloat16, device=dev)
-w = pack_conv3x3(torch.randn(64, 64, 3, 3) * 0.05).to(dev)
+w = (pack_conv3x3_w7 if W7 else pack_conv3x3)(torch.randn(64, 64, 3, 3) * 0.05).to(dev)
+conv = lib.az_nn_conv3x3_w7 if W7 else lib.az_nn_conv3x3
 b = torch.randn(64, device=dev); s2 = torch.rand(64, device=dev); t2 = torch.randn(64, device=dev)
 p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for name, res, out2 in [("conv1-type", None, None), ("conv2+res", r, None), ("conv2+res+out2", r, o2)]:
     def run():
-        rc = lib.az_nn_conv3x3(p(x), p(w), p(b), p(res), p(o), p(out2), p(s2) if out2 is not None else None,
+        rc = conv(p(x), p(w), p(b), p(res), p(o), p(out2), p(s2) if out2 is not None else None,
                                p(t2) if out2 is not None else None, None, None, 0, B, H, W, LEAD, rows, 1 if res is None else 0, 0, st)
         assert rc == 0
     for _ in range(3): run()
@@ -26,4 +28,4 @@ for name, res, out2 in [("conv1-type", None, None), ("conv2+res", r, None), ("co
     e0.record()
     for _ in range(20): run()
     e1.record(); torch.cuda.synchronize()
-    print("AZ_NN_DEBUG=%s %-16s %.1f us" % (os.environ.get("AZ_NN_DEBUG", "0"), name, e0.elapsed_time(e1) / 20 * 1e3))
+    print("W7=%d AZ_NN_DEBUG=%s %-16s %.1f us" % (W7, os.environ.get("AZ_NN_DEBUG", "0"), name, e0.elapsed_time(e1) / 20 * 1e3))

@@ -25,16 +25,18 @@ def _nchw_from_padded(buf, lead, B, H, W):
     return t[:, :H, :W, :].permute(0, 3, 1, 2).contiguous(), t
 
 
-@pytest.mark.parametrize("H,W,B", [(6, 7, 37), (6, 6, 300), (8, 8, 129), (6, 7, 4096)])
-def test_conv3x3_tcgen05_matches_torch(H, W, B):
+@pytest.mark.parametrize("H,W,B,w7", [(6, 7, 37, 0), (6, 6, 300, 0), (8, 8, 129, 0), (6, 7, 4096, 0),
+                                       (6, 7, 37, 1), (6, 7, 4096, 1), (5, 7, 1000, 1)])
+def test_conv3x3_tcgen05_matches_torch(H, W, B, w7):
     """out = conv3x3(in) + bias [-> LeakyReLU] [+ res], out2 = LeakyReLU(s2*out+t2); pad rows stay exactly zero.
     Tolerance: inputs/weights are bf16-exact on both sides, accumulation fp32 -> only the final bf16 rounding differs
     (rel 2^-8) plus fp32 summation-order noise."""
     import torch
     import torch.nn.functional as F
     from alphazero_openspiel_b200 import _lib as L
-    from alphazero_openspiel_b200.nn_fused import pack_conv3x3, LEAD
+    from alphazero_openspiel_b200.nn_fused import pack_conv3x3, pack_conv3x3_w7, LEAD
     lib = L.load()
+    conv = lib.az_nn_conv3x3_w7 if w7 else lib.az_nn_conv3x3     # w7: the dx-fused N = 192 kernel for row pitch 8
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(H * 100 + W + B)
     x = torch.randn((B, 64, H, W), generator=g).to(dev).to(torch.bfloat16).float()
@@ -47,16 +49,16 @@ def test_conv3x3_tcgen05_matches_torch(H, W, B):
     rows_alloc = (LEAD + B * P + W + 2 + 127) // 128 * 128
     xin = _padded_from_nchw(x, LEAD, rows_alloc)
     rin = _padded_from_nchw(res, LEAD, rows_alloc)
-    wp = pack_conv3x3(w).to(dev)
+    wp = (pack_conv3x3_w7 if w7 else pack_conv3x3)(w).to(dev)
     ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     ref = F.conv2d(x, w, bias, padding=1)
     for lrelu, use_res, use_out2 in [(0, 0, 0), (1, 0, 0), (0, 1, 1), (0, 1, 0)]:
         out = torch.zeros((rows_alloc, 64), dtype=torch.bfloat16, device=dev)   # pads are zero from allocation
         out2 = torch.zeros((rows_alloc, 64), dtype=torch.bfloat16, device=dev) if use_out2 else None
-        rc = lib.az_nn_conv3x3(ptr(xin), ptr(wp), ptr(bias), ptr(rin) if use_res else None, ptr(out), ptr(out2),
-                               ptr(s2) if use_out2 else None, ptr(t2) if use_out2 else None, None, None, 0, B, H, W, LEAD,
-                               rows_alloc, lrelu, 0, st)
+        rc = conv(ptr(xin), ptr(wp), ptr(bias), ptr(rin) if use_res else None, ptr(out), ptr(out2),
+                  ptr(s2) if use_out2 else None, ptr(t2) if use_out2 else None, None, None, 0, B, H, W, LEAD,
+                  rows_alloc, lrelu, 0, st)
         assert rc == 0, lib.az_nn_last_error()
         torch.cuda.synchronize()
         want = ref
