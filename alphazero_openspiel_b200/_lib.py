@@ -45,6 +45,8 @@ class EngineUnavailable(RuntimeError):
 
 _VP, _I32P, _U64P, _F64P = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p  # raw addresses (torch data_ptr / ctypes)
 
+NN_F_REVERSE = 1
+
 SIGNATURES = {
     "az_last_error": (C.c_char_p, []),
     "az_version": (C.c_int, []),
@@ -72,8 +74,8 @@ SIGNATURES = {
     "az_game_random_playouts": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, _I32P,
                                           _I32P, _VP]),
     "az_nn_last_error": (C.c_char_p, []),
-    "az_nn_conv3x3": (C.c_int, [_VP] * 10 + [C.c_int32] * 8 + [_VP]),
-    "az_nn_conv3x3_w7": (C.c_int, [_VP] * 10 + [C.c_int32] * 8 + [_VP]),
+    "az_nn_conv3x3": (C.c_int, [_VP] * 10 + [C.c_int32] * 9 + [_VP]),
+    "az_nn_conv3x3_w7": (C.c_int, [_VP] * 10 + [C.c_int32] * 9 + [_VP]),
     "az_nn_stem": (C.c_int, [_VP] * 7 + [C.c_int32] * 7 + [_VP]),
     "az_nn_head": (C.c_int, [_VP] * 5 + [C.c_int32] * 8 + [_VP]),
 }

@@ -73,6 +73,7 @@ struct ConvParams {
   int tile0;                  // first 128-row tile of that range
   int lrelu;                  // apply LeakyReLU to (acc + bias)
   int debug;                  // experiments: 1 = producers skip loads, 2 = epilogue skips math+stores, 4 = no MMAs
+  int flags;                  // AZ_NN_F_*
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -690,6 +691,9 @@ struct TmaConvParams {
   const float* skip_w;
   int n_tiles, lead, boards, P, Wp, H, W, board0, tile0;
   int lrelu, has_res, has_out2, debug;
+  int reverse;   // walk the tiles from the last to the first: the input was written front-to-back by the previous layer, so
+                 // its most recently written (still L2-resident) part is read first
+  int l2_hints;  // evict-first on the (dead after this read) inputs, evict-last on the outputs the next layer reads
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -699,6 +703,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(tm), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* tm, int c0, int c1, uint32_t src, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(tm), "r"(src),
+               "r"(c0), "r"(c1), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
@@ -790,7 +815,10 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
   const int halo = FDX ? p.Wp : p.Wp + 1;
   const int slab_rows = TILE_M + 2 * halo;
   const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto tile_of = [&](int it) { return p.tile0 + (int)blockIdx.x + it * (int)gridDim.x; };
+  auto tile_of = [&](int it) {
+    const int t = (int)blockIdx.x + it * (int)gridDim.x;
+    return p.tile0 + (p.reverse ? p.n_tiles - 1 - t : t);
+  };
   const long long range_lo = (long long)p.lead + (long long)p.board0 * p.P;
   const int range_len = p.boards * p.P;
   const int valid_pos = p.H * p.Wp;
@@ -802,6 +830,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         bulk_g2s(s_w + (uint32_t)i * (W_BYTES / 3), reinterpret_cast<const uint8_t*>(p.wpack) + i * (W_BYTES / 3), W_BYTES / 3, bar_w());
+      const uint64_t pol_first = l2_policy_evict_first();
       asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are the previous layer's output
       for (int it = 0; it < my_tiles; ++it) {
         const int stage = it % S;
@@ -810,7 +839,10 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
           mbar_arrive(bar_full(stage));
         } else {
           mbar_expect_tx(bar_full(stage), (uint32_t)slab_rows * 128u);
-          tma_load_2d(s_a + (uint32_t)stage * L::A_ST, &tm_in, 0, tile_of(it) * TILE_M - halo, bar_full(stage));
+          if (p.l2_hints)
+            tma_load_2d_hint(s_a + (uint32_t)stage * L::A_ST, &tm_in, 0, tile_of(it) * TILE_M - halo, bar_full(stage), pol_first);
+          else
+            tma_load_2d(s_a + (uint32_t)stage * L::A_ST, &tm_in, 0, tile_of(it) * TILE_M - halo, bar_full(stage));
         }
       }
     }
@@ -896,6 +928,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
       }
       return v;
     };
+    const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
     asm volatile("griddepcontrol.wait;" ::: "memory");  // residual reads / output writes depend on the previous layer
     uint2 xnext = make_uint2(0u, 0u);
     bool vnext = false;
@@ -903,7 +936,10 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
       vnext = row_info(j0, xnext);
       if (has_res && !skip_all && lane == 0) {
         mbar_expect_tx(bar_res(e, 0), 2048u);
-        tma_load_2d(stg_u32, &tm_res, (j0 & 1) * 32, tile_of(j0 >> 1) * TILE_M + q * 32, bar_res(e, 0));
+        if (p.l2_hints)
+          tma_load_2d_hint(stg_u32, &tm_res, (j0 & 1) * 32, tile_of(j0 >> 1) * TILE_M + q * 32, bar_res(e, 0), pol_first);
+        else
+          tma_load_2d(stg_u32, &tm_res, (j0 & 1) * 32, tile_of(j0 >> 1) * TILE_M + q * 32, bar_res(e, 0));
       }
     }
     for (int i = j0, n = 0; i < n_items; i += NEQ, ++n) {
@@ -948,8 +984,12 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
         vnext = row_info(inext, xnext);
         if (has_res && lane == 0) {
           mbar_expect_tx(bar_res(e, b ^ 1), 2048u);
-          tma_load_2d(stg_u32 + (uint32_t)(b ^ 1) * 2048u, &tm_res, (inext & 1) * 32, tile_of(inext >> 1) * TILE_M + q * 32,
-                      bar_res(e, b ^ 1));
+          if (p.l2_hints)
+            tma_load_2d_hint(stg_u32 + (uint32_t)(b ^ 1) * 2048u, &tm_res, (inext & 1) * 32,
+                             tile_of(inext >> 1) * TILE_M + q * 32, bar_res(e, b ^ 1), pol_first);
+          else
+            tma_load_2d(stg_u32 + (uint32_t)(b ^ 1) * 2048u, &tm_res, (inext & 1) * 32, tile_of(inext >> 1) * TILE_M + q * 32,
+                        bar_res(e, b ^ 1));
         }
       }
       if (has_res) mbar_wait(bar_res(e, b), (uint32_t)(n >> 1) & 1u);
@@ -997,8 +1037,18 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(&tm_out, col0, row0, stg_u32 + (uint32_t)b * 2048u);
-        if (has_out2) tma_store_2d(&tm_out2, col0, row0, stg_u32 + 4096u);
+        if (p.l2_hints) {
+          // with two outputs the residual stream (out) is read two layers later: only out2 is worth keeping
+          if (has_out2) {
+            tma_store_2d(&tm_out, col0, row0, stg_u32 + (uint32_t)b * 2048u);
+            tma_store_2d_hint(&tm_out2, col0, row0, stg_u32 + 4096u, pol_last);
+          } else {
+            tma_store_2d_hint(&tm_out, col0, row0, stg_u32 + (uint32_t)b * 2048u, pol_last);
+          }
+        } else {
+          tma_store_2d(&tm_out, col0, row0, stg_u32 + (uint32_t)b * 2048u);
+          if (has_out2) tma_store_2d(&tm_out2, col0, row0, stg_u32 + 4096u);
+        }
         bulk_commit();
       }
     }
@@ -1169,6 +1219,11 @@ static int launch_conv(const aznn::ConvParams& p, int n_ctas, void* stream) {
   return 0;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* ev = getenv(name);
+  return ev ? atoi(ev) : dflt;
+}
+
 // ---- TMA path: tensor maps are encoded on the host per launch (pure CPU work; baked into a captured graph's parameters)
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1233,6 +1288,8 @@ static int launch_conv_tma(const aznn::ConvParams& c, int n_ctas, void* stream) 
   p.has_res = c.res != nullptr;
   p.has_out2 = c.out2 != nullptr;
   p.debug = c.debug;
+  p.reverse = (c.flags & AZ_NN_F_REVERSE) != 0 && env_int("AZ_NN_REV", 1);
+  p.l2_hints = env_int("AZ_NN_L2HINT", 1);
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid > p.n_tiles) grid = p.n_tiles;
   cudaLaunchConfig_t cfg;
@@ -1253,15 +1310,11 @@ static int launch_conv_tma(const aznn::ConvParams& c, int n_ctas, void* stream) 
   return 0;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* ev = getenv(name);
-  return ev ? atoi(ev) : dflt;
-}
 
 static int conv_entry(bool dx_fused, const void* in, const void* wpack, const float* bias, const void* res, void* out,
                       void* out2, const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
-                      int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t n_ctas,
-                      void* stream) {
+                      int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t flags,
+                      int32_t n_ctas, void* stream) {
   using namespace aznn;
   if (!in || !wpack || !bias || !out) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: null argument");
@@ -1284,6 +1337,7 @@ static int conv_entry(bool dx_fused, const void* in, const void* wpack, const fl
     return -1;
   }
   p.lrelu = lrelu;
+  p.flags = flags;
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -1378,15 +1432,15 @@ extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float
 extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
                              const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
                              int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu,
-                             int32_t n_ctas, void* stream) {
+                             int32_t flags, int32_t n_ctas, void* stream) {
   return conv_entry(false, in, wpack, bias, res, out, out2, s2, t2, skip_obs, skip_w, board0, boards, H, W, lead, rows_alloc,
-                    lrelu, n_ctas, stream);
+                    lrelu, flags, n_ctas, stream);
 }
 
 extern "C" int az_nn_conv3x3_w7(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
                                 const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
                                 int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu,
-                                int32_t n_ctas, void* stream) {
+                                int32_t flags, int32_t n_ctas, void* stream) {
   return conv_entry(true, in, wpack, bias, res, out, out2, s2, t2, skip_obs, skip_w, board0, boards, H, W, lead, rows_alloc,
-                    lrelu, n_ctas, stream);
+                    lrelu, flags, n_ctas, stream);
 }

@@ -162,14 +162,14 @@ class FusedEvaluator:
         self.timing.append((name, e0, e1))
         return rc
 
-    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, b0, nb, skip_obs=None, skip_w=None):
+    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, b0, nb, skip_obs=None, skip_w=None, flags=0):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         name = "conv" + ("+res" if res is not None else "") + ("+skip" if skip_obs is not None else "") + \
             ("+out2" if out2 is not None else "")
         fn = self.lib.az_nn_conv3x3_w7 if self.w7 else self.lib.az_nn_conv3x3
         rc = self._timed(name, lambda: fn(
             p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), p(skip_obs), p(skip_w), b0, nb, self.h, self.w,
-            LEAD, self.rows_alloc, 1 if lrelu else 0, self.n_ctas, self._stream()))
+            LEAD, self.rows_alloc, 1 if lrelu else 0, flags, self.n_ctas, self._stream()))
         if rc:
             raise RuntimeError("az_nn_conv3x3: " + self.lib.az_nn_last_error().decode())
 
@@ -188,14 +188,18 @@ class FusedEvaluator:
             if self.fuse_skip:
                 # block 1, second conv: X = conv(U) + conv1x1(obs) ; T = lrelu(bn1_2(X))   (skip projection in the epilogue)
                 self._conv(self.U, P_["w2_0"], P_["b2skip_0"], None, self.X, self.T, P_["s_1"], P_["t_1"], False, b0, nb,
-                           skip_obs=self.obs, skip_w=P_["skip_w"])
+                           skip_obs=self.obs, skip_w=P_["skip_w"], flags=L.NN_F_REVERSE)
             else:
-                self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False, b0, nb)
+                self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False, b0, nb,
+                           flags=L.NN_F_REVERSE)
             for k in range(1, 5):
+                # layers alternate their tile direction: each reads its input starting from the part the previous layer
+                # wrote last (still in L2); the stem writes front to back, so the first conv goes back to front
                 self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True, b0, nb)
                 last = k == 4
                 self._conv(self.U, P_["w2_%d" % k], P_["b2_%d" % k], self.X, self.X, None if last else self.T,
-                           None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False, b0, nb)
+                           None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False, b0, nb,
+                           flags=L.NN_F_REVERSE)
             if self.fused_head:
                 rc = self._timed("head", lambda: self.lib.az_nn_head(
                     p(self.X), p(P_["hw"]), p(P_["hb"]), p(self.priors), p(self.values), b0, nb, self.h, self.w, LEAD,

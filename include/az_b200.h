@@ -254,15 +254,17 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  *   over the padded-rows flatten of one board (zero on pad cells / pad channels / unused outputs), bias fp32 [8].
  *   All kernels work on boards [board0, board0+boards) of the full buffers and never read or write pad rows or rows of
  *   other boards (pads must be zero from allocation). */
+#define AZ_NN_F_REVERSE 1 /* walk the 128-row tiles back to front (alternate per layer: the tail of the previous layer's
+                             output is still in L2) */
 const char* az_nn_last_error(void);
 int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
                   const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
-                  int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t n_ctas,
-                  void* stream);
+                  int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t flags,
+                  int32_t n_ctas, void* stream);
 int az_nn_conv3x3_w7(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
                      const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
-                     int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t n_ctas,
-                     void* stream);
+                     int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t flags,
+                     int32_t n_ctas, void* stream);
 int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st, void* u,
                void* r, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc,
                int32_t n_ctas, void* stream);

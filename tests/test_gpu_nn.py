@@ -58,7 +58,7 @@ def test_conv3x3_tcgen05_matches_torch(H, W, B, w7):
         out2 = torch.zeros((rows_alloc, 64), dtype=torch.bfloat16, device=dev) if use_out2 else None
         rc = conv(ptr(xin), ptr(wp), ptr(bias), ptr(rin) if use_res else None, ptr(out), ptr(out2),
                   ptr(s2) if use_out2 else None, ptr(t2) if use_out2 else None, None, None, 0, B, H, W, LEAD,
-                  rows_alloc, lrelu, 0, st)
+                  rows_alloc, lrelu, use_res, 0, st)   # flags: the residual variants also run back to front
         assert rc == 0, lib.az_nn_last_error()
         torch.cuda.synchronize()
         want = ref
