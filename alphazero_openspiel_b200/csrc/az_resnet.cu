@@ -518,11 +518,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
     // residual rows of the NEXT tile are prefetched into registers while the current tile is processed
     uint4 rnext[4];
     uint32_t vmask_next = 0;
+    int urow_next = 0;  // STEM: index of this thread's cell in the [boards][H+1][W] outputs
     auto prefetch = [&](int it) {
       const int tile = tile_of(it);
       const long long m_warp = (long long)tile * TILE_M + q * 32;
       const bool v = qrow_next >= 0 && qrow_next < range_len && pos_next < valid_pos && (pos_next % p.Wp) < p.W;
       vmask_next = __ballot_sync(0xffffffffu, v);
+      if constexpr (STEM) {
+        urow_next = 0;
+        if (v) urow_next = (p.board0 + qrow_next / p.P) * (cells + p.W) + (pos_next / p.Wp) * p.W + pos_next % p.Wp;
+      }
       if (has_skip) {  // this row's 4 observation planes (for the 1x1 skip projection)
         xnext = make_uint2(0u, 0u);
         if (v) {
@@ -549,6 +554,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
       const long long m_warp = (long long)tile * TILE_M + q * 32;
       // Invalid rows (pads, other launches' boards) are never loaded or stored.
       const uint32_t vmask = vmask_next;
+      const int urow = urow_next;
       const uint2 xrow = xnext;
       if (has_res) {
 #pragma unroll
@@ -634,7 +640,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
         }
       }
       __syncwarp();
-      {  // coalesced copy-out of the valid rows
+      if constexpr (STEM) {  // copy-out of the valid rows into the [boards][H+1][W][64] tensors (4 lanes move one 64-byte half row)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + crow;
+          const long long ur = __shfl_sync(0xffffffffu, urow, r);
+          if ((vmask >> r) & 1u) {
+            reinterpret_cast<uint4*>(p.out + ur * CH + col0)[cch] =
+                *reinterpret_cast<const uint4*>(stg_out + r * SmemLayout::STG_ROW + cch * 16);
+            if (p.out2 != nullptr)
+              reinterpret_cast<uint4*>(p.out2 + ur * CH + col0)[cch] =
+                  *reinterpret_cast<const uint4*>(stg_out2 + r * SmemLayout::STG_ROW + cch * 16);
+          }
+        }
+      } else {  // coalesced copy-out of the valid rows
         uint4* op = reinterpret_cast<uint4*>(p.out + m_warp * CH + col0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -670,64 +689,29 @@ teardown:
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_conv_tma: the 64-channel 3x3 conv with TMA on both sides of the tensor core.
-//   warp 0      one thread: bulk-copies the weight image, then one cp.async.bulk.tensor (SWIZZLE_128B box of
-//               128 + 2*halo activation rows) per tile into a ring of S smem stages
-//   warp 1      MMA issuer (tcgen05.mma, accumulators in TMEM), as in k_conv
-//   warps 2..   NE epilogue warps.  A work item is (tile, 32-row TMEM lane quarter, 32-channel half); the NE/4 warps of a
-//               quarter take items round-robin, so several tiles' epilogues are in flight per scheduler.  Residual rows
-//               arrive by TMA (SWIZZLE_64B box of 32 rows x 32 channels, one item ahead), the result is written in place
-//               and leaves by TMA store; every row of the tile is stored, pad rows as zeros, so no per-row predicates
-//               and no LDS/STG copy-out.  (Launches therefore own whole 128-row tiles: no board slices here.)
-// Pad cells of the activation buffers are zero in global memory (never written with anything else), so the loader needs
-// no zero-fill logic: a tap that leaves the board always lands on a pad cell.
+// k_conv8: the 64-channel 3x3 conv on NHWC activations [boards][H+1][W][64] (bf16; board row H is a zero pad row that
+// separates consecutive boards, there are no pad columns in global memory).
+//
+// Inside the SM a board is laid out on a "pitch-8" virtual row space: cell (r, c) of board b is virtual row
+// b*P + r*8 + c with P = (H+1)*8, i.e. every board row is a group of 8 rows (columns c >= W are pad cells).  The pad
+// columns exist only in shared memory: activations move through a 3-D tensor map (channel, c, row group = b*(H+1) + r)
+// whose boxes are 8 columns wide - the TMA unit zero-fills c >= W on loads and clips it on stores; the same goes for row
+// groups before the first / after the last board.  A tile is 128 consecutive virtual rows (16 groups); its slab is the tile
+// plus one group above and below: ONE box of (64, 8, 18).
+//
+// Tensor core: the three dx taps of a kernel row share ONE A view and become the N dimension,
+//   D[v][dx*64 + co] = sum_dy,k A[v + dy*8][k] W(dy,dx)[k][co]          (12 MMAs of M128 N192 K16 per tile)
+// and the epilogue recombines out[v] = D_-1[v-1] + D_0[v] + D_+1[v+1] with one-lane warp shuffles (a 32-row TMEM lane
+// quarter starts at c = 0, so the only cross-quarter neighbours are the masked c = 0 / c = 7 ones).
+//
+//   warp 0      one thread: bulk-copies the weight image, then 18 group loads per tile into a ring of S smem stages
+//   warp 1      MMA issuer (tcgen05.mma, two 192-column accumulators in TMEM)
+//   warps 2..   NE epilogue warps; a work item is (tile, 32-row lane quarter, 32-channel half) and the NE/4 warps of a
+//               quarter take items round-robin.  Residual rows arrive by TMA one item ahead, the result is written in place
+//               into the staging buffer (SWIZZLE_64B, row per thread, conflict-free) and leaves by TMA store.
 // ---------------------------------------------------------------------------------------------------------------------
-struct TmaConvParams {
-  const __nv_bfloat16* wpack;
-  const float* bias;
-  const float* s2;
-  const float* t2;
-  const uint2* skip_obs;
-  const float* skip_w;
-  int n_tiles, lead, boards, P, Wp, H, W, board0, tile0;
-  int lrelu, has_res, has_out2, debug;
-  int reverse;   // walk the tiles from the last to the first: the input was written front-to-back by the previous layer, so
-                 // its most recently written (still L2-resident) part is read first
-  int l2_hints;  // evict-first on the (dead after this read) inputs, evict-last on the outputs the next layer reads
-};
-
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-               "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1), "l"(pol)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* tm, int c0, int c1, uint32_t src, uint64_t pol) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(tm), "r"(src),
-               "r"(c0), "r"(c1), "l"(pol)
-               : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -738,33 +722,57 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <bool FDX, int NE, int S>
-struct TmaSmem {
-  static constexpr int A_ST = (FDX ? 144 : 152) * 128;   // one slab: 128 + 2*halo rows of 128 B
+struct Conv8Params {
+  const __nv_bfloat16* wpack;
+  const float* bias;
+  const float* s2;
+  const float* t2;
+  const uint2* skip_obs;
+  const float* skip_w;
+  int n_tiles, boards, P, H, W, HP;  // HP = H + 1 row groups per board
+  int lrelu, has_res, has_out2, debug, reverse;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+
+constexpr int C8_GROUPS = 18;                 // 8-row groups per slab: 16 of the tile + one above + one below
+constexpr int C8_A_ST = C8_GROUPS * 1024;     // 18,432 B per stage
+constexpr int C8_N = 192;
+
+template <int NE, int S>
+struct Conv8Smem {
   static constexpr int W_OFF = 0;
   static constexpr int A_OFF = W_BYTES;
-  static constexpr int STG_OFF = A_OFF + S * A_ST;       // per epilogue warp: io[2] (residual in / result out), out2
+  static constexpr int STG_OFF = A_OFF + S * C8_A_ST;    // per epilogue warp: io[2] (residual in / result out), out2
   static constexpr int STG_WARP = 3 * 2048;
   static constexpr int BIAS_OFF = STG_OFF + NE * STG_WARP;
   static constexpr int S2_OFF = BIAS_OFF + 256;
   static constexpr int T2_OFF = S2_OFF + 256;
   static constexpr int SKIPW_OFF = T2_OFF + 256;
-  static constexpr int BAR_OFF = SKIPW_OFF + 1024;       // full[S] empty[S] tfull[4] tempty[4] w resbar[NE][2]
-  static constexpr int N_BARS = 2 * S + 9 + 2 * NE;
+  static constexpr int BAR_OFF = SKIPW_OFF + 1024;       // full[S] empty[S] tfull[2] tempty[2] w resbar[NE][2]
+  static constexpr int N_BARS = 2 * S + 5 + 2 * NE;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <bool FDX, int NE, int S>
+template <int NE, int S>
 __global__ void __launch_bounds__((2 + NE) * 32, 1)
-k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_res,
-           const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2, const TmaConvParams p) {
-  using L = TmaSmem<FDX, NE, S>;
-  constexpr int N_MMA = FDX ? 192 : 64;
+k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_res,
+        const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2, const Conv8Params p) {
+  using L = Conv8Smem<NE, S>;
   constexpr int K_STEPS = 4;
-  constexpr int W_TAP_BYTES = N_MMA * 16 * 2 * K_STEPS;
-  constexpr int ACC = FDX ? 2 : 4;
-  constexpr uint32_t TMEM_COLS = FDX ? 512u : 256u;
+  constexpr int W_ROW_BYTES = C8_N * 16 * 2 * K_STEPS;   // one kernel row (dy) of weights: 24,576 B
+  constexpr int ACC = 2;
+  constexpr uint32_t TMEM_COLS = 512u;
   constexpr int NEQ = NE / 4;                            // epilogue warps per TMEM lane quarter
   static_assert(NE % 4 == 0, "whole quarters");
 
@@ -779,9 +787,9 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
   auto bar_full = [&](int s) { return s_bar + 8u * s; };
   auto bar_empty = [&](int s) { return s_bar + 8u * (S + s); };
   auto bar_tfull = [&](int a) { return s_bar + 8u * (2 * S + a); };
-  auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * S + 4 + a); };
-  auto bar_w = [&]() { return s_bar + 8u * (2 * S + 8); };
-  auto bar_res = [&](int e, int b) { return s_bar + 8u * (2 * S + 9 + 2 * e + b); };
+  auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * S + 2 + a); };
+  auto bar_w = [&]() { return s_bar + 8u * (2 * S + 4); };
+  auto bar_res = [&](int e, int b) { return s_bar + 8u * (2 * S + 5 + 2 * e + b); };
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + L::N_BARS * 8);
 
   if (warp == 1 && lane == 0) {
@@ -812,16 +820,11 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
   const uint32_t tmem_base = *s_tmem;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int halo = FDX ? p.Wp : p.Wp + 1;
-  const int slab_rows = TILE_M + 2 * halo;
   const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   auto tile_of = [&](int it) {
     const int t = (int)blockIdx.x + it * (int)gridDim.x;
-    return p.tile0 + (p.reverse ? p.n_tiles - 1 - t : t);
+    return p.reverse ? p.n_tiles - 1 - t : t;
   };
-  const long long range_lo = (long long)p.lead + (long long)p.board0 * p.P;
-  const int range_len = p.boards * p.P;
-  const int valid_pos = p.H * p.Wp;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -829,8 +832,7 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
       mbar_expect_tx(bar_w(), (uint32_t)W_BYTES);
 #pragma unroll
       for (int i = 0; i < 3; ++i)
-        bulk_g2s(s_w + (uint32_t)i * (W_BYTES / 3), reinterpret_cast<const uint8_t*>(p.wpack) + i * (W_BYTES / 3), W_BYTES / 3, bar_w());
-      const uint64_t pol_first = l2_policy_evict_first();
+        bulk_g2s(s_w + (uint32_t)i * W_ROW_BYTES, reinterpret_cast<const uint8_t*>(p.wpack) + i * W_ROW_BYTES, W_ROW_BYTES, bar_w());
       asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are the previous layer's output
       for (int it = 0; it < my_tiles; ++it) {
         const int stage = it % S;
@@ -838,52 +840,39 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
         if (p.debug & 1) {
           mbar_arrive(bar_full(stage));
         } else {
-          mbar_expect_tx(bar_full(stage), (uint32_t)slab_rows * 128u);
-          if (p.l2_hints)
-            tma_load_2d_hint(s_a + (uint32_t)stage * L::A_ST, &tm_in, 0, tile_of(it) * TILE_M - halo, bar_full(stage), pol_first);
-          else
-            tma_load_2d(s_a + (uint32_t)stage * L::A_ST, &tm_in, 0, tile_of(it) * TILE_M - halo, bar_full(stage));
+          // group -1 of the first tile and the groups past the last board are out of range: they arrive as zeros
+          mbar_expect_tx(bar_full(stage), (uint32_t)C8_A_ST);
+          tma_load_3d(s_a + (uint32_t)stage * C8_A_ST, &tm_in, 0, 0, tile_of(it) * 16 - 1, bar_full(stage));
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)N_MMA);
-    uint32_t dlt[9];  // byte offset of each tap's A view inside a stage
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) dlt[tap] = (uint32_t)(halo + (tap / 3 - 1) * p.Wp + (FDX ? 0 : tap % 3 - 1)) * 128u;
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)C8_N);
     mbar_wait(bar_w(), 0u);
     for (int it = 0; it < my_tiles; ++it) {
       const int stage = it % S, acc = it % ACC;
       mbar_wait(bar_full(stage), (uint32_t)(it / S) & 1u);
       mbar_wait(bar_tempty(acc), ((uint32_t)(it / ACC) & 1u) ^ 1u);
       tc_fence_after();
+      // elect.sync (not `lane == 0`): the compiler then knows exactly one lane issues and keeps the descriptors in
+      // uniform registers instead of wrapping every tcgen05.mma in an ELECT / BRA.U.ANY serialisation loop.
       if (elect_one()) {
-        const uint32_t d = tmem_base + (uint32_t)(acc * N_MMA);
-        const uint32_t a_stage = s_a + (uint32_t)stage * L::A_ST;
-        if (p.debug & 4) {
-          // (experiment) no MMAs
-        } else if constexpr (FDX) {
+        const uint32_t d = tmem_base + (uint32_t)(acc * C8_N);
+        const uint32_t a_stage = s_a + (uint32_t)stage * C8_A_ST;
+        if (!(p.debug & 4)) {
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
-            const uint64_t at = umma_desc_sw128(a_stage + dlt[dy * 3]);
-            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)dy * (uint32_t)W_TAP_BYTES);
+            // SW128: every virtual row is its own 128-byte line, so the dy view is the slab shifted by whole groups
+            const uint64_t at = umma_desc_sw128(a_stage + (uint32_t)dy * 1024u);
+            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)dy * (uint32_t)W_ROW_BYTES);
 #pragma unroll
             for (int j = 0; j < K_STEPS; ++j)
               umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (dy | j) != 0 ? 1u : 0u);
           }
-        } else {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t at = umma_desc_sw128(a_stage + dlt[tap]);
-            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)tap * (uint32_t)W_TAP_BYTES);
-#pragma unroll
-            for (int j = 0; j < K_STEPS; ++j)
-              umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (tap | j) != 0 ? 1u : 0u);
-          }
         }
-        umma_commit(bar_empty(stage));
-        umma_commit(bar_tfull(acc));
+        umma_commit(bar_empty(stage));  // smem stage reusable once these MMAs have read it
+        umma_commit(bar_tfull(acc));    // accumulator ready for the epilogue
       }
       __syncwarp();
     }
@@ -913,64 +902,50 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
     const uint32_t row_off = (uint32_t)lane * 64u;
     const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
     const bool skip_all = (p.debug & 2) != 0;
+    const int cc = lane & 7;                         // board column of this thread's row (quarters start at c = 0)
+    const bool up_ok = cc != 0, dn_ok = cc != p.W - 1;
 
-    // validity + observation planes of this thread's row in item i
-    auto row_info = [&](int i, uint2& x) -> bool {
-      const int tile = tile_of(i >> 1);
-      const long long qr = (long long)tile * TILE_M + q * 32 + lane - range_lo;
-      bool v = qr >= 0 && qr < range_len;
-      x = make_uint2(0u, 0u);
-      if (v) {
-        const int b = (int)qr / p.P, pos = (int)qr - b * p.P;
-        const int rr = pos / p.Wp, cc = pos - rr * p.Wp;
-        v = pos < valid_pos && cc < p.W;
-        if (v && has_skip) x = p.skip_obs[(long long)(p.board0 + b) * cells + rr * p.W + cc];
-      }
-      return v;
+    // observation planes of this thread's row in item i (for the fused 1x1 skip projection)
+    auto obs_of = [&](int i) -> uint2 {
+      const int g = tile_of(i >> 1) * 16 + q * 4 + (lane >> 3);
+      const int b = g / p.HP, r = g - b * p.HP;
+      if (b < p.boards && r < p.H && cc < p.W) return p.skip_obs[(long long)b * cells + r * p.W + cc];
+      return make_uint2(0u, 0u);
     };
-    const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+    // the four row groups of item i arrive as one (32 ch, 8, 4) box
+    auto load_res = [&](int i, int buf) {
+      mbar_expect_tx(bar_res(e, buf), 2048u);
+      tma_load_3d(stg_u32 + (uint32_t)buf * 2048u, &tm_res, (i & 1) * 32, 0, tile_of(i >> 1) * 16 + q * 4, bar_res(e, buf));
+    };
     asm volatile("griddepcontrol.wait;" ::: "memory");  // residual reads / output writes depend on the previous layer
     uint2 xnext = make_uint2(0u, 0u);
-    bool vnext = false;
     if (j0 < n_items) {
-      vnext = row_info(j0, xnext);
-      if (has_res && !skip_all && lane == 0) {
-        mbar_expect_tx(bar_res(e, 0), 2048u);
-        if (p.l2_hints)
-          tma_load_2d_hint(stg_u32, &tm_res, (j0 & 1) * 32, tile_of(j0 >> 1) * TILE_M + q * 32, bar_res(e, 0), pol_first);
-        else
-          tma_load_2d(stg_u32, &tm_res, (j0 & 1) * 32, tile_of(j0 >> 1) * TILE_M + q * 32, bar_res(e, 0));
-      }
+      if (has_skip) xnext = obs_of(j0);
+      if (has_res && !skip_all && lane == 0) load_res(j0, 0);
     }
     for (int i = j0, n = 0; i < n_items; i += NEQ, ++n) {
       const int it = i >> 1, half = i & 1, acc = it % ACC, b = n & 1;
       const int col0 = half * 32;
-      const int row0 = tile_of(it) * TILE_M + q * 32;
-      const bool valid = vnext;
       const uint2 xrow = xnext;
+      const int g0 = tile_of(it) * 16 + q * 4;                   // first row group of this quarter
+      const bool pad_row = (g0 + (lane >> 3)) % p.HP == p.H;      // this thread's row lies in a board's zero pad row
       mbar_wait(bar_tfull(acc), (uint32_t)(it / ACC) & 1u);
       tc_fence_after();
       uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_MMA + col0);
-      if constexpr (FDX) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C8_N + col0);
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
-          uint32_t dm[16], d0[16], dp[16];
-          tmem_ld16(taddr + (uint32_t)(cb * 16), dm);
-          tmem_ld16(taddr + (uint32_t)(64 + cb * 16), d0);
-          tmem_ld16(taddr + (uint32_t)(128 + cb * 16), dp);
-          tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(dm[k]), 1);
-            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(dp[k]), 1);
-            v[cb * 16 + k] = __float_as_uint(__uint_as_float(d0[k]) + (lane != 0 ? up : 0.f) + (lane != 31 ? dn : 0.f));
-          }
-        }
-      } else {
-        tmem_ld16(taddr, &v[0]);
-        tmem_ld16(taddr + 16u, &v[16]);
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t dm[16], d0[16], dp[16];
+        tmem_ld16(taddr + (uint32_t)(cb * 16), dm);
+        tmem_ld16(taddr + (uint32_t)(64 + cb * 16), d0);
+        tmem_ld16(taddr + (uint32_t)(128 + cb * 16), dp);
         tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(dm[k]), 1);
+          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(dp[k]), 1);
+          v[cb * 16 + k] = __float_as_uint(__uint_as_float(d0[k]) + (up_ok ? up : 0.f) + (dn_ok ? dn : 0.f));
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -981,16 +956,8 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
       __syncwarp();
       const int inext = i + NEQ;
       if (inext < n_items) {
-        vnext = row_info(inext, xnext);
-        if (has_res && lane == 0) {
-          mbar_expect_tx(bar_res(e, b ^ 1), 2048u);
-          if (p.l2_hints)
-            tma_load_2d_hint(stg_u32 + (uint32_t)(b ^ 1) * 2048u, &tm_res, (inext & 1) * 32,
-                             tile_of(inext >> 1) * TILE_M + q * 32, bar_res(e, b ^ 1), pol_first);
-          else
-            tma_load_2d(stg_u32 + (uint32_t)(b ^ 1) * 2048u, &tm_res, (inext & 1) * 32, tile_of(inext >> 1) * TILE_M + q * 32,
-                        bar_res(e, b ^ 1));
-        }
+        if (has_skip) xnext = obs_of(inext);
+        if (has_res && lane == 0) load_res(inext, b ^ 1);
       }
       if (has_res) mbar_wait(bar_res(e, b), (uint32_t)(n >> 1) & 1u);
       uint8_t* io = stg + b * 2048 + row_off;
@@ -1023,32 +990,23 @@ k_conv_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CU
             f[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
           }
         }
+        // pad columns hold don't-care values (the store clips them); the pad row is stored and must stay zero
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(io + c0) = valid ? pack8(&f[0]) : z;
-        *reinterpret_cast<uint4*>(io + c1) = valid ? pack8(&f[8]) : z;
+        *reinterpret_cast<uint4*>(io + c0) = pad_row ? z : pack8(&f[0]);
+        *reinterpret_cast<uint4*>(io + c1) = pad_row ? z : pack8(&f[8]);
         if (has_out2) {
           float g[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) g[k] = lrelu(s_s2[col0 + cb * 16 + k] * f[k] + s_t2[col0 + cb * 16 + k]);
-          *reinterpret_cast<uint4*>(o2 + c0) = valid ? pack8(&g[0]) : z;
-          *reinterpret_cast<uint4*>(o2 + c1) = valid ? pack8(&g[8]) : z;
+          *reinterpret_cast<uint4*>(o2 + c0) = pad_row ? z : pack8(&g[0]);
+          *reinterpret_cast<uint4*>(o2 + c1) = pad_row ? z : pack8(&g[8]);
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        if (p.l2_hints) {
-          // with two outputs the residual stream (out) is read two layers later: only out2 is worth keeping
-          if (has_out2) {
-            tma_store_2d(&tm_out, col0, row0, stg_u32 + (uint32_t)b * 2048u);
-            tma_store_2d_hint(&tm_out2, col0, row0, stg_u32 + 4096u, pol_last);
-          } else {
-            tma_store_2d_hint(&tm_out, col0, row0, stg_u32 + (uint32_t)b * 2048u, pol_last);
-          }
-        } else {
-          tma_store_2d(&tm_out, col0, row0, stg_u32 + (uint32_t)b * 2048u);
-          if (has_out2) tma_store_2d(&tm_out2, col0, row0, stg_u32 + 4096u);
-        }
+        tma_store_3d(&tm_out, col0, 0, g0, stg_u32 + (uint32_t)b * 2048u);
+        if (has_out2) tma_store_3d(&tm_out2, col0, 0, g0, stg_u32 + 4096u);
         bulk_commit();
       }
     }
@@ -1224,12 +1182,15 @@ static int env_int(const char* name, int dflt) {
   return ev ? atoi(ev) : dflt;
 }
 
-// ---- TMA path: tensor maps are encoded on the host per launch (pure CPU work; baked into a captured graph's parameters)
+// ---- tensor maps are encoded on the host per launch (pure CPU work; baked into a captured graph's kernel parameters)
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tmap(CUtensorMap* m, const void* base, int rows_alloc, int box_c, int box_r, CUtensorMapSwizzle sw) {
+// 3-D view (channel, board column, row group = board*(H+1) + board row) of an activation tensor [boards][H+1][W][64] bf16;
+// boxes are 8 columns wide: c >= W is out of range -> zero-filled on loads, clipped on stores
+static int make_tmap_act(CUtensorMap* m, const void* base, int boards, int H, int W, int box_ch, int box_groups,
+                         CUtensorMapSwizzle sw) {
   static PFN_tmapEncodeTiled fn = nullptr;
   if (!fn) {
     void* f = nullptr;
@@ -1238,11 +1199,12 @@ static int make_tmap(CUtensorMap* m, const void* base, int rows_alloc, int box_c
     if (e != cudaSuccess || !f) return nn_fail(-2, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)", e);
     fn = (PFN_tmapEncodeTiled)f;
   }
-  const cuuint64_t gdim[2] = {(cuuint64_t)aznn::CH, (cuuint64_t)rows_alloc};
-  const cuuint64_t gstr[1] = {(cuuint64_t)aznn::CH * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
-  const cuuint32_t est[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, est,
+  const cuuint64_t row = (cuuint64_t)aznn::CH * 2;
+  const cuuint64_t gdim[3] = {(cuuint64_t)aznn::CH, (cuuint64_t)W, (cuuint64_t)boards * (H + 1)};
+  const cuuint64_t gstr[2] = {row, row * W};
+  const cuuint32_t box[3] = {(cuuint32_t)box_ch, 8u, (cuuint32_t)box_groups};
+  const cuuint32_t est[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, est,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_nn_err, sizeof(g_nn_err), "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -1251,45 +1213,17 @@ static int make_tmap(CUtensorMap* m, const void* base, int rows_alloc, int box_c
   return 0;
 }
 
-template <bool FDX, int NE, int S>
-static int launch_conv_tma(const aznn::ConvParams& c, int n_ctas, void* stream) {
+template <int NE, int S>
+static int launch_conv8(const CUtensorMap& tm_in, const CUtensorMap& tm_res, const CUtensorMap& tm_out, const CUtensorMap& tm_out2,
+                        const aznn::Conv8Params& p, int n_ctas, void* stream) {
   using namespace aznn;
-  using L = TmaSmem<FDX, NE, S>;
+  using L = Conv8Smem<NE, S>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_tma<FDX, NE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv8<NE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
     attr_set = true;
   }
-  const int halo = FDX ? c.Wp : c.Wp + 1;
-  CUtensorMap tm_in, tm_res, tm_out, tm_out2;
-  if (make_tmap(&tm_in, c.in, c.rows_alloc, CH, TILE_M + 2 * halo, CU_TENSOR_MAP_SWIZZLE_128B)) return -2;
-  if (make_tmap(&tm_out, c.out, c.rows_alloc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
-  if (make_tmap(&tm_res, c.res ? c.res : c.out, c.rows_alloc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
-  if (make_tmap(&tm_out2, c.out2 ? c.out2 : c.out, c.rows_alloc, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
-  TmaConvParams p;
-  memset(&p, 0, sizeof(p));
-  p.wpack = c.wpack;
-  p.bias = c.bias;
-  p.s2 = c.s2;
-  p.t2 = c.t2;
-  p.skip_obs = c.skip_obs;
-  p.skip_w = c.skip_w;
-  p.n_tiles = c.n_tiles;
-  p.lead = c.lead;
-  p.boards = c.boards;
-  p.P = c.P;
-  p.Wp = c.Wp;
-  p.H = c.H;
-  p.W = c.W;
-  p.board0 = c.board0;
-  p.tile0 = c.tile0;
-  p.lrelu = c.lrelu;
-  p.has_res = c.res != nullptr;
-  p.has_out2 = c.out2 != nullptr;
-  p.debug = c.debug;
-  p.reverse = (c.flags & AZ_NN_F_REVERSE) != 0 && env_int("AZ_NN_REV", 1);
-  p.l2_hints = env_int("AZ_NN_L2HINT", 1);
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid > p.n_tiles) grid = p.n_tiles;
   cudaLaunchConfig_t cfg;
@@ -1302,77 +1236,58 @@ static int launch_conv_tma(const aznn::ConvParams& c, int n_ctas, void* stream) 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv_tma<FDX, NE, S>, tm_in, tm_res, tm_out, tm_out2, p);
-  if (e != cudaSuccess) return nn_fail(-2, "k_conv_tma launch", e);
+  cfg.numAttrs = env_int("AZ_NN_PDL", 1) ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv8<NE, S>, tm_in, tm_res, tm_out, tm_out2, p);
+  if (e != cudaSuccess) return nn_fail(-2, "k_conv8 launch", e);
   e = cudaGetLastError();
-  if (e != cudaSuccess) return nn_fail(-2, "k_conv_tma launch", e);
+  if (e != cudaSuccess) return nn_fail(-2, "k_conv8 launch", e);
   return 0;
 }
 
-
-static int conv_entry(bool dx_fused, const void* in, const void* wpack, const float* bias, const void* res, void* out,
-                      void* out2, const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
-                      int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t flags,
-                      int32_t n_ctas, void* stream) {
+extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
+                             const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t boards,
+                             int32_t H, int32_t W, int32_t lrelu, int32_t flags, int32_t n_ctas, void* stream) {
   using namespace aznn;
   if (!in || !wpack || !bias || !out) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: null argument");
     return -1;
   }
-  ConvParams p;
+  if (boards <= 0 || H < 3 || H > 16 || W < 2 || W > 8 || (skip_obs && !skip_w)) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: needs boards > 0, 3 <= H <= 16, 2 <= W <= 8, skip_w with skip_obs");
+    return -1;
+  }
+  Conv8Params p;
   memset(&p, 0, sizeof(p));
-  p.in = (const __nv_bfloat16*)in;
   p.wpack = (const __nv_bfloat16*)wpack;
   p.bias = bias;
-  p.res = (const __nv_bfloat16*)res;
-  p.out = (__nv_bfloat16*)out;
-  p.out2 = (__nv_bfloat16*)out2;
   p.s2 = s2;
   p.t2 = t2;
   p.skip_obs = (const uint2*)skip_obs;
   p.skip_w = skip_obs ? skip_w : nullptr;
-  if (skip_obs && !skip_w) {
-    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: skip_obs needs skip_w");
-    return -1;
-  }
+  p.boards = boards;
+  p.H = H;
+  p.W = W;
+  p.HP = H + 1;
+  p.P = p.HP * 8;
+  p.n_tiles = (int)(((long long)boards * p.P + TILE_M - 1) / TILE_M);
   p.lrelu = lrelu;
-  p.flags = flags;
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("AZ_NN_DEBUG");
-      dbg = e ? atoi(e) : 0;
-    }
-    p.debug = dbg;
-  }
-  if (fill_geometry(p, board0, boards, H, W, lead, rows_alloc, "az_nn_conv3x3")) return -1;
-  static int use_pair = -1;
-  if (use_pair < 0) {
-    const char* ev = getenv("AZ_NN_PAIR");
-    use_pair = ev ? atoi(ev) : 0;  // measured on B200 (scripts/conv_microbench.py): the cta_group::2 pair halves the B
-                                   // fetch but couples two CTAs' pipelines: 76/97/122 us vs 70/78/93 us single-CTA
-  }
-  if (dx_fused && (p.Wp != 8 || lead % 8 != 0)) {
-    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3_w7: needs W == 7 (row pitch 8) and lead %% 8 == 0");
-    return -1;
-  }
-  static int use_tma = -1, ne = 12;
-  if (use_tma < 0) {
-    use_tma = env_int("AZ_NN_TMA", 1);
-    ne = env_int("AZ_NN_NE", 12);
-  }
-  if (use_tma) {
-    if (dx_fused) return ne == 16 ? launch_conv_tma<true, 16, 3>(p, n_ctas, stream) : launch_conv_tma<true, 12, 4>(p, n_ctas, stream);
-    return launch_conv_tma<false, 12, 4>(p, n_ctas, stream);
-  }
-  if (dx_fused) return launch_conv<MODE_DX, 1>(p, n_ctas, stream);
-  return use_pair ? launch_conv<MODE_CONV, 2>(p, n_ctas, stream) : launch_conv<MODE_CONV, 1>(p, n_ctas, stream);
+  p.has_res = res != nullptr;
+  p.has_out2 = out2 != nullptr;
+  p.debug = env_int("AZ_NN_DEBUG", 0);
+  p.reverse = (flags & AZ_NN_F_REVERSE) != 0 && env_int("AZ_NN_REV", 1);
+  CUtensorMap tm_in, tm_res, tm_out, tm_out2;
+  if (make_tmap_act(&tm_in, in, boards, H, W, CH, C8_GROUPS, CU_TENSOR_MAP_SWIZZLE_128B)) return -2;
+  if (make_tmap_act(&tm_res, res ? res : out, boards, H, W, 32, 4, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
+  if (make_tmap_act(&tm_out, out, boards, H, W, 32, 4, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
+  if (make_tmap_act(&tm_out2, out2 ? out2 : out, boards, H, W, 32, 4, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
+  static int ne = -1;
+  if (ne < 0) ne = env_int("AZ_NN_NE", 12);
+  return ne == 16 ? launch_conv8<16, 3>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream)
+                  : launch_conv8<12, 4>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream);
 }
 
 extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st,
-                          void* u, void* r, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead,
-                          int32_t rows_alloc, int32_t n_ctas, void* stream) {
+                          void* u, void* r, int32_t boards, int32_t H, int32_t W, int32_t n_ctas, void* stream) {
   using namespace aznn;
   if (!obs || !wpack || !b1 || !b3 || !bn_st || !u) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_stem: null argument");
@@ -1388,25 +1303,29 @@ extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, c
   p.t2 = b3;
   p.lrelu = 1;
   p.stem_st = bn_st;
-  if (fill_geometry(p, board0, boards, H, W, lead, rows_alloc, "az_nn_stem")) return -1;
+  p.debug = env_int("AZ_NN_DEBUG", 0);
+  // the stem tiles its own virtual row space (pitch W+1, 16 lead rows); only the stores address the [boards][H+1][W][64] outputs
+  const int lead = 16;
+  const long long rows = (long long)lead + (long long)boards * (H + 1) * (W + 1) + W + 2;
+  if (rows > 0x7fffff00LL) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_stem: too many boards");
+    return -1;
+  }
+  if (fill_geometry(p, 0, boards, H, W, lead, (int)((rows + TILE_M - 1) / TILE_M * TILE_M), "az_nn_stem")) return -1;
   return launch_conv<MODE_STEM, 1>(p, n_ctas, stream);
 }
 
-extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t board0,
-                          int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t n_actions,
-                          int32_t n_ctas, void* stream) {
+extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t boards,
+                          int32_t H, int32_t W, int32_t n_actions, int32_t n_ctas, void* stream) {
   using namespace aznn;
   if (!x || !w || !bias || !priors || !values) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head: null argument");
     return -1;
   }
-  const int P = (H + 1) * (W + 1);
-  const int chunks = P * CH / 8;
+  const int chunks = (H + 1) * W * CH / 8;
   const size_t smem = (size_t)HEAD_OUT * (chunks + HEAD_WPAD) * 16;
-  if (n_actions < 1 || n_actions + 1 > HEAD_OUT || smem > 100 * 1024 || board0 < 0 || boards <= 0 || (lead * CH) % 8 != 0 ||
-      (long long)lead + (long long)(board0 + boards) * P > rows_alloc) {
-    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head: needs n_actions + 1 <= %d, (H+1)*(W+1)*1024 <= 100 KB, boards in range",
-             HEAD_OUT);
+  if (n_actions < 1 || n_actions + 1 > HEAD_OUT || smem > 100 * 1024 || boards <= 0 || chunks % 4 != 0) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head: needs n_actions + 1 <= %d and (H+1)*W*1024 <= 100 KB", HEAD_OUT);
     return -1;
   }
   static size_t smem_set = 0;
@@ -1421,26 +1340,9 @@ extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float
   if (grid > need) grid = need;
   // plain launch: measured on B200, letting k_head start under programmatic dependent launch behind the last conv costs
   // ~2% of the step (its CTAs take the SM slots the conv's tail and the concurrent k_compact want)
-  const uint4* xp = reinterpret_cast<const uint4*>((const __nv_bfloat16*)x + (long long)lead * CH);
-  k_head<<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>(xp, (const uint4*)w, bias, priors, values, (int)board0, (int)boards,
+  k_head<<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)w, bias, priors, values, 0, (int)boards,
                                                              chunks, (int)n_actions);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_head launch", e);
   return 0;
-}
-
-extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                             const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
-                             int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu,
-                             int32_t flags, int32_t n_ctas, void* stream) {
-  return conv_entry(false, in, wpack, bias, res, out, out2, s2, t2, skip_obs, skip_w, board0, boards, H, W, lead, rows_alloc,
-                    lrelu, flags, n_ctas, stream);
-}
-
-extern "C" int az_nn_conv3x3_w7(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                                const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
-                                int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu,
-                                int32_t flags, int32_t n_ctas, void* stream) {
-  return conv_entry(true, in, wpack, bias, res, out, out2, s2, t2, skip_obs, skip_w, board0, boards, H, W, lead, rows_alloc,
-                    lrelu, flags, n_ctas, stream);
 }

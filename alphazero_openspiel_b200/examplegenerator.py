@@ -147,7 +147,7 @@ class SelfPlayRunner:
                  dirichlet_ratio=0.25, temperature=1.0, num_probabilistic_actions=1000, keep_search_tree=True,
                  backup="on-policy", seed=0, max_games=0, auto_restart=True, random_start_mod=0,
                  max_sims_per_step=8, records=True, use_graph=True, noise_mode=None, node_capacity=0,
-                 record_capacity=0, evaluator="fused", nn_slice=0, **_ignored):
+                 record_capacity=0, evaluator="fused", **_ignored):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.EngineUnavailable("SelfPlayRunner needs a CUDA device; there is no CPU fallback")
@@ -178,7 +178,7 @@ class SelfPlayRunner:
                                  record_capacity=record_capacity)
             if evaluator == "fused":      # hand-written tcgen05 convs (csrc/az_resnet.cu)
                 from .nn_fused import FusedEvaluator
-                self.evaluator = FusedEvaluator(net, n_trees, self.device, slice_boards=nn_slice)
+                self.evaluator = FusedEvaluator(net, n_trees, self.device)
             elif evaluator == "torch":    # cuDNN/cuBLAS through PyTorch (numerics reference for the fused path)
                 self.evaluator = BatchedEvaluator(net, n_trees, self.device, use_graph=False)
             else:

@@ -2,10 +2,11 @@
 
 Same contract as network.BatchedEvaluator -- obs bf16 [B,H,W,4] (written by az_step) -> priors fp32 [B,A], values
 fp32 [B] -- but the ten 3x3 convolutions run as tcgen05 implicit GEMMs with BatchNorm / LeakyReLU / bias / residual
-fused into their epilogues (11 launches instead of ~45 PyTorch kernels), on bf16 "padded rows" activations
+fused into their epilogues (11 launches instead of ~45 PyTorch kernels), on NHWC bf16 activations [B,H+1,W,64] (row H
+of every board is a zero pad row)
 (see az_resnet.cu).  Host code here only folds/packs weights and sequences the launches.  The FC head is the streaming
 k_head kernel (FC + softmax + tanh in one launch, fp32 logits) when A + 1 <= 8 (Connect Four); for larger action spaces
-it is a plain [B, P*64] x [P*64, A+1] GEMM and stays a cuBLAS call through torch, with softmax/tanh on its output.
+it is a plain [B, (H+1)*W*64] x [(H+1)*W*64, A+1] GEMM and stays a cuBLAS call through torch, with softmax/tanh on its output.
 
 Per evaluation:   stem(obs) -> U
                   X = conv(U) + conv1x1(obs), T = lrelu(bn1_2(X))      (block 1, conv2; skip projection in its epilogue)
@@ -22,62 +23,44 @@ from . import _lib as L
 from .network import N_FILTERS, _fold_bn
 
 CH = 64
-LEAD = 16
 
 
 def pack_conv3x3(w):
-    """[64 out][64 in][3][3] (any float dtype, already zero-padded) -> bf16 [9][64 n][8 chunks][8] UMMA operand image
-    in the SWIZZLE_128B K-major layout: row n is 128 B, its 16-byte chunk c is stored at chunk position c ^ (n & 7)."""
-    co, ci = w.shape[0], w.shape[1]
-    assert co == CH and ci == CH
-    t = w.permute(2, 3, 0, 1).reshape(9, co, 8, 8)           # [tap][n][chunk][k%8]
-    n = torch.arange(co).view(1, co, 1)
-    c = torch.arange(8).view(1, 1, 8)
-    src_chunk = (c ^ (n & 7)).expand(9, co, 8)               # position p holds chunk p ^ (n & 7)
-    out = torch.gather(t, 2, src_chunk.unsqueeze(-1).expand(9, co, 8, 8).to(t.device))
-    return out.contiguous().to(torch.bfloat16)
-
-
-def pack_conv3x3_w7(w):
-    """Same weights for az_nn_conv3x3_w7: bf16 [3 ky][192 = kx*64 + n][8 chunks][8], SWIZZLE_128B K-major per row."""
+    """[64 out][64 in][3][3] (any float dtype, already zero-padded) -> bf16 [3 ky][192 = kx*64 + n][8 chunks][8]: the UMMA
+    B operand image of az_nn_conv3x3, SWIZZLE_128B K-major: row (kx, n) is the 128 B of input channels, its 16-byte chunk
+    c is stored at chunk position c ^ (n & 7)."""
     co, ci = w.shape[0], w.shape[1]
     assert co == CH and ci == CH
     t = w.permute(2, 3, 0, 1).reshape(3, 3 * co, 8, 8)       # [ky][kx*64 + n][chunk][k%8]
     n = torch.arange(3 * co).view(1, 3 * co, 1)
     c = torch.arange(8).view(1, 1, 8)
-    src_chunk = (c ^ (n & 7)).expand(3, 3 * co, 8)
+    src_chunk = (c ^ (n & 7)).expand(3, 3 * co, 8)           # position p holds chunk p ^ (n & 7)
     out = torch.gather(t, 2, src_chunk.unsqueeze(-1).expand(3, 3 * co, 8, 8).to(t.device))
     return out.contiguous().to(torch.bfloat16)
 
 
 class FusedEvaluator:
-    def __init__(self, net, batch, device, n_ctas=0, slice_boards=0):
+    def __init__(self, net, batch, device, n_ctas=0):
         self.lib = L.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.EngineUnavailable("FusedEvaluator needs a CUDA device; there is no CPU fallback")
         self.batch = batch
         self.h, self.w, self.A = net.height, net.width, net.num_distinct_actions
-        self.Wp = self.w + 1
-        self.P = (self.h + 1) * self.Wp
+        if not (3 <= self.h <= 16 and 2 <= self.w <= 8):
+            raise ValueError("FusedEvaluator supports boards with 3 <= H <= 16 and 2 <= W <= 8")
         self.n_ctas = n_ctas
-        # optional board slices (measured: per-launch overhead outweighs L2 residency, so the default is one slice)
-        slice_boards = batch if slice_boards <= 0 else slice_boards
-        self.slices = [(b0, min(slice_boards, batch - b0)) for b0 in range(0, batch, slice_boards)]
-        rows = LEAD + batch * self.P + self.Wp + 1
-        self.rows_alloc = (rows + 127) // 128 * 128
         dev = self.device
-        self.U = torch.zeros((self.rows_alloc, CH), dtype=torch.bfloat16, device=dev)
-        self.X = torch.zeros((self.rows_alloc, CH), dtype=torch.bfloat16, device=dev)
-        self.T = torch.zeros((self.rows_alloc, CH), dtype=torch.bfloat16, device=dev)
+        self.U = torch.zeros((batch, self.h + 1, self.w, CH), dtype=torch.bfloat16, device=dev)
+        self.X = torch.zeros((batch, self.h + 1, self.w, CH), dtype=torch.bfloat16, device=dev)
+        self.T = torch.zeros((batch, self.h + 1, self.w, CH), dtype=torch.bfloat16, device=dev)
         self.obs = torch.zeros((batch, self.h, self.w, 4), dtype=torch.bfloat16, device=dev)
         self.priors = torch.zeros((batch, self.A), dtype=torch.float32, device=dev)
         self.values = torch.zeros((batch,), dtype=torch.float32, device=dev)
         self.par = None
         # small action spaces (Connect Four) finish with the streaming k_head kernel; larger ones with a cuBLAS GEMM
-        self.fused_head = self.A + 1 <= 8 and 8 * (self.P * 8 + 4) * 16 <= 100 * 1024 and os.environ.get("AZ_NN_HEAD", "1") != "0"
-        # width-7 boards (row pitch 8) take the dx-fused N = 192 conv kernel
-        self.w7 = self.Wp == 8 and LEAD % 8 == 0 and os.environ.get("AZ_NN_W7", "1") != "0"
+        self.fused_head = self.A + 1 <= 8 and 8 * ((self.h + 1) * self.w * 8 + 4) * 16 <= 100 * 1024 and \
+            os.environ.get("AZ_NN_HEAD", "1") != "0"
         self.fuse_skip = os.environ.get("AZ_NN_SKIPFUSE", "1") != "0"
         self.timing = None   # set to a list to collect (kernel, start_event, end_event) per launch (bench.py roofline)
         self.load(net)
@@ -103,8 +86,7 @@ class FusedEvaluator:
             bias2[:N_FILTERS] = c2b
             w2p = torch.zeros((CH, CH, 3, 3), dtype=torch.float64)
             w2p[:N_FILTERS, :N_FILTERS] = w2
-            pack = pack_conv3x3_w7 if self.w7 else pack_conv3x3
-            new["w2_%d" % k] = pack(w2p)
+            new["w2_%d" % k] = pack_conv3x3(w2p)
             new["b2_%d" % k] = bias2.float()
             new["b1_%d" % k] = bias1.float()
             if k == 0:
@@ -126,19 +108,19 @@ class FusedEvaluator:
             else:
                 w1p = torch.zeros((CH, CH, 3, 3), dtype=torch.float64)
                 w1p[:N_FILTERS, :N_FILTERS] = w1
-                new["w1_%d" % k] = pack(w1p)
+                new["w1_%d" % k] = pack_conv3x3(w1p)
                 s = torch.zeros(CH, dtype=torch.float64)
                 t = torch.zeros(CH, dtype=torch.float64)
                 s[:N_FILTERS], t[:N_FILTERS] = a1, b1
                 new["s_%d" % k], new["t_%d" % k] = s.float(), t.float()   # bn1 of block k, applied by block k-1's epilogue
-        # FC head over the padded-rows flatten: [A+1][P][64]
+        # FC head over the flatten of one board: [A+1][H+1][W][64] (zero on the pad row)
         fw = net.fc1.weight.double().cpu().view(self.A + 1, N_FILTERS, self.h, self.w)
-        fwp = torch.zeros((self.A + 1, self.h + 1, self.Wp, CH), dtype=torch.float64)
-        fwp[:, :self.h, :self.w, :N_FILTERS] = fw.permute(0, 2, 3, 1)
+        fwp = torch.zeros((self.A + 1, self.h + 1, self.w, CH), dtype=torch.float64)
+        fwp[:, :self.h, :, :N_FILTERS] = fw.permute(0, 2, 3, 1)
         new["fw"] = fwp.reshape(self.A + 1, -1).to(torch.bfloat16)
         new["fb"] = net.fc1.bias.double().cpu().float()
-        if self.fused_head:   # k_head operand: [8 outputs][P*64] bf16 (unused outputs zero), bias [8]
-            hw = torch.zeros((8, self.P * CH), dtype=torch.float64)
+        if self.fused_head:   # k_head operand: [8 outputs][(H+1)*W*64] bf16 (unused outputs zero), bias [8]
+            hw = torch.zeros((8, (self.h + 1) * self.w * CH), dtype=torch.float64)
             hw[:self.A + 1] = fwp.reshape(self.A + 1, -1)
             hb = torch.zeros(8, dtype=torch.float64)
             hb[:self.A + 1] = net.fc1.bias.double().cpu()
@@ -162,14 +144,13 @@ class FusedEvaluator:
         self.timing.append((name, e0, e1))
         return rc
 
-    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, b0, nb, skip_obs=None, skip_w=None, flags=0):
+    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, skip_obs=None, skip_w=None, flags=0):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         name = "conv" + ("+res" if res is not None else "") + ("+skip" if skip_obs is not None else "") + \
             ("+out2" if out2 is not None else "")
-        fn = self.lib.az_nn_conv3x3_w7 if self.w7 else self.lib.az_nn_conv3x3
-        rc = self._timed(name, lambda: fn(
-            p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), p(skip_obs), p(skip_w), b0, nb, self.h, self.w,
-            LEAD, self.rows_alloc, 1 if lrelu else 0, flags, self.n_ctas, self._stream()))
+        rc = self._timed(name, lambda: self.lib.az_nn_conv3x3(
+            p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), p(skip_obs), p(skip_w), self.batch, self.h, self.w,
+            1 if lrelu else 0, flags, self.n_ctas, self._stream()))
         if rc:
             raise RuntimeError("az_nn_conv3x3: " + self.lib.az_nn_last_error().decode())
 
@@ -178,40 +159,36 @@ class FusedEvaluator:
         """Evaluate self.obs into self.priors / self.values on the current stream (graph-capturable)."""
         P_ = self.par
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-        for b0, nb in self.slices:
-            rc = self._timed("stem", lambda: self.lib.az_nn_stem(
-                p(self.obs), p(P_["stem_w"]), p(P_["b1_0"]), p(P_["stem_b3"]), p(P_["stem_st"]), p(self.U),
-                None if self.fuse_skip else p(self.X),
-                b0, nb, self.h, self.w, LEAD, self.rows_alloc, self.n_ctas, self._stream()))
+        rc = self._timed("stem", lambda: self.lib.az_nn_stem(
+            p(self.obs), p(P_["stem_w"]), p(P_["b1_0"]), p(P_["stem_b3"]), p(P_["stem_st"]), p(self.U),
+            None if self.fuse_skip else p(self.X), self.batch, self.h, self.w, self.n_ctas, self._stream()))
+        if rc:
+            raise RuntimeError("az_nn_stem: " + self.lib.az_nn_last_error().decode())
+        # Layers alternate their tile direction: each reads its input starting from the part the previous layer wrote
+        # last (still in L2); the stem writes front to back, so the first conv goes back to front.
+        if self.fuse_skip:
+            # block 1, second conv: X = conv(U) + conv1x1(obs) ; T = lrelu(bn1_2(X))   (skip projection in the epilogue)
+            self._conv(self.U, P_["w2_0"], P_["b2skip_0"], None, self.X, self.T, P_["s_1"], P_["t_1"], False,
+                       skip_obs=self.obs, skip_w=P_["skip_w"], flags=L.NN_F_REVERSE)
+        else:
+            self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False,
+                       flags=L.NN_F_REVERSE)
+        for k in range(1, 5):
+            self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True)
+            last = k == 4
+            self._conv(self.U, P_["w2_%d" % k], P_["b2_%d" % k], self.X, self.X, None if last else self.T,
+                       None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False,
+                       flags=L.NN_F_REVERSE)
+        if self.fused_head:
+            rc = self._timed("head", lambda: self.lib.az_nn_head(
+                p(self.X), p(P_["hw"]), p(P_["hb"]), p(self.priors), p(self.values), self.batch, self.h, self.w, self.A,
+                self.n_ctas, self._stream()))
             if rc:
-                raise RuntimeError("az_nn_stem: " + self.lib.az_nn_last_error().decode())
-            if self.fuse_skip:
-                # block 1, second conv: X = conv(U) + conv1x1(obs) ; T = lrelu(bn1_2(X))   (skip projection in the epilogue)
-                self._conv(self.U, P_["w2_0"], P_["b2skip_0"], None, self.X, self.T, P_["s_1"], P_["t_1"], False, b0, nb,
-                           skip_obs=self.obs, skip_w=P_["skip_w"], flags=L.NN_F_REVERSE)
-            else:
-                self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False, b0, nb,
-                           flags=L.NN_F_REVERSE)
-            for k in range(1, 5):
-                # layers alternate their tile direction: each reads its input starting from the part the previous layer
-                # wrote last (still in L2); the stem writes front to back, so the first conv goes back to front
-                self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True, b0, nb)
-                last = k == 4
-                self._conv(self.U, P_["w2_%d" % k], P_["b2_%d" % k], self.X, self.X, None if last else self.T,
-                           None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False, b0, nb,
-                           flags=L.NN_F_REVERSE)
-            if self.fused_head:
-                rc = self._timed("head", lambda: self.lib.az_nn_head(
-                    p(self.X), p(P_["hw"]), p(P_["hb"]), p(self.priors), p(self.values), b0, nb, self.h, self.w, LEAD,
-                    self.rows_alloc, self.A, self.n_ctas, self._stream()))
-                if rc:
-                    raise RuntimeError("az_nn_head: " + self.lib.az_nn_last_error().decode())
-                continue
-            lo = (LEAD + b0 * self.P) * CH
-            flat = self.X.view(-1)[lo:lo + nb * self.P * CH].view(nb, self.P * CH)
-            out = F.linear(flat, P_["fw"]).float() + P_["fb"]
-            torch.softmax(out[:, :self.A], dim=1, out=self.priors[b0:b0 + nb])
-            torch.tanh(out[:, self.A], out=self.values[b0:b0 + nb])
+                raise RuntimeError("az_nn_head: " + self.lib.az_nn_last_error().decode())
+        else:
+            out = F.linear(self.X.view(self.batch, -1), P_["fw"]).float() + P_["fb"]
+            torch.softmax(out[:, :self.A], dim=1, out=self.priors)
+            torch.tanh(out[:, self.A], out=self.values)
         return self.priors, self.values
 
     @torch.no_grad()

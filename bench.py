@@ -195,7 +195,7 @@ def run_ours(args):
     runner = SelfPlayRunner(net, game, dev, args.trees, n_playouts=args.playouts, c_puct=2.5, use_dirichlet=True,
                             dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", seed=0xC4 + rank,
                             auto_restart=True, random_start_mod=21, max_sims_per_step=args.sim_cap, records=True,
-                            use_graph=not args.no_graph, evaluator=args.evaluator, nn_slice=args.nn_slice,
+                            use_graph=not args.no_graph, evaluator=args.evaluator,
                             keep_search_tree=not args.no_keep_tree, node_capacity=args.node_capacity)
     # ---- warm-up (untimed): builds the first searches so trees are in steady state
     runner.round(args.warmup)
@@ -383,7 +383,6 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--ref-repeat", action="store_true")
     ap.add_argument("--evaluator", default="fused", choices=["fused", "torch"])
-    ap.add_argument("--nn-slice", type=int, default=0)
     ap.add_argument("--node-capacity", type=int, default=0)
     ap.add_argument("--no-keep-tree", action="store_true", help="experiment: fresh tree every move (no re-root compaction)")
     args = ap.parse_args()

@@ -233,44 +233,36 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
                             int32_t max_plies, int32_t* hist_dev, int32_t* len_dev, void* stream);
 
 /* ---- evaluator kernels (az_resnet.cu): the ResNet of network.py:21-104 for the batched evaluator ----
- * Activations are bf16 "padded rows" [rows_alloc][64]: board b, cell (r,c) at row lead + b*(H+1)*(W+1) + r*(W+1) + c,
- * pad rows/columns hold zeros; 50 filters are zero-padded to 64.  All pointers are device pointers.
+ * Activations are NHWC bf16 tensors [boards][H+1][W][64]: the 50 filters zero-padded to 64, and one extra board row (row H)
+ * that must be zero when a tensor is first used and is kept zero by the kernels - it separates consecutive boards.  There
+ * are no pad columns in global memory (TMA zero-fills / clips them).  All pointers are device pointers; 3 <= H <= 16,
+ * 2 <= W <= 8.
  *
  * az_nn_conv3x3: out = conv3x3(in) + bias, optional LeakyReLU, optional + res; optional second output
- *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  wpack is [9 taps][64 n][8][8] bf16,
- *   the SWIZZLE_128B K-major operand image (tap = ky*3+kx; 16-byte chunk c of row n stored at position c ^ (n & 7)).
- *   tcgen05 implicit GEMM; n_ctas <= 0 -> one CTA per SM.  With skip_obs (the az_step observation batch) and skip_w
- *   [64][4] fp32 the epilogue adds the 1x1 skip projection of the raw planes (resblock1.conv3, network.py:101-103) instead
- *   of reading a residual tensor, so the stem never has to write one.
- * az_nn_conv3x3_w7: the same operator for boards of width 7 (padded row pitch 8, Connect Four; lead % 8 == 0): the three
- *   dx taps of a kernel row are one MMA of N = 192 and are recombined by the epilogue, so the activation slab is fetched
- *   from shared memory 3x instead of 9x per tile.  wpack is [3 ky][192 = kx*64 + n][8][8] bf16, SWIZZLE_128B as above.
- * az_nn_stem: the 4-plane first block on the same tcgen05 kernel (the slab is built from the az_step
- *   AZ_OBS_BF16_NHWC batch [boards][H][W][4]): u = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1), r = conv1x1(x) + b3
- *   (network.py:99-103 for resblock1; r may be NULL when the next conv computes the projection itself).  wpack is [9 taps][2][128][8] bf16: rows 0-63 = conv1 (BatchNorm folded) on
- *   k 0-3, rows 64-127 = the 1x1 skip projection on k 4-7 of the centre tap.  bn_st = device [8]: scale[4], shift[4].
+ *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  wpack is bf16 [3 ky][192 = kx*64 + n][8][8]:
+ *   per kernel row the three kx taps side by side, each row n = 64 input channels (128 B) in the SWIZZLE_128B K-major UMMA
+ *   image (16-byte chunk c stored at position c ^ (n & 7)).  tcgen05 implicit GEMM, 12 MMAs of M128 N192 K16 per 128-row
+ *   tile; n_ctas <= 0 -> one CTA per SM.  With skip_obs (the az_step observation batch) and skip_w [64][4] fp32 the
+ *   epilogue adds the 1x1 skip projection of the raw planes (resblock1.conv3, network.py:101-103) instead of reading a
+ *   residual tensor.  res may alias out (in-place residual stream).  flags: AZ_NN_F_*.
+ * az_nn_stem: the 4-plane first block, slab built from the az_step AZ_OBS_BF16_NHWC batch [boards][H][W][4]:
+ *   u = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1), r = conv1x1(x) + b3 (network.py:99-103 for resblock1; r may be NULL when
+ *   the next conv computes the projection itself).  wpack is [9 taps][2][128][8] bf16: rows 0-63 = conv1 (BatchNorm
+ *   folded) on k 0-3, rows 64-127 = the 1x1 skip projection on k 4-7 of the centre tap.  bn_st = device [8]: scale[4],
+ *   shift[4].
  * az_nn_head: the FC head (fc1, network.py:48,61-66) for games with n_actions + 1 <= 8 outputs: priors [.][n_actions] =
- *   softmax(x_flat @ w[0..A-1]^T + bias), values = tanh(x_flat @ w[A]^T + bias[A]), fp32.  w is bf16 [8][(H+1)*(W+1)*64]
- *   over the padded-rows flatten of one board (zero on pad cells / pad channels / unused outputs), bias fp32 [8].
- *   All kernels work on boards [board0, board0+boards) of the full buffers and never read or write pad rows or rows of
- *   other boards (pads must be zero from allocation). */
+ *   softmax(x_flat @ w[0..A-1]^T + bias), values = tanh(x_flat @ w[A]^T + bias[A]), fp32.  w is bf16 [8][(H+1)*W*64] over the
+ *   flatten of one board (zero on the pad row / pad channels / unused outputs), bias fp32 [8]. */
 #define AZ_NN_F_REVERSE 1 /* walk the 128-row tiles back to front (alternate per layer: the tail of the previous layer's
                              output is still in L2) */
 const char* az_nn_last_error(void);
 int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                  const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
-                  int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t flags,
-                  int32_t n_ctas, void* stream);
-int az_nn_conv3x3_w7(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                     const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t board0,
-                     int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t lrelu, int32_t flags,
-                     int32_t n_ctas, void* stream);
+                  const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t boards, int32_t H,
+                  int32_t W, int32_t lrelu, int32_t flags, int32_t n_ctas, void* stream);
 int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st, void* u,
-               void* r, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc,
-               int32_t n_ctas, void* stream);
-int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t board0,
-               int32_t boards, int32_t H, int32_t W, int32_t lead, int32_t rows_alloc, int32_t n_actions, int32_t n_ctas,
-               void* stream);
+               void* r, int32_t boards, int32_t H, int32_t W, int32_t n_ctas, void* stream);
+int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t boards, int32_t H,
+               int32_t W, int32_t n_actions, int32_t n_ctas, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,31 +1,28 @@
-"""Times az_nn_conv3x3 alone (CUDA events) for 16384 Connect Four boards; AZ_NN_DEBUG selects experiment modes."""
+"""Times az_nn_conv3x3 alone (CUDA events) for 16384 Connect Four boards; AZ_NN_DEBUG selects experiment modes
+(1 = no loads, 2 = no epilogue math/stores, 4 = no MMAs)."""
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alphazero_openspiel_b200 import _lib as L
-from alphazero_openspiel_b200.nn_fused import pack_conv3x3, pack_conv3x3_w7, LEAD
-W7 = os.environ.get("AZ_NN_W7", "1") != "0"
+from alphazero_openspiel_b200.nn_fused import pack_conv3x3
 lib = L.load()
 dev = torch.device("cuda:0")
 B, H, W = 16384, 6, 7
-P = (H + 1) * (W + 1)
-rows = (LEAD + B * P + W + 2 + 127) // 128 * 128
-x = torch.randn((rows, 64), device=dev).to(torch.bfloat16)
-r = torch.randn((rows, 64), device=dev).to(torch.bfloat16)
-o = torch.zeros((rows, 64), dtype=torch.bfloat16, device=dev)
-o2 = torch.zeros((rows, 64), dtype=torch.bfloat16, device=dev)
-w = (pack_conv3x3_w7 if W7 else pack_conv3x3)(torch.randn(64, 64, 3, 3) * 0.05).to(dev)
-conv = lib.az_nn_conv3x3_w7 if W7 else lib.az_nn_conv3x3
+x = torch.randn((B, H + 1, W, 64), device=dev).to(torch.bfloat16)
+r = torch.randn((B, H + 1, W, 64), device=dev).to(torch.bfloat16)
+o = torch.zeros((B, H + 1, W, 64), dtype=torch.bfloat16, device=dev)
+o2 = torch.zeros((B, H + 1, W, 64), dtype=torch.bfloat16, device=dev)
+w = pack_conv3x3(torch.randn(64, 64, 3, 3) * 0.05).to(dev)
 b = torch.randn(64, device=dev); s2 = torch.rand(64, device=dev); t2 = torch.randn(64, device=dev)
 p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for name, res, out2 in [("conv1-type", None, None), ("conv2+res", r, None), ("conv2+res+out2", r, o2)]:
     def run():
-        rc = conv(p(x), p(w), p(b), p(res), p(o), p(out2), p(s2) if out2 is not None else None,
-                               p(t2) if out2 is not None else None, None, None, 0, B, H, W, LEAD, rows, 1 if res is None else 0, 0, 0, st)
-        assert rc == 0
+        rc = lib.az_nn_conv3x3(p(x), p(w), p(b), p(res), p(o), p(out2), p(s2) if out2 is not None else None,
+                               p(t2) if out2 is not None else None, None, None, B, H, W, 1 if res is None else 0, 0, 0, st)
+        assert rc == 0, lib.az_nn_last_error()
     for _ in range(3): run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20): run()
     e1.record(); torch.cuda.synchronize()
-    print("W7=%d AZ_NN_DEBUG=%s %-16s %.1f us" % (W7, os.environ.get("AZ_NN_DEBUG", "0"), name, e0.elapsed_time(e1) / 20 * 1e3))
+    print("AZ_NN_DEBUG=%s %-16s %.1f us" % (os.environ.get("AZ_NN_DEBUG", "0"), name, e0.elapsed_time(e1) / 20 * 1e3))
