@@ -626,8 +626,16 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
   h.root_b1 = s2.b1;
   h.root_ply = s2.ply;
   if ((p.flags & AZ_F_KEEP_TREE) && nc > 0) {
-    // Re-rooting copies the kept subtree (hundreds of dependent loads): done by k_compact, off this kernel's critical
-    // path, so that one moving tree does not set the duration of the whole lock-step launch.
+    // MCTS.update_root (mcts.py:192-203).  While the arena half still has room for the worst case of one more search
+    // (every simulation expands one leaf), the chosen child simply becomes the root in place and the discarded siblings
+    // stay behind as garbage; the tree continues with its next root evaluation in this very launch.
+    if (!(p.flags & AZ_F_EAGER_COMPACT) && (long long)h.alloc + (long long)(p.n_playouts + 1) * GM::MAXC <= (long long)p.cap) {
+      h.root_node = fc + k;
+      h.phase = PH_BEGIN;
+      return;
+    }
+    // Otherwise the kept subtree is copied into the other half (hundreds of dependent loads): done by k_compact, off this
+    // kernel's critical path, so that one moving tree does not set the duration of the whole lock-step launch.
     h.pend_node = fc + k;
     h.phase = PH_COMPACT;
     if (lane == 0) p.compact_list[atomicAdd(p.compact_count, 1)] = tree;

@@ -58,6 +58,8 @@ extern "C" {
 #define AZ_F_PRIORS_F64     (1u << 6) /* az_step priors/values are double (generic policy_fn), else float (Net outputs) */
 #define AZ_F_RANDOM_START   (1u << 7) /* (re)started games begin after counter%start_plies_mod random plies (bench synthetic positions) */
 #define AZ_F_ASYNC_COMPACT  (1u << 8) /* the caller runs az_compact() itself (e.g. on a side stream next to the evaluator) */
+#define AZ_F_EAGER_COMPACT  (1u << 9) /* compact the kept subtree after EVERY move; default: re-root in place and compact
+                                         only when the arena half cannot hold another worst-case search */
 
 /* root noise (mcts.py:182-190) */
 #define AZ_NOISE_NONE      0 /* use_dirichlet=False */

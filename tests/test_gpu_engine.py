@@ -233,13 +233,16 @@ def test_device_move_sampling_follows_visit_counts(temperature):
     assert chi2 < 30.0, (chi2, freq, n * p)                  # 6 dof: P(chi2 > 30) ~ 4e-5
 
 
-def test_async_compaction_on_side_stream_is_bit_exact():
+@pytest.mark.parametrize("eager", [0, 1])
+def test_async_compaction_on_side_stream_is_bit_exact(eager):
     """AZ_F_ASYNC_COMPACT: the caller runs az_compact on a side stream between two az_step calls (what SelfPlayRunner does
-    next to the evaluator).  Results must equal the oracle exactly, like the synchronous mode."""
+    next to the evaluator).  Results must equal the oracle exactly, like the synchronous mode -- both when the kept subtree
+    is compacted after every move (AZ_F_EAGER_COMPACT) and when the tree re-roots in place until its arena half fills up."""
     import torch
     from alphazero_openspiel_b200 import engine as E, _lib as L
     game, n_trees, n_playouts, seed = "connect_four", 64, 100, 4321
-    flags = L.F_RECORDS | L.F_OFFPOLICY | L.F_KEEP_TREE | L.F_SAMPLE_MOVES | L.F_ASYNC_COMPACT
+    flags = L.F_RECORDS | L.F_OFFPOLICY | L.F_KEEP_TREE | L.F_SAMPLE_MOVES | L.F_ASYNC_COMPACT | \
+        (L.F_EAGER_COMPACT if eager else 0)
     eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=L.NOISE_COUNTER, eval_mode=L.EVAL_HASH, flags=flags,
                    seed=seed)
     side = torch.cuda.Stream()
