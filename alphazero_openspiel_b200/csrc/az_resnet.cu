@@ -4,32 +4,14 @@
 // block BatchNorm -> LeakyReLU -> conv3x3 -> BatchNorm -> LeakyReLU -> conv3x3 -> add) that PyTorch runs as ~45 separate
 // kernels (profiles/r01_summary.md: 57 % of a round trip was un-fused elementwise traffic).
 //
-// Activation layout ("padded rows"): bf16 [rows][64]; board b, cell (r,c) lives at row
-//     LEAD + b*P + r*Wp + c,   Wp = W+1 (one shared zero column), P = (H+1)*Wp (one zero row per board)
-// and every pad row holds zeros, so a 3x3 convolution is 9 shifted copies of the same operand:
-//     out[m][:] = sum_tap  in[m + (ky-1)*Wp + (kx-1)][:] @ W_tap          (implicit GEMM, no im2col)
-// Pad rows are zero from allocation and are never read or written by these kernels.
-//
-// k_conv<STEM>: persistent CTAs (one per SM), warp-specialised, 13 warps:
-//   warps 0..3  producers, one per smem stage: bring the A slab (128 + 2*HALO rows) of a tile into the stage, laid out
-//               [k-chunk of 8 channels][row] x 16 B == the UMMA "no-swizzle, K-major" canonical layout, so a tap is just a
-//               different 16-byte-aligned start address in the operand descriptor.
-//                 STEM=false: cp.async from the previous layer's activations.
-//                 STEM=true : built on the fly from the az_step observation planes: channels 0-3 = LeakyReLU(bn1(x)),
-//                             channels 4-7 = x (for the 1x1 skip projection), one k-step of 16.
-//   warp 4      MMA issuer: one elected lane issues tcgen05.mma (M=128, K=16, bf16 -> fp32 in TMEM):
-//                 STEM=false: 9 taps x 4 k-steps, N=64;  STEM=true: 9 taps x 1 k-step, N=128 (conv1 | skip).
-//               two TMEM accumulator stages; tcgen05.commit -> mbarriers.
-//   warps 5..12 epilogue: tcgen05.ld (32 rows x 32 channels per warp), + bias, LeakyReLU, + residual, second output
-//               (next block's BatchNorm + LeakyReLU, or the skip projection for STEM), bf16 stores coalesced through smem.
-// The layer's weights (72 KB / 36 KB, BatchNorm folded) are resident in smem for the whole launch.
-//
-// Operand layouts: STEM=false uses SWIZZLE_128B K-major (one activation row = one 128-byte line, so tap shifts never
-// straddle lines); STEM=true keeps the no-swizzle layout (its K is a single 16-channel step).
-// Measured limiter (profiles/r01_summary.md, scripts/conv_microbench.py): shared-memory bandwidth.  Every tile moves
-// ~216 KB of MMA operands (the slab is re-read once per tap, the 72 KB of weights once per tile) plus producer writes
-// and epilogue staging through the SM's 128 B/clk smem datapath; the MMAs alone take ~67 cycles each vs 32 of math.
+// Activations are NHWC bf16 tensors [boards][H+1][W][64] (50 filters zero-padded to 64; board row H is a zero pad row that
+// separates consecutive boards).  Three kernels:
+//   k_conv8<false>  3x3 conv 64 -> 64 with bias / LeakyReLU / residual / next-BatchNorm / skip-projection epilogues
+//   k_conv8<true>   the 4-plane stem (first conv of block 1), same pipeline with a computing producer
+//   k_head          FC + softmax + tanh for small action spaces
+// Measured history of the conv kernel (limiters, what was tried) is in profiles/r01_summary.md.
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -37,44 +19,14 @@
 #include <string.h>
 #include <stdlib.h>
 
-#include <cuda.h>
-
 #include "../../include/az_b200.h"
 
 namespace aznn {
 
 constexpr int CH = 64;            // padded channel count (50 filters -> 64)
 constexpr int TILE_M = 128;       // output rows per MMA tile
-constexpr int SLAB = 153;         // smem rows per A stage (>= 128 + 2*HALO; odd => conflict-free scatter)
-constexpr int MAX_HALO = 12;
-constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = 160 * 128;            // 20,480: 160 rows x 128 B (SW128, 1024-aligned) >= 2 * SLAB * 16 (stem)
-constexpr int W_BYTES = 9 * CH * CH * 2;            // 73,728 (STEM: 9 x 128 x 16 x 2 = 36,864)
-constexpr int NUM_THREADS = 416;                    // 13 warps: 4 producers, 1 MMA issuer, 8 epilogue
-constexpr int EPI_WARPS = 8;
+constexpr int W_BYTES = 9 * CH * CH * 2;            // 73,728: one layer's weights, resident in smem for the whole launch
 constexpr float LRELU_SLOPE = 0.01f;
-
-struct ConvParams {
-  const __nv_bfloat16* in;    // [rows_alloc][64]            (STEM: observation planes [boards][H][W][4])
-  const __nv_bfloat16* wpack; // [9][8][64][8]  (tap, k-chunk, n, k%8)      (STEM: [9][2][128][8])
-  const float* bias;          // [64]
-  const __nv_bfloat16* res;   // [rows_alloc][64] or null
-  __nv_bfloat16* out;         // [rows_alloc][64]
-  __nv_bfloat16* out2;        // [rows_alloc][64] or null: lrelu(s2*out + t2)   (STEM: skip projection + t2)
-  const float* s2;
-  const float* t2;
-  const float* stem_st;       // STEM: device [8]: bn1 scale[4], shift[4] of the input planes
-  const uint2* skip_obs;      // optional: observation planes [boards][H][W][4]; the epilogue adds the 1x1 skip projection
-  const float* skip_w;        //   skip_w [64][4] of the raw planes (network.py:101-103) instead of reading a residual tensor
-  int rows_alloc;             // multiple of 128
-  int n_tiles;
-  int lead, boards, P, Wp, H, W;
-  int board0;                 // this launch handles boards [board0, board0 + boards)
-  int tile0;                  // first 128-row tile of that range
-  int lrelu;                  // apply LeakyReLU to (acc + bias)
-  int debug;                  // experiments: 1 = producers skip loads, 2 = epilogue skips math+stores, 4 = no MMAs
-  int flags;                  // AZ_NN_F_*
-};
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,12 +51,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // UMMA shared-memory operand descriptor, SWIZZLE_NONE ("interleave"), K-major:
 //   core matrix = 8 rows x 16 B (rows 16 B apart); SBO = bytes between 8-row groups; LBO = bytes between K core matrices.
@@ -138,34 +84,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-// cta_group::2 pair (two CTAs of a cluster, M = 256): each CTA supplies its own 128 A rows and HALF of B (N/2 rows), so
-// the per-SM shared-memory fetch of B halves.  Issued by the leader CTA only; commits are multicast to both CTAs.
-__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar),
-      "r"(rank)
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -197,496 +115,6 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return o;
 }
 
-// smem carve-up (dynamic): [weights 73,728][A stages 4 x 19,584][bias 256][s2 256][t2 256][barriers][epilogue staging]
-struct SmemLayout {
-  static constexpr int W_OFF = 0;
-  static constexpr int A_OFF = W_BYTES;
-  static constexpr int BIAS_OFF = A_OFF + STAGES * A_STAGE_BYTES;
-  static constexpr int S2_OFF = BIAS_OFF + 256;
-  static constexpr int T2_OFF = S2_OFF + 256;
-  static constexpr int SKIPW_OFF = T2_OFF + 256;         // [64][4] fp32 skip-projection weights
-  static constexpr int BAR_OFF = SKIPW_OFF + 1024;       // up to 24 mbarriers (8 B each), then the TMEM base address
-  static constexpr int STG_OFF = BAR_OFF + 24 * 8 + 16;  // per epilogue warp: res / out / out2 staging, 32 rows x 80 B
-  static constexpr int STG_ROW = 80;                     // 64 B (half a row) + 16 B pad: conflict-free row-per-thread access
-  static constexpr int STG_WARP = 3 * 32 * STG_ROW;
-  static constexpr int TOTAL = STG_OFF + EPI_WARPS * STG_WARP;
-};
-
-// MODE_CONV: nine row-shifted A views (one per tap), N = 64.  MODE_STEM: the 4-plane first block.  MODE_DX: boards whose
-// padded row pitch is exactly 8 (W = 7, Connect Four): the three dx taps of a kernel row share ONE A view and become the N
-// dimension, D[row][dx*64 + co] = sum_dy,k A[row + dy*8][k] W(dy,dx)[k][co] (12 MMAs of N = 192 instead of 36 of N = 64:
-// the slab is fetched from shared memory 3x instead of 9x per tile), and the epilogue adds the three column blocks of the
-// neighbouring rows, out[q] = D_-1[q-1] + D_0[q] + D_+1[q+1], with one-lane warp shuffles.  Rows q-1 / q+1 of a lane at a
-// 32-row boundary are pad-column cells (row % 8 == 7 / 0), whose partial sums are zero because their activations are.
-constexpr int MODE_CONV = 0, MODE_STEM = 1, MODE_DX = 2;
-
-template <int MODE, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1) k_conv(const ConvParams p) {
-  constexpr bool STEM = MODE == MODE_STEM, FDX = MODE == MODE_DX;
-  static_assert(CG == 1 || (CG == 2 && MODE == MODE_CONV), "the CTA-pair variant exists for the plain 64-channel convs only");
-  constexpr int N_MMA = STEM ? 128 : FDX ? 192 : 64;  // accumulator columns per tile
-  constexpr int K_STEPS = STEM ? 1 : 4;               // 16-channel k-steps per tap
-  constexpr int W_N = STEM ? 128 : FDX ? 192 : 64 / CG;  // rows of the B operand image held by THIS CTA
-  constexpr int W_TAP_BYTES = W_N * 16 * 2 * K_STEPS; // bytes of one tap's (FDX: one kernel row's) weights
-  constexpr int W_TOTAL = (FDX ? 3 : 9) * W_TAP_BYTES;
-  constexpr int ACC = (STEM || FDX) ? 2 : 4;          // TMEM accumulator stages (the MMA warp may run ACC tiles ahead)
-  constexpr uint32_t TMEM_COLS = FDX ? 512u : 256u;   // >= ACC * N_MMA, power of two
-
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t s_base = smem_u32(smem);
-  const uint32_t s_w = s_base + SmemLayout::W_OFF;
-  const uint32_t s_a = s_base + SmemLayout::A_OFF;
-  float* s_bias = reinterpret_cast<float*>(smem + SmemLayout::BIAS_OFF);
-  float* s_s2 = reinterpret_cast<float*>(smem + SmemLayout::S2_OFF);
-  float* s_t2 = reinterpret_cast<float*>(smem + SmemLayout::T2_OFF);
-  const uint32_t s_bar = s_base + SmemLayout::BAR_OFF;
-  auto bar_full = [&](int s) { return s_bar + 8u * s; };
-  auto bar_empty = [&](int s) { return s_bar + 8u * (STAGES + s); };
-  auto bar_tfull = [&](int a) { return s_bar + 8u * (2 * STAGES + a); };
-  auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * STAGES + ACC + a); };
-  auto bar_w = [&]() { return s_bar + 8u * (2 * STAGES + 2 * ACC); };
-  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + SmemLayout::BAR_OFF + 24 * 8);
-  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;  // rank 0 = leader: issues the MMAs for the pair
-  // all hand-offs TO the MMA issuer go to the leader's barriers
-  auto arrive_leader = [&](uint32_t bar) {
-    if (CG == 1 || cta_rank == 0) mbar_arrive(bar); else mbar_arrive_cluster(bar, 0u);
-  };
-
-  // ---- one-time setup: barriers + TMEM (weights and epilogue vectors are loaded by the epilogue warps, see below)
-  if (warp == 4 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(bar_full(s), CG);  // one producer warp per CTA of the pair
-      mbar_init(bar_empty(s), 1);
-    }
-    for (int a = 0; a < ACC; ++a) {
-      mbar_init(bar_tfull(a), 1);
-      mbar_init(bar_tempty(a), EPI_WARPS * CG);  // one arrive per epilogue warp (of both CTAs of a pair)
-    }
-    mbar_init(bar_w(), CG);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 4) {
-    if constexpr (CG == 2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
-                   "r"(TMEM_COLS)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
-                   "r"(TMEM_COLS)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-  }
-  if (STEM) {  // k-chunk 1 (channels 8..15) of every stage is constant zero in stem mode
-    for (int i = threadIdx.x; i < STAGES * SLAB; i += NUM_THREADS) {
-      const int st = i / SLAB, r = i % SLAB;
-      *reinterpret_cast<uint4*>(smem + SmemLayout::A_OFF + st * A_STAGE_BYTES + (SLAB + r) * 16) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    fence_proxy_async();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone arrives remotely
-  tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
-  // Programmatic dependent launch: let the next layer's CTAs start their own prologue as soon as SMs free up ...
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-  const int halo = FDX ? p.Wp : p.Wp + 1;
-  const int slab_rows = TILE_M + 2 * halo;
-  // work units: CG == 1: one tile; CG == 2: a pair of adjacent tiles (2u, 2u+1), one per CTA of the cluster
-  const int n_units = (p.n_tiles + CG - 1) / CG;
-  const int unit0 = (int)blockIdx.x / CG, unit_stride = (int)gridDim.x / CG;
-  const int my_tiles = (n_units - unit0 + unit_stride - 1) / unit_stride;
-  auto tile_of = [&](int it) { return p.tile0 + (unit0 + it * unit_stride) * CG + (int)cta_rank; };
-  const long long range_lo = (long long)p.lead + (long long)p.board0 * p.P;
-  const long long range_hi = range_lo + (long long)p.boards * p.P;
-  const int valid_pos = p.H * p.Wp;
-
-  if (warp < STAGES) {
-    // =========================== producers (one warp per smem stage) ===========================
-    // Warp w owns stage w and the tiles it == w (mod STAGES): wait until the MMA warp has released the stage, fill the
-    // slab, wait for ITS OWN copies only, make them visible to the tensor core's async proxy, signal `full`.
-    // Four such warps keep four slabs in flight without any cross-tile dependency between load issue and hand-off.
-    const int stage = warp;
-    // ... and do not touch the previous layer's output before that layer has completely finished.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int it = stage, round = 0; it < my_tiles; it += STAGES, ++round) {
-      mbar_wait(bar_empty(stage), ((uint32_t)round & 1u) ^ 1u);
-      const int tile = tile_of(it);
-      if (p.debug & 1) {
-        // (experiment) no loads
-      } else if constexpr (!STEM) {
-        // SW128 layout: smem row r (128 B) holds the 8 chunks of one activation row, chunk c at ((c ^ (r & 7)) * 16)
-        const uint32_t dst_stage = s_a + (uint32_t)stage * A_STAGE_BYTES;
-        const int n_it = (slab_rows + 3) / 4;
-        long long grow = (long long)tile * TILE_M - halo + (lane >> 3);
-        const __nv_bfloat16* src = p.in + grow * CH + (lane & 7) * 8;
-        // position of this lane's first row inside its board, then advanced incrementally (4 rows per step, 4 < Wp)
-        const long long q0 = grow - range_lo;
-        int pos = (int)(((q0 % p.P) + p.P) % p.P);
-        int col = pos % p.Wp;
-        for (int i = 0; i < n_it; ++i) {
-          if ((lane >> 3) + 4 * i < slab_rows) {
-            // pad rows / pad columns / rows outside this launch's boards are zero by construction: zero-fill, no read
-            const bool ok = grow >= range_lo && grow < range_hi && pos < valid_pos && col < p.W;
-            const uint32_t r = (uint32_t)((lane >> 3) + 4 * i);
-            cp_async16(dst_stage + r * 128u + ((((uint32_t)lane & 7u) ^ (r & 7u)) << 4),
-                       ok ? (const void*)src : (const void*)p.in, ok ? 16u : 0u);
-          }
-          grow += 4;
-          src += 4 * CH;
-          pos += 4;
-          if (pos >= p.P) pos -= p.P;
-          col += 4;
-          if (col >= p.Wp) col -= p.Wp;
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-      } else {
-        // Build k-chunk 0 of the slab from the observation planes: [lrelu(bn1(x))_0..3 | x_0..3] per cell.
-        uint8_t* dst = smem + SmemLayout::A_OFF + stage * A_STAGE_BYTES;
-        const uint2* obs = reinterpret_cast<const uint2*>(p.in);
-        const int cells = p.H * p.W;
-        const long long row0 = (long long)tile * TILE_M - halo;
-        constexpr int PER_LANE = (SLAB + 31) / 32;
-        float bs[4], bt[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          bs[i] = p.stem_st[i];
-          bt[i] = p.stem_st[4 + i];
-        }
-        uint2 raw[PER_LANE];
-        bool okv[PER_LANE];
-#pragma unroll
-        for (int i = 0; i < PER_LANE; ++i) {
-          const int r = lane + 32 * i;
-          const long long grow = row0 + r;
-          bool ok = r < slab_rows && grow >= range_lo && grow < range_hi;
-          long long cell_index = 0;
-          if (ok) {
-            const long long q = grow - p.lead;
-            const int b = (int)(q / p.P), pos = (int)(q % p.P);
-            const int rr = pos / p.Wp, cc = pos % p.Wp;
-            ok = pos < valid_pos && cc < p.W;
-            cell_index = (long long)b * cells + rr * p.W + cc;
-          }
-          okv[i] = ok;
-          raw[i] = ok ? obs[cell_index] : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int i = 0; i < PER_LANE; ++i) {
-          const int r = lane + 32 * i;
-          if (r < slab_rows) {
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (okv[i]) {
-              const __nv_bfloat162 x01 = *reinterpret_cast<const __nv_bfloat162*>(&raw[i].x);
-              const __nv_bfloat162 x23 = *reinterpret_cast<const __nv_bfloat162*>(&raw[i].y);
-              const float x0 = __bfloat162float(x01.x), x1 = __bfloat162float(x01.y);
-              const float x2 = __bfloat162float(x23.x), x3 = __bfloat162float(x23.y);
-              o.x = pack_bf16(lrelu(bs[0] * x0 + bt[0]), lrelu(bs[1] * x1 + bt[1]));
-              o.y = pack_bf16(lrelu(bs[2] * x2 + bt[2]), lrelu(bs[3] * x3 + bt[3]));
-              o.z = raw[i].x;
-              o.w = raw[i].y;
-            }
-            *reinterpret_cast<uint4*>(dst + r * 16) = o;
-          }
-        }
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) arrive_leader(bar_full(stage));
-    }
-  } else if (warp == 4) {
-    // =========================== MMA issuer ===========================
-    // cta_group::2: M = 256 (m_dim field 16) across the pair
-    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)N_MMA) + (CG == 2 ? ((128u >> 4) << 24) : 0u);
-    // Operand descriptors differ only in their 14-bit start-address field (units of 16 B): precompute the bases and the
-    // nine tap offsets so that the issue loop is two integer adds per tcgen05.mma (the single issuing thread is
-    // latency-bound on whatever address arithmetic sits between two MMAs).
-    long long dlt[9];
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) dlt[tap] = (long long)((tap / 3 - 1) * p.Wp + (tap % 3 - 1));
-    if (CG == 2 && cta_rank != 0) goto teardown;  // the peer CTA's tensor core is driven by the leader's instructions
-    mbar_wait(bar_w(), 0u);  // weights resident (loaded by the epilogue warps while the first slabs were in flight)
-    for (int it = 0; it < my_tiles; ++it) {
-      const int stage = it % STAGES, acc = it % ACC;
-      mbar_wait(bar_full(stage), (uint32_t)(it / STAGES) & 1u);
-      mbar_wait(bar_tempty(acc), ((uint32_t)(it / ACC) & 1u) ^ 1u);
-      tc_fence_after();
-      // elect.sync (not `lane == 0`): the compiler then knows exactly one lane issues and keeps the descriptors in
-      // uniform registers instead of wrapping every tcgen05.mma in an ELECT / BRA.U.ANY serialisation loop.
-      if (elect_one()) {
-        const uint32_t d = tmem_base + (uint32_t)(acc * N_MMA);
-        if (p.debug & 4) {
-          // (experiment) no MMAs
-        } else if constexpr (STEM) {
-          const uint64_t wdesc0 = umma_desc(s_w, (uint32_t)W_N * 16u, 128u);
-          const uint64_t ab = umma_desc(s_a + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)halo * 16u, SLAB * 16u, 128u);
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap)
-            umma_bf16(d, ab + (uint64_t)dlt[tap], wdesc0 + (uint64_t)(tap * (W_TAP_BYTES / 16)), idesc, tap != 0 ? 1u : 0u);
-        } else if constexpr (FDX) {
-          const uint32_t a_stage = s_a + (uint32_t)stage * A_STAGE_BYTES;
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const uint64_t at = umma_desc_sw128(a_stage + (uint32_t)(halo + (dy - 1) * p.Wp) * 128u);
-            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)dy * (uint32_t)W_TAP_BYTES);
-#pragma unroll
-            for (int j = 0; j < K_STEPS; ++j)
-              umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (dy | j) != 0 ? 1u : 0u);
-          }
-        } else {
-          // SW128: every activation row is its own 128-byte line, so a tap shift of delta rows never straddles lines.
-          const uint32_t a_stage = s_a + (uint32_t)stage * A_STAGE_BYTES;
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t at = umma_desc_sw128(a_stage + (uint32_t)(halo + (int)dlt[tap]) * 128u);
-            const uint64_t bt = umma_desc_sw128(s_w + (uint32_t)tap * (uint32_t)W_TAP_BYTES);
-#pragma unroll
-            for (int j = 0; j < K_STEPS; ++j) {
-              if constexpr (CG == 2)
-                umma_bf16_2cta(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (tap | j) != 0 ? 1u : 0u);
-              else
-                umma_bf16(d, at + (uint64_t)(j * 2), bt + (uint64_t)(j * 2), idesc, (tap | j) != 0 ? 1u : 0u);
-            }
-          }
-        }
-        if constexpr (CG == 2) {
-          umma_commit_2cta(bar_empty(stage));  // both CTAs' stages reusable / both accumulators ready
-          umma_commit_2cta(bar_tfull(acc));
-        } else {
-          umma_commit(bar_empty(stage));  // smem stage reusable once these MMAs have read it
-          umma_commit(bar_tfull(acc));    // accumulator ready for the epilogue
-        }
-      }
-      __syncwarp();
-    }
-  } else {
-    // =========================== epilogue (warps 5..12) ===========================
-    // Warp e owns 32 rows (its TMEM lane quarter q) x 32 channels (column half).  Two warps per scheduler hide each
-    // other's TMEM / smem / global latencies.  Global traffic is coalesced through per-warp smem staging: 4 lanes move
-    // one 64-byte half row, so a warp instruction touches 8 rows x 2 full sectors instead of 32 scattered 16-byte pieces.
-    const int e = warp - 5;
-    const int q = warp & 3;     // TMEM lane quarter this warp may access
-    const int half = e >> 2;    // channels [32*half, 32*half+32)
-    {  // weights + epilogue vectors -> smem, asynchronously to the producers' first slabs
-      const int et = e * 32 + lane;
-      for (int i = et; i < W_TOTAL / 16; i += EPI_WARPS * 32) {
-        // global image: [tap][64 n][128 B]; this CTA keeps rows n = W_N*rank .. +W_N of every tap
-        const int tap = i / (W_TAP_BYTES / 16), off = i % (W_TAP_BYTES / 16);
-        const int gsrc = CG == 1 ? i : tap * (CG * W_TAP_BYTES / 16) + (int)cta_rank * (W_TAP_BYTES / 16) + off;
-        cp_async16(s_w + (uint32_t)i * 16u, reinterpret_cast<const uint4*>(p.wpack) + gsrc, 16u);
-      }
-      cp_async_commit();
-      if (et < CH) {
-        s_bias[et] = p.bias[et];
-        s_s2[et] = (p.out2 && p.s2) ? p.s2[et] : 0.f;
-        s_t2[et] = (p.out2 && p.t2) ? p.t2[et] : 0.f;
-        reinterpret_cast<float4*>(smem + SmemLayout::SKIPW_OFF)[et] =
-            p.skip_obs ? reinterpret_cast<const float4*>(p.skip_w)[et] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      cp_async_wait<0>();
-      fence_proxy_async();
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      if (et == 0) arrive_leader(bar_w());
-    }
-    uint8_t* stg = smem + SmemLayout::STG_OFF + e * SmemLayout::STG_WARP;
-    uint8_t* stg_res = stg;
-    uint8_t* stg_out = stg + 32 * SmemLayout::STG_ROW;
-    uint8_t* stg_out2 = stg + 64 * SmemLayout::STG_ROW;
-    const int crow = lane >> 2, cch = lane & 3;  // cooperative copy: lane -> (row within group of 8, 16-byte chunk)
-    const int col0 = half * 32;
-    const bool has_res = !STEM && p.res != nullptr;
-    const bool has_skip = !STEM && p.skip_obs != nullptr;
-    const float4* s_skipw = reinterpret_cast<const float4*>(smem + SmemLayout::SKIPW_OFF);
-    const int cells = p.H * p.W;
-    uint2 xnext = make_uint2(0u, 0u);
-
-    // Row validity without per-tile divisions: this thread's row advances by gridDim.x * 128 rows per tile, so its
-    // position inside the board advances by a constant (mod P).  32-bit arithmetic throughout.
-    const int range_len = (int)(range_hi - range_lo);
-    const int step_rows = (int)gridDim.x * TILE_M;
-    const int step_pos = step_rows % p.P;
-    int qrow_next = (int)((long long)(p.tile0 + (int)blockIdx.x) * TILE_M + q * 32 + lane - range_lo);  // may be < 0
-    int pos_next = ((qrow_next % p.P) + p.P) % p.P;
-    float bias_r[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) bias_r[i] = s_bias[col0 + i];
-    // residual rows of the NEXT tile are prefetched into registers while the current tile is processed
-    uint4 rnext[4];
-    uint32_t vmask_next = 0;
-    int urow_next = 0;  // STEM: index of this thread's cell in the [boards][H+1][W] outputs
-    auto prefetch = [&](int it) {
-      const int tile = tile_of(it);
-      const long long m_warp = (long long)tile * TILE_M + q * 32;
-      const bool v = qrow_next >= 0 && qrow_next < range_len && pos_next < valid_pos && (pos_next % p.Wp) < p.W;
-      vmask_next = __ballot_sync(0xffffffffu, v);
-      if constexpr (STEM) {
-        urow_next = 0;
-        if (v) urow_next = (p.board0 + qrow_next / p.P) * (cells + p.W) + (pos_next / p.Wp) * p.W + pos_next % p.Wp;
-      }
-      if (has_skip) {  // this row's 4 observation planes (for the 1x1 skip projection)
-        xnext = make_uint2(0u, 0u);
-        if (v) {
-          const int b = qrow_next / p.P;
-          xnext = p.skip_obs[(long long)(p.board0 + b) * cells + (pos_next / p.Wp) * p.W + pos_next % p.Wp];
-        }
-      }
-      qrow_next += step_rows;
-      pos_next += step_pos;
-      if (pos_next >= p.P) pos_next -= p.P;
-      if (has_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + m_warp * CH + col0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          rnext[i] = ((vmask_next >> (i * 8 + crow)) & 1u) ? rp[(i * 8 + crow) * 8 + cch] : make_uint4(0u, 0u, 0u, 0u);
-      }
-    };
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // residual reads / output writes depend on the previous layer
-    if (my_tiles > 0) prefetch(0);
-
-    for (int it = 0; it < my_tiles; ++it) {
-      const int acc = it % ACC;
-      const int tile = tile_of(it);
-      const long long m_warp = (long long)tile * TILE_M + q * 32;
-      // Invalid rows (pads, other launches' boards) are never loaded or stored.
-      const uint32_t vmask = vmask_next;
-      const int urow = urow_next;
-      const uint2 xrow = xnext;
-      if (has_res) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(stg_res + (i * 8 + crow) * SmemLayout::STG_ROW + cch * 16) = rnext[i];
-      }
-      if (it + 1 < my_tiles) prefetch(it + 1);
-      __syncwarp();
-      mbar_wait(bar_tfull(acc), (uint32_t)(it / ACC) & 1u);
-      tc_fence_after();
-      uint32_t v[32];
-      uint32_t w[STEM ? 32 : 1];
-      if constexpr (FDX) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_MMA + col0);
-#pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
-          uint32_t dm[16], d0[16], dp[16];
-          tmem_ld16(taddr + (uint32_t)(cb * 16), dm);
-          tmem_ld16(taddr + (uint32_t)(64 + cb * 16), d0);
-          tmem_ld16(taddr + (uint32_t)(128 + cb * 16), dp);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(dm[i]), 1);
-            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(dp[i]), 1);
-            v[cb * 16 + i] = __float_as_uint(__uint_as_float(d0[i]) + (lane != 0 ? up : 0.f) + (lane != 31 ? dn : 0.f));
-          }
-        }
-      } else {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_MMA + col0);
-        tmem_ld16(taddr, &v[0]);
-        tmem_ld16(taddr + 16u, &v[16]);
-        if constexpr (STEM) {
-          tmem_ld16(taddr + 64u, &w[0]);
-          tmem_ld16(taddr + 80u, &w[16]);
-        }
-        tmem_ld_wait();
-      }
-      // accumulator read -> hand the TMEM stage back to the MMA warp before the math and the global stores
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) arrive_leader(bar_tempty(acc));
-      if (p.debug & 2) continue;
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {  // 16 columns at a time
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          f[i] = __uint_as_float(v[cb * 16 + i]) + bias_r[cb * 16 + i];
-          if (p.lrelu) f[i] = lrelu(f[i]);
-        }
-        if (has_skip) {
-          const float x0 = __uint_as_float(xrow.x << 16), x1 = __uint_as_float(xrow.x & 0xffff0000u);
-          const float x2 = __uint_as_float(xrow.y << 16), x3 = __uint_as_float(xrow.y & 0xffff0000u);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 wv = s_skipw[col0 + cb * 16 + i];
-            f[i] += x0 * wv.x + x1 * wv.y + x2 * wv.z + x3 * wv.w;
-          }
-        }
-        if (has_res) {
-          const uint4 r0 = *reinterpret_cast<const uint4*>(stg_res + lane * SmemLayout::STG_ROW + cb * 32);
-          const uint4 r1 = *reinterpret_cast<const uint4*>(stg_res + lane * SmemLayout::STG_ROW + cb * 32 + 16);
-          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
-            f[2 * i] += __bfloat162float(r2.x);
-            f[2 * i + 1] += __bfloat162float(r2.y);
-          }
-        }
-        *reinterpret_cast<uint4*>(stg_out + lane * SmemLayout::STG_ROW + cb * 32) = pack8(&f[0]);
-        *reinterpret_cast<uint4*>(stg_out + lane * SmemLayout::STG_ROW + cb * 32 + 16) = pack8(&f[8]);
-        if (p.out2 != nullptr) {
-          float g[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if constexpr (STEM) g[i] = __uint_as_float(w[cb * 16 + i]) + s_t2[col0 + cb * 16 + i];
-            else g[i] = lrelu(s_s2[col0 + cb * 16 + i] * f[i] + s_t2[col0 + cb * 16 + i]);
-          }
-          *reinterpret_cast<uint4*>(stg_out2 + lane * SmemLayout::STG_ROW + cb * 32) = pack8(&g[0]);
-          *reinterpret_cast<uint4*>(stg_out2 + lane * SmemLayout::STG_ROW + cb * 32 + 16) = pack8(&g[8]);
-        }
-      }
-      __syncwarp();
-      if constexpr (STEM) {  // copy-out of the valid rows into the [boards][H+1][W][64] tensors (4 lanes move one 64-byte half row)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = i * 8 + crow;
-          const long long ur = __shfl_sync(0xffffffffu, urow, r);
-          if ((vmask >> r) & 1u) {
-            reinterpret_cast<uint4*>(p.out + ur * CH + col0)[cch] =
-                *reinterpret_cast<const uint4*>(stg_out + r * SmemLayout::STG_ROW + cch * 16);
-            if (p.out2 != nullptr)
-              reinterpret_cast<uint4*>(p.out2 + ur * CH + col0)[cch] =
-                  *reinterpret_cast<const uint4*>(stg_out2 + r * SmemLayout::STG_ROW + cch * 16);
-          }
-        }
-      } else {  // coalesced copy-out of the valid rows
-        uint4* op = reinterpret_cast<uint4*>(p.out + m_warp * CH + col0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = i * 8 + crow;
-          if ((vmask >> r) & 1u)
-            op[r * 8 + cch] = *reinterpret_cast<const uint4*>(stg_out + r * SmemLayout::STG_ROW + cch * 16);
-        }
-        if (p.out2 != nullptr) {
-          uint4* op2 = reinterpret_cast<uint4*>(p.out2 + m_warp * CH + col0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = i * 8 + crow;
-            if ((vmask >> r) & 1u)
-              op2[r * 8 + cch] = *reinterpret_cast<const uint4*>(stg_out2 + r * SmemLayout::STG_ROW + cch * 16);
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-
-teardown:
-  // ---- teardown
-  tc_fence_before();
-  __syncthreads();
-  if constexpr (CG == 2) cluster_sync_all();  // the peer may still be arriving on / reading from this CTA
-  if (warp == 4) {
-    if constexpr (CG == 2)
-      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    else
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // k_conv8: the 64-channel 3x3 conv on NHWC activations [boards][H+1][W][64] (bf16; board row H is a zero pad row that
@@ -697,19 +125,37 @@ teardown:
 // columns exist only in shared memory: activations move through a 3-D tensor map (channel, c, row group = b*(H+1) + r)
 // whose boxes are 8 columns wide - the TMA unit zero-fills c >= W on loads and clips it on stores; the same goes for row
 // groups before the first / after the last board.  A tile is 128 consecutive virtual rows (16 groups); its slab is the tile
-// plus one group above and below: ONE box of (64, 8, 18).
+// plus one group above and below: ONE box of (64, 8, 18), SWIZZLE_128B, i.e. one 128-byte line per virtual row.
 //
 // Tensor core: the three dx taps of a kernel row share ONE A view and become the N dimension,
 //   D[v][dx*64 + co] = sum_dy,k A[v + dy*8][k] W(dy,dx)[k][co]          (12 MMAs of M128 N192 K16 per tile)
-// and the epilogue recombines out[v] = D_-1[v-1] + D_0[v] + D_+1[v+1] with one-lane warp shuffles (a 32-row TMEM lane
-// quarter starts at c = 0, so the only cross-quarter neighbours are the masked c = 0 / c = 7 ones).
+// (the dy view is the slab shifted by whole groups) and the epilogue recombines
+//   out[v] = D_-1[v-1] + D_0[v] + D_+1[v+1]
+// with one-lane warp shuffles: a 32-row TMEM lane quarter starts at c = 0, so the only cross-quarter neighbours are the
+// masked c = 0 / c = W-1 ones.  Compared with nine row-shifted views of N = 64 the slab is fetched from shared memory 3x
+// instead of 9x per tile (the shared-memory datapath, 128 B/clk, was the limiter of that version).
 //
-//   warp 0      one thread: bulk-copies the weight image, then 18 group loads per tile into a ring of S smem stages
-//   warp 1      MMA issuer (tcgen05.mma, two 192-column accumulators in TMEM)
-//   warps 2..   NE epilogue warps; a work item is (tile, 32-row lane quarter, 32-channel half) and the NE/4 warps of a
-//               quarter take items round-robin.  Residual rows arrive by TMA one item ahead, the result is written in place
-//               into the staging buffer (SWIZZLE_64B, row per thread, conflict-free) and leaves by TMA store.
+//   warp 0      one thread: bulk-copies the weight image, then one TMA box per tile into a ring of S smem stages
+//               (STEM: warps 0-3 build the slab of their stage from the 4 observation planes instead)
+//   next warp   MMA issuer (tcgen05.mma, two 192-column accumulators in TMEM)
+//   NE warps    epilogue; a work item is (tile, 32-row lane quarter, 32-channel half) and the NE/4 warps of a quarter take
+//               items round-robin, so several tiles' epilogues are in flight per scheduler.  Residual rows arrive by TMA
+//               one item ahead, the result is written in place into the staging buffer (SWIZZLE_64B, row per thread,
+//               conflict-free) and leaves by TMA store - no per-row predicates, no LDS/STG copy-out.
 // ---------------------------------------------------------------------------------------------------------------------
+struct Conv8Params {
+  const __nv_bfloat16* wpack;
+  const float* bias;
+  const float* s2;
+  const float* t2;
+  const uint2* skip_obs;   // optional: observation planes [boards][H][W][4]; the epilogue adds the 1x1 skip projection
+  const float* skip_w;     //   skip_w [64][4] of the raw planes (network.py:101-103) instead of reading a residual tensor
+  const uint2* stem_obs;   // STEM: the observation planes the slab is built from
+  const float* stem_st;    // STEM: device [8]: bn1 scale[4], shift[4] of the input planes
+  int n_tiles, boards, P, H, W, HP;  // HP = H + 1 row groups per board
+  int lrelu, has_res, has_out2, debug, reverse;
+};
+
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -721,18 +167,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-struct Conv8Params {
-  const __nv_bfloat16* wpack;
-  const float* bias;
-  const float* s2;
-  const float* t2;
-  const uint2* skip_obs;
-  const float* skip_w;
-  int n_tiles, boards, P, H, W, HP;  // HP = H + 1 row groups per board
-  int lrelu, has_res, has_out2, debug, reverse;
-};
-
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
                "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
@@ -747,10 +181,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int 
 constexpr int C8_GROUPS = 18;                 // 8-row groups per slab: 16 of the tile + one above + one below
 constexpr int C8_A_ST = C8_GROUPS * 1024;     // 18,432 B per stage
 constexpr int C8_N = 192;
+constexpr int STEM_SLAB = C8_GROUPS * 8;      // slab rows (the stem's operand is [k-chunk][row] x 16 B)
 
 template <int NE, int S>
 struct Conv8Smem {
-  static constexpr int W_OFF = 0;
+  static constexpr int W_OFF = 0;                        // 73,728 B weight image (stem: 18,432 B)
   static constexpr int A_OFF = W_BYTES;
   static constexpr int STG_OFF = A_OFF + S * C8_A_ST;    // per epilogue warp: io[2] (residual in / result out), out2
   static constexpr int STG_WARP = 3 * 2048;
@@ -764,15 +199,17 @@ struct Conv8Smem {
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <int NE, int S>
-__global__ void __launch_bounds__((2 + NE) * 32, 1)
+template <bool STEM, int NE, int S>
+__global__ void __launch_bounds__(((STEM ? 5 : 2) + NE) * 32, 1)
 k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_res,
         const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2, const Conv8Params p) {
   using L = Conv8Smem<NE, S>;
-  constexpr int K_STEPS = 4;
-  constexpr int W_ROW_BYTES = C8_N * 16 * 2 * K_STEPS;   // one kernel row (dy) of weights: 24,576 B
+  constexpr int NPROD = STEM ? 4 : 1;                    // producer warps; the MMA issuer is warp NPROD, then the epilogue
+  constexpr int K_STEPS = STEM ? 1 : 4;                  // 16-channel k-steps per kernel row
+  constexpr int W_ROW_BYTES = C8_N * 16 * 2 * K_STEPS;   // one kernel row (dy) of weights: 24,576 B (STEM: 6,144 B)
   constexpr int ACC = 2;
   constexpr uint32_t TMEM_COLS = 512u;
+  static_assert(!STEM || S == 4, "one stem producer warp per stage");
   constexpr int NEQ = NE / 4;                            // epilogue warps per TMEM lane quarter
   static_assert(NE % 4 == 0, "whole quarters");
 
@@ -792,7 +229,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
   auto bar_res = [&](int e, int b) { return s_bar + 8u * (2 * S + 5 + 2 * e + b); };
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + L::N_BARS * 8);
 
-  if (warp == 1 && lane == 0) {
+  if (warp == NPROD && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
@@ -808,11 +245,17 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == NPROD) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
                  "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if constexpr (STEM) {  // k-chunk 1 (channels 8..15) of every stage is constant zero
+    for (int i = threadIdx.x; i < S * STEM_SLAB; i += blockDim.x)
+      *reinterpret_cast<uint4*>(smem + L::A_OFF + (i / STEM_SLAB) * C8_A_ST + (STEM_SLAB + i % STEM_SLAB) * 16) =
+          make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -826,9 +269,66 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     return p.reverse ? p.n_tiles - 1 - t : t;
   };
 
-  if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
+  if (warp < NPROD) {
+    if constexpr (STEM) {
+      // =========================== stem producers (one warp per smem stage) ===========================
+      // Build the slab from the observation planes [boards][H][W][4]: k-chunk 0 of virtual row v holds
+      // [LeakyReLU(bn1(x))_0..3 | 0 0 0 0], zero for pad cells.  Operand layout: no-swizzle K-major, [k-chunk][row] x 16 B.
+      const int stage = warp;
+      if (lane == 0 && warp == 0) {
+        mbar_expect_tx(bar_w(), (uint32_t)(3 * W_ROW_BYTES));
+        bulk_g2s(s_w, p.wpack, 3 * W_ROW_BYTES, bar_w());
+      }
+      float bs[4], bt[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        bs[i] = p.stem_st[i];
+        bt[i] = p.stem_st[4 + i];
+      }
+      const uint2* obs = p.stem_obs;
+      const int cells = p.H * p.W;
+      constexpr int PER_LANE = (STEM_SLAB + 31) / 32;
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // the observations are written by the preceding az_step
+      for (int it = stage, round = 0; it < my_tiles; it += S, ++round) {
+        mbar_wait(bar_empty(stage), ((uint32_t)round & 1u) ^ 1u);
+        uint8_t* dst = smem + L::A_OFF + stage * C8_A_ST;
+        const int g_first = tile_of(it) * 16 - 1;
+        uint2 raw[PER_LANE];
+        bool okv[PER_LANE];
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+          const int row = lane + 32 * i;                   // slab row = 8 * group + column
+          const int g = g_first + (row >> 3), c = row & 7;
+          bool ok = row < STEM_SLAB && g >= 0 && c < p.W;
+          int cell = 0;
+          if (ok) {
+            const int b = g / p.HP, r = g - b * p.HP;
+            ok = b < p.boards && r < p.H;
+            cell = b * cells + r * p.W + c;
+          }
+          okv[i] = ok;
+          raw[i] = ok ? obs[cell] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+          const int row = lane + 32 * i;
+          if (row < STEM_SLAB) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (okv[i]) {
+              const float x0 = __uint_as_float(raw[i].x << 16), x1 = __uint_as_float(raw[i].x & 0xffff0000u);
+              const float x2 = __uint_as_float(raw[i].y << 16), x3 = __uint_as_float(raw[i].y & 0xffff0000u);
+              o.x = pack_bf16(lrelu(bs[0] * x0 + bt[0]), lrelu(bs[1] * x1 + bt[1]));
+              o.y = pack_bf16(lrelu(bs[2] * x2 + bt[2]), lrelu(bs[3] * x3 + bt[3]));
+            }
+            *reinterpret_cast<uint4*>(dst + row * 16) = o;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full(stage));
+      }
+    } else if (lane == 0) {
+      // =========================== TMA producer ===========================
       mbar_expect_tx(bar_w(), (uint32_t)W_BYTES);
 #pragma unroll
       for (int i = 0; i < 3; ++i)
@@ -846,7 +346,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == NPROD) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)C8_N);
     mbar_wait(bar_w(), 0u);
@@ -860,7 +360,17 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       if (elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)(acc * C8_N);
         const uint32_t a_stage = s_a + (uint32_t)stage * C8_A_ST;
-        if (!(p.debug & 4)) {
+        if (p.debug & 4) {
+          // (experiment) no MMAs
+        } else if constexpr (STEM) {
+          // no-swizzle K-major: LBO = bytes between the two k-chunks, SBO = 128 B between 8-row groups; the dy view is the
+          // slab shifted by one group
+          const uint64_t ab = umma_desc(a_stage, STEM_SLAB * 16u, 128u);
+          const uint64_t wb = umma_desc(s_w, C8_N * 16u, 128u);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+            umma_bf16(d, ab + (uint64_t)(dy * (128 >> 4)), wb + (uint64_t)(dy * (W_ROW_BYTES >> 4)), idesc, dy != 0 ? 1u : 0u);
+        } else {
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             // SW128: every virtual row is its own 128-byte line, so the dy view is the slab shifted by whole groups
@@ -878,7 +388,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     }
   } else {
     // =========================== epilogue ===========================
-    const int e = warp - 2;
+    const int e = warp - (NPROD + 1);
     const int q = warp & 3;      // TMEM lane quarter this warp may access
     const int j0 = e >> 2;       // round-robin slot among the NEQ warps of this quarter
     {
@@ -903,7 +413,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
     const bool skip_all = (p.debug & 2) != 0;
     const int cc = lane & 7;                         // board column of this thread's row (quarters start at c = 0)
-    const bool up_ok = cc != 0, dn_ok = cc != p.W - 1;
+    const float w_up = (p.W == 8 && cc == 0) ? 0.f : 1.f, w_dn = (p.W == 8 && cc == 7) ? 0.f : 1.f;
 
     // observation planes of this thread's row in item i (for the fused 1x1 skip projection)
     auto obs_of = [&](int i) -> uint2 {
@@ -940,11 +450,14 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         tmem_ld16(taddr + (uint32_t)(64 + cb * 16), d0);
         tmem_ld16(taddr + (uint32_t)(128 + cb * 16), dp);
         tmem_ld_wait();
+        // Rotating shuffles: lane 0 receives lane 31's D_-1 and lane 31 lane 0's D_+1.  With pad columns (W < 8) the
+        // partial sums of a pad cell are zero and its own output is never stored, so the weights are 1; without (W == 8)
+        // the row wrap-around at c = 0 / c = 7 gets weight 0.  (The partial sums are finite, so 0 * x is exact.)
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(dm[k]), 1);
-          const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(dp[k]), 1);
-          v[cb * 16 + k] = __float_as_uint(__uint_as_float(d0[k]) + (up_ok ? up : 0.f) + (dn_ok ? dn : 0.f));
+          const float up = __shfl_sync(0xffffffffu, __uint_as_float(dm[k]), (lane + 31) & 31);
+          const float dn = __shfl_sync(0xffffffffu, __uint_as_float(dp[k]), (lane + 1) & 31);
+          v[cb * 16 + k] = __float_as_uint(fmaf(w_dn, dn, fmaf(w_up, up, __uint_as_float(d0[k]))));
         }
       }
       tc_fence_before();
@@ -1015,7 +528,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  if (warp == NPROD) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1109,74 +622,6 @@ static int nn_fail(int code, const char* what, cudaError_t e) {
   return code;
 }
 
-static int fill_geometry(aznn::ConvParams& p, int32_t board0, int32_t boards, int32_t H, int32_t W, int32_t lead,
-                         int32_t rows_alloc, const char* who) {
-  using namespace aznn;
-  p.Wp = W + 1;
-  p.P = (H + 1) * p.Wp;
-  p.H = H;
-  p.W = W;
-  p.lead = lead;
-  p.boards = boards;
-  p.board0 = board0;
-  p.rows_alloc = rows_alloc;
-  if (rows_alloc % TILE_M != 0 || p.Wp + 1 > MAX_HALO || TILE_M + 2 * (p.Wp + 1) > SLAB || lead < p.Wp + 1 || board0 < 0 ||
-      boards <= 0 || (long long)lead + (long long)(board0 + boards) * p.P > rows_alloc) {
-    snprintf(g_nn_err, sizeof(g_nn_err), "%s: bad geometry (rows_alloc %% 128, lead >= W+2, capacity)", who);
-    return -1;
-  }
-  const long long lo = (long long)lead + (long long)board0 * p.P, hi = lo + (long long)boards * p.P;
-  p.tile0 = (int)(lo / TILE_M);
-  p.n_tiles = (int)((hi + TILE_M - 1) / TILE_M) - p.tile0;
-  return 0;
-}
-
-template <int MODE, int CG>
-static int launch_conv(const aznn::ConvParams& p, int n_ctas, void* stream) {
-  using namespace aznn;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout::TOTAL);
-    if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
-    attr_set = true;
-  }
-  int grid = n_ctas > 0 ? n_ctas : 148;
-  if (grid > p.n_tiles) grid = p.n_tiles;
-  if (CG == 2) grid = grid < 2 ? 2 : (grid & ~1);
-  static int use_pdl = -1;
-  if (use_pdl < 0) {
-    const char* ev = getenv("AZ_NN_PDL");
-    use_pdl = ev ? atoi(ev) : 1;
-  }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = SmemLayout::TOTAL;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
-  if (CG == 2) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2;
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = 1;
-    ++na;
-  }
-  if (use_pdl) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  cfg.attrs = attr;
-  cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv<MODE, CG>, p);
-  if (e != cudaSuccess) return nn_fail(-2, "k_conv launch", e);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return nn_fail(-2, "k_conv launch", e);
-  return 0;
-}
-
 static int env_int(const char* name, int dflt) {
   const char* ev = getenv(name);
   return ev ? atoi(ev) : dflt;
@@ -1213,14 +658,14 @@ static int make_tmap_act(CUtensorMap* m, const void* base, int boards, int H, in
   return 0;
 }
 
-template <int NE, int S>
+template <bool STEM, int NE, int S>
 static int launch_conv8(const CUtensorMap& tm_in, const CUtensorMap& tm_res, const CUtensorMap& tm_out, const CUtensorMap& tm_out2,
                         const aznn::Conv8Params& p, int n_ctas, void* stream) {
   using namespace aznn;
   using L = Conv8Smem<NE, S>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv8<NE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv8<STEM, NE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
     attr_set = true;
   }
@@ -1229,7 +674,7 @@ static int launch_conv8(const CUtensorMap& tm_in, const CUtensorMap& tm_res, con
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((2 + NE) * 32);
+  cfg.blockDim = dim3(((STEM ? 5 : 2) + NE) * 32);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
@@ -1237,7 +682,7 @@ static int launch_conv8(const CUtensorMap& tm_in, const CUtensorMap& tm_res, con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = env_int("AZ_NN_PDL", 1) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv8<NE, S>, tm_in, tm_res, tm_out, tm_out2, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv8<STEM, NE, S>, tm_in, tm_res, tm_out, tm_out2, p);
   if (e != cudaSuccess) return nn_fail(-2, "k_conv8 launch", e);
   e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_conv8 launch", e);
@@ -1282,37 +727,38 @@ extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bia
   if (make_tmap_act(&tm_out2, out2 ? out2 : out, boards, H, W, 32, 4, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
   static int ne = -1;
   if (ne < 0) ne = env_int("AZ_NN_NE", 12);
-  return ne == 16 ? launch_conv8<16, 3>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream)
-                  : launch_conv8<12, 4>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream);
+  return ne == 16 ? launch_conv8<false, 16, 3>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream)
+                  : launch_conv8<false, 12, 4>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream);
 }
 
-extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st,
-                          void* u, void* r, int32_t boards, int32_t H, int32_t W, int32_t n_ctas, void* stream) {
+extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* bn_st, void* u, int32_t boards,
+                          int32_t H, int32_t W, int32_t n_ctas, void* stream) {
   using namespace aznn;
-  if (!obs || !wpack || !b1 || !b3 || !bn_st || !u) {
+  if (!obs || !wpack || !b1 || !bn_st || !u) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_stem: null argument");
     return -1;
   }
-  ConvParams p;
-  memset(&p, 0, sizeof(p));
-  p.in = (const __nv_bfloat16*)obs;
-  p.wpack = (const __nv_bfloat16*)wpack;
-  p.bias = b1;
-  p.out = (__nv_bfloat16*)u;
-  p.out2 = (__nv_bfloat16*)r;
-  p.t2 = b3;
-  p.lrelu = 1;
-  p.stem_st = bn_st;
-  p.debug = env_int("AZ_NN_DEBUG", 0);
-  // the stem tiles its own virtual row space (pitch W+1, 16 lead rows); only the stores address the [boards][H+1][W][64] outputs
-  const int lead = 16;
-  const long long rows = (long long)lead + (long long)boards * (H + 1) * (W + 1) + W + 2;
-  if (rows > 0x7fffff00LL) {
-    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_stem: too many boards");
+  if (boards <= 0 || H < 3 || H > 16 || W < 2 || W > 8) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_stem: needs boards > 0, 3 <= H <= 16, 2 <= W <= 8");
     return -1;
   }
-  if (fill_geometry(p, 0, boards, H, W, lead, (int)((rows + TILE_M - 1) / TILE_M * TILE_M), "az_nn_stem")) return -1;
-  return launch_conv<MODE_STEM, 1>(p, n_ctas, stream);
+  Conv8Params p;
+  memset(&p, 0, sizeof(p));
+  p.wpack = (const __nv_bfloat16*)wpack;
+  p.bias = b1;
+  p.stem_obs = (const uint2*)obs;
+  p.stem_st = bn_st;
+  p.boards = boards;
+  p.H = H;
+  p.W = W;
+  p.HP = H + 1;
+  p.P = p.HP * 8;
+  p.n_tiles = (int)(((long long)boards * p.P + TILE_M - 1) / TILE_M);
+  p.lrelu = 1;
+  p.debug = env_int("AZ_NN_DEBUG", 0);
+  CUtensorMap tm_out;
+  if (make_tmap_act(&tm_out, u, boards, H, W, 32, 4, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
+  return launch_conv8<true, 12, 4>(tm_out, tm_out, tm_out, tm_out, p, n_ctas, stream);
 }
 
 extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t boards,

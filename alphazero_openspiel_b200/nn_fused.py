@@ -61,7 +61,6 @@ class FusedEvaluator:
         # small action spaces (Connect Four) finish with the streaming k_head kernel; larger ones with a cuBLAS GEMM
         self.fused_head = self.A + 1 <= 8 and 8 * ((self.h + 1) * self.w * 8 + 4) * 16 <= 100 * 1024 and \
             os.environ.get("AZ_NN_HEAD", "1") != "0"
-        self.fuse_skip = os.environ.get("AZ_NN_SKIPFUSE", "1") != "0"
         self.timing = None   # set to a list to collect (kernel, start_event, end_event) per launch (bench.py roofline)
         self.load(net)
 
@@ -92,14 +91,14 @@ class FusedEvaluator:
             if k == 0:
                 cin = blk.conv1.in_channels
                 assert cin == 4 and blk.use_1x1conv
-                # stem operand image [9 taps][2 k-chunks][128 n][8]: n<64 conv1 on k 0-3 (input lrelu(bn1(x))),
-                # n>=64 the 1x1 skip projection on k 4-7 (raw x) of the centre tap
-                sw = torch.zeros((9, 2, 128, 8), dtype=torch.float64)
-                sw[:, 0, :N_FILTERS, 0:4] = w1.permute(2, 3, 0, 1).reshape(9, N_FILTERS, 4)
-                sw[4, 0, CH:CH + N_FILTERS, 4:8] = blk.conv3.weight.double().cpu().reshape(N_FILTERS, 4)
+                # stem operand image [3 ky][2 k-chunks][192 = kx*64 + n][8]: conv1 on k 0-3 (its input is lrelu(bn1(x)))
+                sw = torch.zeros((3, 2, 3 * CH, 8), dtype=torch.float64)
+                w1p = torch.zeros((CH, 4, 3, 3), dtype=torch.float64)
+                w1p[:N_FILTERS] = w1
+                sw[:, 0, :, 0:4] = w1p.permute(2, 3, 0, 1).reshape(3, 3 * CH, 4)
+                new["stem_w"] = sw.to(torch.bfloat16)
                 sb3 = torch.zeros(CH, dtype=torch.float64)
                 sb3[:N_FILTERS] = blk.conv3.bias.double().cpu()
-                new["stem_w"], new["stem_b3"] = sw.to(torch.bfloat16), sb3.float()
                 skw = torch.zeros((CH, 4), dtype=torch.float64)        # 1x1 skip projection, added by block 1's conv2
                 skw[:N_FILTERS] = blk.conv3.weight.double().cpu().reshape(N_FILTERS, 4)
                 new["skip_w"] = skw.float()
@@ -160,19 +159,15 @@ class FusedEvaluator:
         P_ = self.par
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         rc = self._timed("stem", lambda: self.lib.az_nn_stem(
-            p(self.obs), p(P_["stem_w"]), p(P_["b1_0"]), p(P_["stem_b3"]), p(P_["stem_st"]), p(self.U),
-            None if self.fuse_skip else p(self.X), self.batch, self.h, self.w, self.n_ctas, self._stream()))
+            p(self.obs), p(P_["stem_w"]), p(P_["b1_0"]), p(P_["stem_st"]), p(self.U), self.batch, self.h, self.w,
+            self.n_ctas, self._stream()))
         if rc:
             raise RuntimeError("az_nn_stem: " + self.lib.az_nn_last_error().decode())
         # Layers alternate their tile direction: each reads its input starting from the part the previous layer wrote
         # last (still in L2); the stem writes front to back, so the first conv goes back to front.
-        if self.fuse_skip:
-            # block 1, second conv: X = conv(U) + conv1x1(obs) ; T = lrelu(bn1_2(X))   (skip projection in the epilogue)
-            self._conv(self.U, P_["w2_0"], P_["b2skip_0"], None, self.X, self.T, P_["s_1"], P_["t_1"], False,
-                       skip_obs=self.obs, skip_w=P_["skip_w"], flags=L.NN_F_REVERSE)
-        else:
-            self._conv(self.U, P_["w2_0"], P_["b2_0"], self.X, self.X, self.T, P_["s_1"], P_["t_1"], False,
-                       flags=L.NN_F_REVERSE)
+        # block 1, second conv: X = conv(U) + conv1x1(obs) ; T = lrelu(bn1_2(X))   (skip projection in the epilogue)
+        self._conv(self.U, P_["w2_0"], P_["b2skip_0"], None, self.X, self.T, P_["s_1"], P_["t_1"], False,
+                   skip_obs=self.obs, skip_w=P_["skip_w"], flags=L.NN_F_REVERSE)
         for k in range(1, 5):
             self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True)
             last = k == 4

@@ -247,11 +247,10 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  *   tile; n_ctas <= 0 -> one CTA per SM.  With skip_obs (the az_step observation batch) and skip_w [64][4] fp32 the
  *   epilogue adds the 1x1 skip projection of the raw planes (resblock1.conv3, network.py:101-103) instead of reading a
  *   residual tensor.  res may alias out (in-place residual stream).  flags: AZ_NN_F_*.
- * az_nn_stem: the 4-plane first block, slab built from the az_step AZ_OBS_BF16_NHWC batch [boards][H][W][4]:
- *   u = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1), r = conv1x1(x) + b3 (network.py:99-103 for resblock1; r may be NULL when
- *   the next conv computes the projection itself).  wpack is [9 taps][2][128][8] bf16: rows 0-63 = conv1 (BatchNorm
- *   folded) on k 0-3, rows 64-127 = the 1x1 skip projection on k 4-7 of the centre tap.  bn_st = device [8]: scale[4],
- *   shift[4].
+ * az_nn_stem: the first conv of resblock1 on the 4 observation planes, slab built from the az_step AZ_OBS_BF16_NHWC batch
+ *   [boards][H][W][4]: u = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1) (network.py:99-100; the block's 1x1 skip projection
+ *   is added by the following az_nn_conv3x3 through skip_obs).  wpack is bf16 [3 ky][2 k-chunks][192 = kx*64 + n][8],
+ *   no-swizzle K-major, only k 0-3 of chunk 0 non-zero (BatchNorm 2 folded).  bn_st = device [8]: scale[4], shift[4].
  * az_nn_head: the FC head (fc1, network.py:48,61-66) for games with n_actions + 1 <= 8 outputs: priors [.][n_actions] =
  *   softmax(x_flat @ w[0..A-1]^T + bias), values = tanh(x_flat @ w[A]^T + bias[A]), fp32.  w is bf16 [8][(H+1)*W*64] over the
  *   flatten of one board (zero on the pad row / pad channels / unused outputs), bias fp32 [8]. */
@@ -261,8 +260,8 @@ const char* az_nn_last_error(void);
 int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
                   const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t boards, int32_t H,
                   int32_t W, int32_t lrelu, int32_t flags, int32_t n_ctas, void* stream);
-int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* b3, const float* bn_st, void* u,
-               void* r, int32_t boards, int32_t H, int32_t W, int32_t n_ctas, void* stream);
+int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* bn_st, void* u, int32_t boards, int32_t H,
+               int32_t W, int32_t n_ctas, void* stream);
 int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t boards, int32_t H,
                int32_t W, int32_t n_actions, int32_t n_ctas, void* stream);
 
