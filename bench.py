@@ -26,6 +26,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per k_conv8 launch, averaged over the nine launches of one evaluation
+# (ncu --set full, profiles/r01_conv8_full_raw.csv; Connect Four, 16,384 boards).  None until captured for another shape.
+CONV_DRAM_TRAFFIC = 250.1e6
 FLOPS_PER_EVAL = {"connect_four": 17211600, "breakthrough(rows=6,columns=6)": 16282800, "breakthrough": 31097600}
 
 
@@ -313,26 +316,37 @@ def run_ours(args):
                      "share_of_step": step_ms / (step_ms + nn_ms)}
     conv_roofline = None
     if fused and conv_n:
-        # dominant kernel: k_conv<false> (3x3 conv, 50->50 filters).  Algorithmic FLOPs per launch = boards x 2*HW*50*50*9.
+        # dominant kernel: k_conv8 (3x3 conv, 50->50 filters, nine launches per evaluation).  Per launch the algorithm
+        # needs boards x 2*HW*50*50*9 FLOPs (30.97 GFLOP, 19 us at the bf16 peak) and reads / writes every [B][H][W][64] bf16
+        # tensor it touches once: in + out (+ residual) (+ second output) = 2-4 x 88 MB, 254 MB averaged over the nine
+        # launches of one evaluation (39 us at the measured HBM peak) -> HBM is the binding roofline.
         conv_flops = args.trees * 2.0 * rows * cols * 50 * 50 * 9
+        tensor_bytes = args.trees * rows * cols * 64 * 2.0
+        n_tensors = {"conv": 2, "conv+res": 3, "conv+res+out2": 4, "conv+skip+out2": 3}
+        conv_bytes = sum(n_tensors.get(k, 2) * tensor_bytes * v[1] for k, v in by_name.items() if k.startswith("conv")) / conv_n
         avg_conv_ms = conv_ms / conv_n
-        ach = conv_flops / (avg_conv_ms / 1e3) / 1e12
-        conv_roofline = {"kernel": "k_conv<false> (tcgen05 implicit-GEMM 3x3 conv + fused BN/LeakyReLU/residual epilogue)",
-                         "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["bf16_tflops"], "traffic": 134.4e6, "peak_source": peaks["source"] + " (burst)",
+        ach = conv_bytes / (avg_conv_ms / 1e3) / 1e9
+        conv_roofline = {"kernel": "k_conv8 (tcgen05 implicit-GEMM 3x3 conv, TMA in/out, fused BN/LeakyReLU/residual epilogue)",
+                         "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": ach / peaks["hbm_gbs"], "traffic": CONV_DRAM_TRAFFIC, "peak_source": peaks["source"],
                          "avg_launch_ms": avg_conv_ms, "launches_per_step": conv_n / n_probe,
-                         "algorithmic_flops_per_launch": conv_flops, "stem_avg_launch_ms": stem_ms / n_probe,
+                         "algorithmic_bytes_per_launch": conv_bytes, "algorithmic_flops_per_launch": conv_flops,
+                         "tensor_tflops": conv_flops / (avg_conv_ms / 1e3) / 1e12,
+                         "tensor_frac_of_burst_peak": conv_flops / (avg_conv_ms / 1e3) / 1e12 / peaks["bf16_tflops"],
+                         "stem_avg_launch_ms": stem_ms / n_probe,
                          "share_of_step": conv_ms / n_probe / (step_ms + nn_ms),
                          "launch_ms_by_kind": {k: v[0] / v[1] for k, v in sorted(by_name.items())},
-                         "note": "measured limiter is shared-memory bandwidth (SS-mode operand fetch at N=64), see DESIGN.md; "
-                                 "traffic = dram read+write of a conv1-type launch from profiles/r01_conv_full_raw.csv"}
+                         "note": "averaged over the nine conv launches of one evaluation (4 plain, 1 +res, 3 +res+out2, "
+                                 "1 +skip+out2); traffic = dram read+write per launch averaged the same way from "
+                                 "profiles/r01_conv8_full_raw.csv; the run is power-capped (see clocks), so the launch "
+                                 "times are those of ~1.6 GHz SM clocks"}
     line = {
         "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "game": game, "n_playouts": args.playouts,
                    "trees_per_gpu": args.trees, "parallelism": "independent game pool per GPU (x%d)" % world,
-                   "evaluator": ("ResNet 5x50 bf16, hand-written tcgen05 implicit-GEMM convs (az_resnet.cu) + cuBLAS FC head"
+                   "evaluator": ("ResNet 5x50 bf16, hand-written tcgen05 implicit-GEMM convs + FC head kernel (az_resnet.cu)"
                                  if args.evaluator == "fused" else "ResNet 5x50 bf16 channels-last via PyTorch")
                    + ", random-init weights",
                    "noise": "device Dirichlet(0.3), ratio 0.25", "start": "counter % 21 random plies",
@@ -345,8 +359,9 @@ def run_ours(args):
         "e2e": {"value": e2e_sims / t_e2e, "unit": "sims/s", "h2d_bytes_per_step": h2d / args.steps,
                 "d2h_bytes_per_step": d2h / args.steps,
                 "what": "SelfPlayRunner.load_weights(host net) + round(K) + drain()/counters() to host, wall clock"},
-        # our kernels per round trip: k_step, k_compact, stem + 9 convs (the FC head / softmax / tanh are library calls)
-        "gpu_launches": args.steps * world * ((2 if not args.no_keep_tree else 1) + ((11 if getattr(ev, 'fused_head', False) else 10) if fused else 0)),
+        # our kernels per round trip: k_step, k_compact, stem + 9 convs + k_head (larger action spaces: cuBLAS FC head)
+        "gpu_launches": args.steps * world * ((2 if not args.no_keep_tree else 1) +
+                                              ((11 if getattr(ev, "fused_head", False) else 10) if fused else 0)),
         "roofline": conv_roofline if fused else tree_roofline,
         "tree_roofline": tree_roofline,
         "nn_roofline": {"kernel": "ResNet forward (%s): stem + 9 convs + FC head" % args.evaluator, "bound": "tensor",
