@@ -6,7 +6,7 @@
 //
 // Activations are NHWC bf16 tensors [boards][H+1][W][64] (50 filters zero-padded to 64; board row H is a zero pad row that
 // separates consecutive boards).  Three kernels:
-//   k_conv8<false>  3x3 conv 64 -> 64 with bias / LeakyReLU / residual / next-BatchNorm / skip-projection epilogues
+//   k_conv8<false>  3x3 conv 64 -> 64 with bias / LeakyReLU / residual / next-BatchNorm epilogues
 //   k_conv8<true>   the 4-plane stem (first conv of block 1), same pipeline with a computing producer
 //   k_head          FC + softmax + tanh for small action spaces
 // Measured history of the conv kernel (limiters, what was tried) is in profiles/r01_summary.md.
@@ -148,8 +148,6 @@ struct Conv8Params {
   const float* bias;
   const float* s2;
   const float* t2;
-  const uint2* skip_obs;   // optional: observation planes [boards][H][W][4]; the epilogue adds the 1x1 skip projection
-  const float* skip_w;     //   skip_w [64][4] of the raw planes (network.py:101-103) instead of reading a residual tensor
   const uint2* stem_obs;   // STEM: the observation planes the slab is built from
   const float* stem_st;    // STEM: device [8]: bn1 scale[4], shift[4] of the input planes
   int n_tiles, boards, P, H, W, HP;  // HP = H + 1 row groups per board
@@ -192,8 +190,7 @@ struct Conv8Smem {
   static constexpr int BIAS_OFF = STG_OFF + NE * STG_WARP;
   static constexpr int S2_OFF = BIAS_OFF + 256;
   static constexpr int T2_OFF = S2_OFF + 256;
-  static constexpr int SKIPW_OFF = T2_OFF + 256;
-  static constexpr int BAR_OFF = SKIPW_OFF + 1024;       // full[S] empty[S] tfull[2] tempty[2] w resbar[NE][2]
+  static constexpr int BAR_OFF = T2_OFF + 256;       // full[S] empty[S] tfull[2] tempty[2] w resbar[NE][2]
   static constexpr int N_BARS = 2 * S + 5 + 2 * NE;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
   static_assert(TOTAL <= 232448, "shared memory budget");
@@ -397,15 +394,12 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         s_bias[et] = p.bias[et];
         s_s2[et] = (p.has_out2 && p.s2) ? p.s2[et] : 0.f;
         s_t2[et] = (p.has_out2 && p.t2) ? p.t2[et] : 0.f;
-        reinterpret_cast<float4*>(smem + L::SKIPW_OFF)[et] =
-            p.skip_obs ? reinterpret_cast<const float4*>(p.skip_w)[et] : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(NE * 32) : "memory");
     }
     uint8_t* stg = smem + L::STG_OFF + e * L::STG_WARP;
     const uint32_t stg_u32 = smem_u32(stg);
-    const bool has_res = p.has_res != 0, has_out2 = p.has_out2 != 0, has_skip = p.skip_obs != nullptr;
-    const float4* s_skipw = reinterpret_cast<const float4*>(smem + L::SKIPW_OFF);
+    const bool has_res = p.has_res != 0, has_out2 = p.has_out2 != 0;
     const int cells = p.H * p.W;
     const int n_items = my_tiles * 2;
     // this thread's row inside a 32-row x 64-byte SWIZZLE_64B box: chunk c lives at chunk position c ^ ((row >> 1) & 3)
@@ -415,11 +409,13 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     const int cc = lane & 7;                         // board column of this thread's row (quarters start at c = 0)
     const float w_up = (p.W == 8 && cc == 0) ? 0.f : 1.f, w_dn = (p.W == 8 && cc == 7) ? 0.f : 1.f;
 
-    // observation planes of this thread's row in item i (for the fused 1x1 skip projection)
+    // STEM: the raw observation planes of this thread's row in item i; they ride along in the spare channels 50-53 of the
+    // stem's output, where the next conv's centre tap holds the 1x1 skip projection of the block (network.py:101-103), so
+    // the projection costs nothing but four weight rows
     auto obs_of = [&](int i) -> uint2 {
       const int g = tile_of(i >> 1) * 16 + q * 4 + (lane >> 3);
       const int b = g / p.HP, r = g - b * p.HP;
-      if (b < p.boards && r < p.H && cc < p.W) return p.skip_obs[(long long)b * cells + r * p.W + cc];
+      if (b < p.boards && r < p.H && cc < p.W) return p.stem_obs[(long long)b * cells + r * p.W + cc];
       return make_uint2(0u, 0u);
     };
     // the four row groups of item i arrive as one (32 ch, 8, 4) box
@@ -430,7 +426,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     asm volatile("griddepcontrol.wait;" ::: "memory");  // residual reads / output writes depend on the previous layer
     uint2 xnext = make_uint2(0u, 0u);
     if (j0 < n_items) {
-      if (has_skip) xnext = obs_of(j0);
+      if (STEM) xnext = obs_of(j0);
       if (has_res && !skip_all && lane == 0) load_res(j0, 0);
     }
     for (int i = j0, n = 0; i < n_items; i += NEQ, ++n) {
@@ -469,7 +465,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       __syncwarp();
       const int inext = i + NEQ;
       if (inext < n_items) {
-        if (has_skip) xnext = obs_of(inext);
+        if (STEM) xnext = obs_of(inext);
         if (has_res && lane == 0) load_res(inext, b ^ 1);
       }
       if (has_res) mbar_wait(bar_res(e, b), (uint32_t)(n >> 1) & 1u);
@@ -484,13 +480,12 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
           f[k] = __uint_as_float(v[cb * 16 + k]) + s_bias[col0 + cb * 16 + k];
           if (p.lrelu) f[k] = lrelu(f[k]);
         }
-        if (has_skip) {
-          const float x0 = __uint_as_float(xrow.x << 16), x1 = __uint_as_float(xrow.x & 0xffff0000u);
-          const float x2 = __uint_as_float(xrow.y << 16), x3 = __uint_as_float(xrow.y & 0xffff0000u);
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float4 wv = s_skipw[col0 + cb * 16 + k];
-            f[k] += x0 * wv.x + x1 * wv.y + x2 * wv.z + x3 * wv.w;
+        if constexpr (STEM) {
+          if (half == 1 && cb == 1) {  // channels 50..53 = columns 2..5 of this 16-column block
+            f[2] = __uint_as_float(xrow.x << 16);
+            f[3] = __uint_as_float(xrow.x & 0xffff0000u);
+            f[4] = __uint_as_float(xrow.y << 16);
+            f[5] = __uint_as_float(xrow.y & 0xffff0000u);
           }
         }
         if (has_res) {
@@ -690,15 +685,15 @@ static int launch_conv8(const CUtensorMap& tm_in, const CUtensorMap& tm_res, con
 }
 
 extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                             const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t boards,
-                             int32_t H, int32_t W, int32_t lrelu, int32_t flags, int32_t n_ctas, void* stream) {
+                             const float* s2, const float* t2, int32_t boards, int32_t H, int32_t W, int32_t lrelu,
+                             int32_t flags, int32_t n_ctas, void* stream) {
   using namespace aznn;
   if (!in || !wpack || !bias || !out) {
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: null argument");
     return -1;
   }
-  if (boards <= 0 || H < 3 || H > 16 || W < 2 || W > 8 || (skip_obs && !skip_w)) {
-    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: needs boards > 0, 3 <= H <= 16, 2 <= W <= 8, skip_w with skip_obs");
+  if (boards <= 0 || H < 3 || H > 16 || W < 2 || W > 8) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_conv3x3: needs boards > 0, 3 <= H <= 16, 2 <= W <= 8");
     return -1;
   }
   Conv8Params p;
@@ -707,8 +702,6 @@ extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bia
   p.bias = bias;
   p.s2 = s2;
   p.t2 = t2;
-  p.skip_obs = (const uint2*)skip_obs;
-  p.skip_w = skip_obs ? skip_w : nullptr;
   p.boards = boards;
   p.H = H;
   p.W = W;

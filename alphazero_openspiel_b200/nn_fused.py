@@ -8,8 +8,8 @@ of every board is a zero pad row)
 k_head kernel (FC + softmax + tanh in one launch, fp32 logits) when A + 1 <= 8 (Connect Four); for larger action spaces
 it is a plain [B, (H+1)*W*64] x [(H+1)*W*64, A+1] GEMM and stays a cuBLAS call through torch, with softmax/tanh on its output.
 
-Per evaluation:   stem(obs) -> U
-                  X = conv(U) + conv1x1(obs), T = lrelu(bn1_2(X))      (block 1, conv2; skip projection in its epilogue)
+Per evaluation:   stem(obs) -> U (channels 50-53: the raw planes)
+                  X = conv(U) [+ conv1x1(obs) through those channels], T = lrelu(bn1_2(X))      (block 1, conv2)
                   for k = 2..5:  U = lrelu(conv(T) + b)  ;  X = conv(U) + X, T = lrelu(bn1_{k+1}(X))
                   head: softmax / tanh (X_flat @ Wfc + b)
 """
@@ -23,6 +23,7 @@ from . import _lib as L
 from .network import N_FILTERS, _fold_bn
 
 CH = 64
+SKIP_CH = 50   # first of the four spare channels that carry the raw observation planes out of the stem
 
 
 def pack_conv3x3(w):
@@ -99,10 +100,11 @@ class FusedEvaluator:
                 new["stem_w"] = sw.to(torch.bfloat16)
                 sb3 = torch.zeros(CH, dtype=torch.float64)
                 sb3[:N_FILTERS] = blk.conv3.bias.double().cpu()
-                skw = torch.zeros((CH, 4), dtype=torch.float64)        # 1x1 skip projection, added by block 1's conv2
-                skw[:N_FILTERS] = blk.conv3.weight.double().cpu().reshape(N_FILTERS, 4)
-                new["skip_w"] = skw.float()
-                new["b2skip_0"] = (bias2 + sb3).float()                 # conv2 bias + projection bias
+                # the 1x1 skip projection (conv3) rides in conv2: the stem leaves the raw planes in channels 50..53 of U,
+                # conv2's centre tap maps them with conv3's weights, conv3's bias joins conv2's
+                w2p[:N_FILTERS, SKIP_CH:SKIP_CH + 4, 1, 1] = blk.conv3.weight.double().cpu().reshape(N_FILTERS, 4)
+                new["w2_0"] = pack_conv3x3(w2p)
+                new["b2_0"] = (bias2 + sb3).float()
                 new["stem_st"] = torch.cat([a1, b1]).float()
             else:
                 w1p = torch.zeros((CH, CH, 3, 3), dtype=torch.float64)
@@ -143,12 +145,11 @@ class FusedEvaluator:
         self.timing.append((name, e0, e1))
         return rc
 
-    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, skip_obs=None, skip_w=None, flags=0):
+    def _conv(self, inp, w, b, res, out, out2, s2, t2, lrelu, flags=0):
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
-        name = "conv" + ("+res" if res is not None else "") + ("+skip" if skip_obs is not None else "") + \
-            ("+out2" if out2 is not None else "")
+        name = "conv" + ("+res" if res is not None else "") + ("+out2" if out2 is not None else "")
         rc = self._timed(name, lambda: self.lib.az_nn_conv3x3(
-            p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), p(skip_obs), p(skip_w), self.batch, self.h, self.w,
+            p(inp), p(w), p(b), p(res), p(out), p(out2), p(s2), p(t2), self.batch, self.h, self.w,
             1 if lrelu else 0, flags, self.n_ctas, self._stream()))
         if rc:
             raise RuntimeError("az_nn_conv3x3: " + self.lib.az_nn_last_error().decode())
@@ -165,9 +166,8 @@ class FusedEvaluator:
             raise RuntimeError("az_nn_stem: " + self.lib.az_nn_last_error().decode())
         # Layers alternate their tile direction: each reads its input starting from the part the previous layer wrote
         # last (still in L2); the stem writes front to back, so the first conv goes back to front.
-        # block 1, second conv: X = conv(U) + conv1x1(obs) ; T = lrelu(bn1_2(X))   (skip projection in the epilogue)
-        self._conv(self.U, P_["w2_0"], P_["b2skip_0"], None, self.X, self.T, P_["s_1"], P_["t_1"], False,
-                   skip_obs=self.obs, skip_w=P_["skip_w"], flags=L.NN_F_REVERSE)
+        # block 1, second conv: X = conv(U) + conv1x1(obs) ; T = lrelu(bn1_2(X))   (skip projection inside the conv)
+        self._conv(self.U, P_["w2_0"], P_["b2_0"], None, self.X, self.T, P_["s_1"], P_["t_1"], False, flags=L.NN_F_REVERSE)
         for k in range(1, 5):
             self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True)
             last = k == 4

@@ -244,12 +244,11 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  wpack is bf16 [3 ky][192 = kx*64 + n][8][8]:
  *   per kernel row the three kx taps side by side, each row n = 64 input channels (128 B) in the SWIZZLE_128B K-major UMMA
  *   image (16-byte chunk c stored at position c ^ (n & 7)).  tcgen05 implicit GEMM, 12 MMAs of M128 N192 K16 per 128-row
- *   tile; n_ctas <= 0 -> one CTA per SM.  With skip_obs (the az_step observation batch) and skip_w [64][4] fp32 the
- *   epilogue adds the 1x1 skip projection of the raw planes (resblock1.conv3, network.py:101-103) instead of reading a
- *   residual tensor.  res may alias out (in-place residual stream).  flags: AZ_NN_F_*.
+ *   tile; n_ctas <= 0 -> one CTA per SM.  res may alias out (in-place residual stream).  flags: AZ_NN_F_*.
  * az_nn_stem: the first conv of resblock1 on the 4 observation planes, slab built from the az_step AZ_OBS_BF16_NHWC batch
- *   [boards][H][W][4]: u = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1) (network.py:99-100; the block's 1x1 skip projection
- *   is added by the following az_nn_conv3x3 through skip_obs).  wpack is bf16 [3 ky][2 k-chunks][192 = kx*64 + n][8],
+ *   [boards][H][W][4]: u[0..49] = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1) (network.py:99-100) and u[50..53] = x, the raw
+ *   planes: the block's 1x1 skip projection (resblock1.conv3, network.py:101-103) is then four extra input channels of the
+ *   centre tap of the following az_nn_conv3x3.  wpack is bf16 [3 ky][2 k-chunks][192 = kx*64 + n][8],
  *   no-swizzle K-major, only k 0-3 of chunk 0 non-zero (BatchNorm 2 folded).  bn_st = device [8]: scale[4], shift[4].
  * az_nn_head: the FC head (fc1, network.py:48,61-66) for games with n_actions + 1 <= 8 outputs: priors [.][n_actions] =
  *   softmax(x_flat @ w[0..A-1]^T + bias), values = tanh(x_flat @ w[A]^T + bias[A]), fp32.  w is bf16 [8][(H+1)*W*64] over the
@@ -258,8 +257,8 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
                              output is still in L2) */
 const char* az_nn_last_error(void);
 int az_nn_conv3x3(const void* in, const void* wpack, const float* bias, const void* res, void* out, void* out2,
-                  const float* s2, const float* t2, const void* skip_obs, const float* skip_w, int32_t boards, int32_t H,
-                  int32_t W, int32_t lrelu, int32_t flags, int32_t n_ctas, void* stream);
+                  const float* s2, const float* t2, int32_t boards, int32_t H, int32_t W, int32_t lrelu, int32_t flags,
+                  int32_t n_ctas, void* stream);
 int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* bn_st, void* u, int32_t boards, int32_t H,
                int32_t W, int32_t n_ctas, void* stream);
 int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t boards, int32_t H,

@@ -18,7 +18,7 @@ st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for name, res, out2 in [("conv1-type", None, None), ("conv2+res", r, None), ("conv2+res+out2", r, o2)]:
     def run():
         rc = lib.az_nn_conv3x3(p(x), p(w), p(b), p(res), p(o), p(out2), p(s2) if out2 is not None else None,
-                               p(t2) if out2 is not None else None, None, None, B, H, W, 1 if res is None else 0, 0, 0, st)
+                               p(t2) if out2 is not None else None, B, H, W, 1 if res is None else 0, 0, 0, st)
         assert rc == 0, lib.az_nn_last_error()
     for _ in range(3): run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -44,7 +44,7 @@ def test_conv3x3_tcgen05_matches_torch(H, W, B):
         out = rin.clone() if inplace else torch.full((B, H + 1, W, 64), 7.0, dtype=torch.bfloat16, device=dev)
         out2 = torch.full((B, H + 1, W, 64), 7.0, dtype=torch.bfloat16, device=dev) if use_out2 else None
         rc = lib.az_nn_conv3x3(ptr(xin), ptr(wp), ptr(bias), ptr(out if inplace else rin) if use_res else None, ptr(out),
-                               ptr(out2), ptr(s2) if use_out2 else None, ptr(t2) if use_out2 else None, None, None, B, H, W,
+                               ptr(out2), ptr(s2) if use_out2 else None, ptr(t2) if use_out2 else None, B, H, W,
                                lrelu, use_res, 0, st)   # flags: the residual variants also run back to front
         assert rc == 0, lib.az_nn_last_error()
         torch.cuda.synchronize()
