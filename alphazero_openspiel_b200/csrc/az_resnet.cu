@@ -179,7 +179,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int 
 constexpr int C8_GROUPS = 18;                 // 8-row groups per slab: 16 of the tile + one above + one below
 constexpr int C8_A_ST = C8_GROUPS * 1024;     // 18,432 B per stage
 constexpr int C8_N = 192;
-constexpr int STEM_SLAB = C8_GROUPS * 8;      // slab rows (the stem's operand is [k-chunk][row] x 16 B)
+// The stem's tensor-core work is tiny (K = 16), so it keeps nine row-shifted views of N = 64 and the cheap epilogue: no
+// dx recombination.  Its slab has two groups of halo on each side (a tap reaches 9 rows back) and exists in three copies,
+// one per dx, because without a pad column (W = 8) the dx = -1 / +1 views must not see the cell that wraps around from
+// the neighbouring board row: copy 0 has column 7 zeroed, copy 2 column 0.  Layout per copy: [2 k-chunks][row] x 16 B.
+constexpr int STEM_SLAB = 20 * 8;             // slab rows
+constexpr int STEM_COPY = 2 * STEM_SLAB * 16; // 5,120 B per copy, three copies per stage
 
 template <int NE, int S>
 struct Conv8Smem {
@@ -202,8 +207,9 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2, const Conv8Params p) {
   using L = Conv8Smem<NE, S>;
   constexpr int NPROD = STEM ? 4 : 1;                    // producer warps; the MMA issuer is warp NPROD, then the epilogue
-  constexpr int K_STEPS = STEM ? 1 : 4;                  // 16-channel k-steps per kernel row
-  constexpr int W_ROW_BYTES = C8_N * 16 * 2 * K_STEPS;   // one kernel row (dy) of weights: 24,576 B (STEM: 6,144 B)
+  constexpr int K_STEPS = 4;                             // 16-channel k-steps per kernel row
+  constexpr int W_ROW_BYTES = C8_N * 16 * 2 * K_STEPS;   // one kernel row (dy) of weights: 24,576 B
+  constexpr int STEM_TAP_BYTES = 2 * CH * 16;            // stem: one tap = [2 k-chunks][64 n][8] bf16
   constexpr int ACC = 2;
   constexpr uint32_t TMEM_COLS = 512u;
   static_assert(!STEM || S == 4, "one stem producer warp per stage");
@@ -248,10 +254,12 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if constexpr (STEM) {  // k-chunk 1 (channels 8..15) of every stage is constant zero
-    for (int i = threadIdx.x; i < S * STEM_SLAB; i += blockDim.x)
-      *reinterpret_cast<uint4*>(smem + L::A_OFF + (i / STEM_SLAB) * C8_A_ST + (STEM_SLAB + i % STEM_SLAB) * 16) =
+  if constexpr (STEM) {  // k-chunk 1 (channels 8..15) of every slab copy is constant zero
+    for (int i = threadIdx.x; i < S * 3 * STEM_SLAB; i += blockDim.x) {
+      const int st = i / (3 * STEM_SLAB), cp = (i / STEM_SLAB) % 3, row = i % STEM_SLAB;
+      *reinterpret_cast<uint4*>(smem + L::A_OFF + st * C8_A_ST + cp * STEM_COPY + (STEM_SLAB + row) * 16) =
           make_uint4(0u, 0u, 0u, 0u);
+    }
     fence_proxy_async();
   }
   tc_fence_before();
@@ -269,12 +277,12 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
   if (warp < NPROD) {
     if constexpr (STEM) {
       // =========================== stem producers (one warp per smem stage) ===========================
-      // Build the slab from the observation planes [boards][H][W][4]: k-chunk 0 of virtual row v holds
-      // [LeakyReLU(bn1(x))_0..3 | 0 0 0 0], zero for pad cells.  Operand layout: no-swizzle K-major, [k-chunk][row] x 16 B.
+      // Build the slab copies from the observation planes [boards][H][W][4]: k-chunk 0 of virtual row v holds
+      // [LeakyReLU(bn1(x))_0..3 | 0 0 0 0], zero for pad cells.  Operand layout: no-swizzle K-major.
       const int stage = warp;
       if (lane == 0 && warp == 0) {
-        mbar_expect_tx(bar_w(), (uint32_t)(3 * W_ROW_BYTES));
-        bulk_g2s(s_w, p.wpack, 3 * W_ROW_BYTES, bar_w());
+        mbar_expect_tx(bar_w(), (uint32_t)(9 * STEM_TAP_BYTES));
+        bulk_g2s(s_w, p.wpack, 9 * STEM_TAP_BYTES, bar_w());
       }
       float bs[4], bt[4];
 #pragma unroll
@@ -289,7 +297,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       for (int it = stage, round = 0; it < my_tiles; it += S, ++round) {
         mbar_wait(bar_empty(stage), ((uint32_t)round & 1u) ^ 1u);
         uint8_t* dst = smem + L::A_OFF + stage * C8_A_ST;
-        const int g_first = tile_of(it) * 16 - 1;
+        const int g_first = tile_of(it) * 16 - 2;
         uint2 raw[PER_LANE];
         bool okv[PER_LANE];
 #pragma unroll
@@ -317,7 +325,11 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
               o.x = pack_bf16(lrelu(bs[0] * x0 + bt[0]), lrelu(bs[1] * x1 + bt[1]));
               o.y = pack_bf16(lrelu(bs[2] * x2 + bt[2]), lrelu(bs[3] * x3 + bt[3]));
             }
-            *reinterpret_cast<uint4*>(dst + row * 16) = o;
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            const int c = row & 7;
+            *reinterpret_cast<uint4*>(dst + row * 16) = (p.W == 8 && c == 7) ? z : o;                  // dx = -1 views
+            *reinterpret_cast<uint4*>(dst + STEM_COPY + row * 16) = o;                                 // dx = 0
+            *reinterpret_cast<uint4*>(dst + 2 * STEM_COPY + row * 16) = (p.W == 8 && c == 0) ? z : o;  // dx = +1
           }
         }
         fence_proxy_async();
@@ -345,7 +357,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     }
   } else if (warp == NPROD) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)C8_N);
+    const uint32_t idesc = umma_idesc_bf16_m128(STEM ? (uint32_t)CH : (uint32_t)C8_N);
     mbar_wait(bar_w(), 0u);
     for (int it = 0; it < my_tiles; ++it) {
       const int stage = it % S, acc = it % ACC;
@@ -360,13 +372,16 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         if (p.debug & 4) {
           // (experiment) no MMAs
         } else if constexpr (STEM) {
-          // no-swizzle K-major: LBO = bytes between the two k-chunks, SBO = 128 B between 8-row groups; the dy view is the
-          // slab shifted by one group
-          const uint64_t ab = umma_desc(a_stage, STEM_SLAB * 16u, 128u);
-          const uint64_t wb = umma_desc(s_w, C8_N * 16u, 128u);
+          // no-swizzle K-major: LBO = bytes between the two k-chunks, SBO = 128 B between 8-row groups; output row m of the
+          // tile is slab row 16 + m, tap (dy, dx) reads slab row 16 + m + (dy-1)*8 + (dx-1) of copy dx
+          const uint64_t wb = umma_desc(s_w, CH * 16u, 128u);
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy)
-            umma_bf16(d, ab + (uint64_t)(dy * (128 >> 4)), wb + (uint64_t)(dy * (W_ROW_BYTES >> 4)), idesc, dy != 0 ? 1u : 0u);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+            const uint64_t ab = umma_desc(a_stage + (uint32_t)(dx * STEM_COPY + (16 + (dy - 1) * 8 + (dx - 1)) * 16),
+                                          STEM_SLAB * 16u, 128u);
+            umma_bf16(d, ab, wb + (uint64_t)(tap * (STEM_TAP_BYTES >> 4)), idesc, tap != 0 ? 1u : 0u);
+          }
         } else {
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
@@ -439,6 +454,11 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       tc_fence_after();
       uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C8_N + col0);
+      if constexpr (STEM) {
+        tmem_ld16(taddr, &v[0]);
+        tmem_ld16(taddr + 16u, &v[16]);
+        tmem_ld_wait();
+      } else {
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
         uint32_t dm[16], d0[16], dp[16];
@@ -455,6 +475,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
           const float dn = __shfl_sync(0xffffffffu, __uint_as_float(dp[k]), (lane + 1) & 31);
           v[cb * 16 + k] = __float_as_uint(fmaf(w_dn, dn, fmaf(w_up, up, __uint_as_float(d0[k]))));
         }
+      }
       }
       tc_fence_before();
       __syncwarp();

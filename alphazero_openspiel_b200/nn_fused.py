@@ -92,11 +92,11 @@ class FusedEvaluator:
             if k == 0:
                 cin = blk.conv1.in_channels
                 assert cin == 4 and blk.use_1x1conv
-                # stem operand image [3 ky][2 k-chunks][192 = kx*64 + n][8]: conv1 on k 0-3 (its input is lrelu(bn1(x)))
-                sw = torch.zeros((3, 2, 3 * CH, 8), dtype=torch.float64)
+                # stem operand image [9 taps][2 k-chunks][64 n][8]: conv1 on k 0-3 (its input is lrelu(bn1(x)))
+                sw = torch.zeros((9, 2, CH, 8), dtype=torch.float64)
                 w1p = torch.zeros((CH, 4, 3, 3), dtype=torch.float64)
                 w1p[:N_FILTERS] = w1
-                sw[:, 0, :, 0:4] = w1p.permute(2, 3, 0, 1).reshape(3, 3 * CH, 4)
+                sw[:, 0, :, 0:4] = w1p.permute(2, 3, 0, 1).reshape(9, CH, 4)
                 new["stem_w"] = sw.to(torch.bfloat16)
                 sb3 = torch.zeros(CH, dtype=torch.float64)
                 sb3[:N_FILTERS] = blk.conv3.bias.double().cpu()

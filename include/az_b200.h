@@ -248,7 +248,7 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  * az_nn_stem: the first conv of resblock1 on the 4 observation planes, slab built from the az_step AZ_OBS_BF16_NHWC batch
  *   [boards][H][W][4]: u[0..49] = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1) (network.py:99-100) and u[50..53] = x, the raw
  *   planes: the block's 1x1 skip projection (resblock1.conv3, network.py:101-103) is then four extra input channels of the
- *   centre tap of the following az_nn_conv3x3.  wpack is bf16 [3 ky][2 k-chunks][192 = kx*64 + n][8],
+ *   centre tap of the following az_nn_conv3x3.  wpack is bf16 [9 taps = ky*3+kx][2 k-chunks][64 n][8],
  *   no-swizzle K-major, only k 0-3 of chunk 0 non-zero (BatchNorm 2 folded).  bn_st = device [8]: scale[4], shift[4].
  * az_nn_head: the FC head (fc1, network.py:48,61-66) for games with n_actions + 1 <= 8 outputs: priors [.][n_actions] =
  *   softmax(x_flat @ w[0..A-1]^T + bias), values = tanh(x_flat @ w[A]^T + bias[A]), fp32.  w is bf16 [8][(H+1)*W*64] over the
