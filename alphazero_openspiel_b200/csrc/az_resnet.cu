@@ -294,12 +294,10 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       const int cells = p.H * p.W;
       constexpr int PER_LANE = (STEM_SLAB + 31) / 32;
       asm volatile("griddepcontrol.wait;" ::: "memory");  // the observations are written by the preceding az_step
-      for (int it = stage, round = 0; it < my_tiles; it += S, ++round) {
-        mbar_wait(bar_empty(stage), ((uint32_t)round & 1u) ^ 1u);
-        uint8_t* dst = smem + L::A_OFF + stage * C8_A_ST;
+      // the observation cells of the NEXT tile of this stage are fetched while the current one is converted and stored
+      uint2 raw[PER_LANE], raw_next[PER_LANE];
+      auto fetch = [&](int it) {
         const int g_first = tile_of(it) * 16 - 2;
-        uint2 raw[PER_LANE];
-        bool okv[PER_LANE];
 #pragma unroll
         for (int i = 0; i < PER_LANE; ++i) {
           const int row = lane + 32 * i;                   // slab row = 8 * group + column
@@ -311,15 +309,24 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
             ok = b < p.boards && r < p.H;
             cell = b * cells + r * p.W + c;
           }
-          okv[i] = ok;
-          raw[i] = ok ? obs[cell] : make_uint2(0u, 0u);
+          // pad cells must come out as zeros, not as bn1 + LeakyReLU of zero planes: mark them with a bit pattern no
+          // observation has (two bf16 NaNs)
+          raw_next[i] = ok ? obs[cell] : make_uint2(0xffffffffu, 0u);
         }
+      };
+      if (stage < my_tiles) fetch(stage);
+      for (int it = stage, round = 0; it < my_tiles; it += S, ++round) {
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) raw[i] = raw_next[i];
+        if (it + S < my_tiles) fetch(it + S);
+        mbar_wait(bar_empty(stage), ((uint32_t)round & 1u) ^ 1u);
+        uint8_t* dst = smem + L::A_OFF + stage * C8_A_ST;
 #pragma unroll
         for (int i = 0; i < PER_LANE; ++i) {
           const int row = lane + 32 * i;
           if (row < STEM_SLAB) {
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (okv[i]) {
+            if (raw[i].x != 0xffffffffu) {
               const float x0 = __uint_as_float(raw[i].x << 16), x1 = __uint_as_float(raw[i].x & 0xffff0000u);
               const float x2 = __uint_as_float(raw[i].y << 16), x3 = __uint_as_float(raw[i].y & 0xffff0000u);
               o.x = pack_bf16(lrelu(bs[0] * x0 + bt[0]), lrelu(bs[1] * x1 + bt[1]));
