@@ -52,6 +52,10 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.rows = []
         self.proc = None
+        self.n0 = 0
+
+    def mark(self):
+        self.n0 = len(self.rows)
 
     def start(self):
         try:
@@ -73,7 +77,10 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows, where = self.rows[self.n0:], "timed region"
+        if not rows:
+            rows, where = self.rows[-5:], "end of warm-up (timed region shorter than the sampling latency)"
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -87,7 +94,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled_during": where}
 
 
 def algorithmic_bytes(d, game_cells, num_actions):
@@ -200,7 +207,12 @@ def run_ours(args):
                             auto_restart=True, random_start_mod=21, max_sims_per_step=args.sim_cap, records=True,
                             use_graph=not args.no_graph, evaluator=args.evaluator,
                             keep_search_tree=not args.no_keep_tree, node_capacity=args.node_capacity)
-    # ---- warm-up (untimed): builds the first searches so trees are in steady state
+    # ---- warm-up (untimed): builds the first searches so trees are in steady state.  nvidia-smi needs up to a second to
+    # deliver its first sample, so the clock sampler starts here and only the samples taken after mark() (the start of the
+    # timed region) are reported; a timed region too short for any sample reports the warm-up's last ones and says so.
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     runner.round(args.warmup)
     runner.drain()
     torch.cuda.synchronize(dev)
@@ -211,11 +223,9 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- timed region: K rounds, CUDA events on the launching stream
-    sampler = ClockSampler(local)
     c0 = runner.counters()
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     runner.round(args.steps)
