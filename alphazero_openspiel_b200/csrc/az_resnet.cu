@@ -567,7 +567,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
 constexpr int HEAD_OUT = 8;
 constexpr int HEAD_BOARDS = 8;      // boards per warp
 constexpr int HEAD_THREADS = 256;
-constexpr int HEAD_UNROLL = 8;
+constexpr int HEAD_UNROLL = 12;
 constexpr int HEAD_WPAD = 4;        // uint4 of padding per weight row in shared memory
 
 __device__ __forceinline__ void mma_bf16_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -579,7 +579,8 @@ __device__ __forceinline__ void mma_bf16_m16n8k16(float (&c)[4], uint32_t a0, ui
 
 __global__ void __launch_bounds__(HEAD_THREADS, 2)
 k_head(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __restrict__ bias, float* __restrict__ priors,
-       float* __restrict__ values, int board0, int boards, int chunks /* K/8 per board */, int A) {
+       float* __restrict__ values, int board0, int boards, int chunks /* K/8 per board */, int xstride /* uint4 per board */,
+       int A) {
   extern __shared__ __align__(16) uint8_t hsmem[];
   uint4* s_w = reinterpret_cast<uint4*>(hsmem);  // [HEAD_OUT][chunks + HEAD_WPAD]
   const int wstride = chunks + HEAD_WPAD;
@@ -595,7 +596,7 @@ k_head(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __
   for (int grp = warp_global; grp < n_groups; grp += n_warps) {
     const int b = grp * HEAD_BOARDS + g;
     const int bc = b < boards ? b : boards - 1;       // ragged tail: recompute the last board, never stored
-    const uint4* xr = x + (long long)(board0 + bc) * chunks + t;
+    const uint4* xr = x + (long long)(board0 + bc) * xstride + t;   // the pad row at the end of a board is skipped
     const uint4* wr = s_w + g * wstride + t;
     float c[4] = {0.f, 0.f, 0.f, 0.f};
     for (int it0 = 0; it0 < n_it; it0 += HEAD_UNROLL) {
@@ -789,10 +790,10 @@ extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head: null argument");
     return -1;
   }
-  const int chunks = (H + 1) * W * CH / 8;
+  const int chunks = H * W * CH / 8;
   const size_t smem = (size_t)HEAD_OUT * (chunks + HEAD_WPAD) * 16;
   if (n_actions < 1 || n_actions + 1 > HEAD_OUT || smem > 100 * 1024 || boards <= 0 || chunks % 4 != 0) {
-    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head: needs n_actions + 1 <= %d and (H+1)*W*1024 <= 100 KB", HEAD_OUT);
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head: needs n_actions + 1 <= %d and H*W*1024 <= 100 KB", HEAD_OUT);
     return -1;
   }
   static size_t smem_set = 0;
@@ -808,7 +809,7 @@ extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float
   // plain launch: measured on B200, letting k_head start under programmatic dependent launch behind the last conv costs
   // ~2% of the step (its CTAs take the SM slots the conv's tail and the concurrent k_compact want)
   k_head<<<grid, HEAD_THREADS, smem, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)w, bias, priors, values, 0, (int)boards,
-                                                             chunks, (int)n_actions);
+                                                             chunks, (H + 1) * W * CH / 8, (int)n_actions);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_head launch", e);
   return 0;

@@ -60,7 +60,7 @@ class FusedEvaluator:
         self.values = torch.zeros((batch,), dtype=torch.float32, device=dev)
         self.par = None
         # small action spaces (Connect Four) finish with the streaming k_head kernel; larger ones with a cuBLAS GEMM
-        self.fused_head = self.A + 1 <= 8 and 8 * ((self.h + 1) * self.w * 8 + 4) * 16 <= 100 * 1024 and \
+        self.fused_head = self.A + 1 <= 8 and 8 * (self.h * self.w * 8 + 4) * 16 <= 100 * 1024 and \
             os.environ.get("AZ_NN_HEAD", "1") != "0"
         self.timing = None   # set to a list to collect (kernel, start_event, end_event) per launch (bench.py roofline)
         self.load(net)
@@ -120,9 +120,9 @@ class FusedEvaluator:
         fwp[:, :self.h, :, :N_FILTERS] = fw.permute(0, 2, 3, 1)
         new["fw"] = fwp.reshape(self.A + 1, -1).to(torch.bfloat16)
         new["fb"] = net.fc1.bias.double().cpu().float()
-        if self.fused_head:   # k_head operand: [8 outputs][(H+1)*W*64] bf16 (unused outputs zero), bias [8]
-            hw = torch.zeros((8, (self.h + 1) * self.w * CH), dtype=torch.float64)
-            hw[:self.A + 1] = fwp.reshape(self.A + 1, -1)
+        if self.fused_head:   # k_head operand: [8 outputs][H*W*64] bf16 (unused outputs zero), bias [8]
+            hw = torch.zeros((8, self.h * self.w * CH), dtype=torch.float64)
+            hw[:self.A + 1] = fwp[:, :self.h].reshape(self.A + 1, -1)
             hb = torch.zeros(8, dtype=torch.float64)
             hb[:self.A + 1] = net.fc1.bias.double().cpu()
             new["hw"], new["hb"] = hw.to(torch.bfloat16), hb.float()

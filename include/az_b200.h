@@ -251,8 +251,8 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  *   centre tap of the following az_nn_conv3x3.  wpack is bf16 [9 taps = ky*3+kx][2 k-chunks][64 n][8],
  *   no-swizzle K-major, only k 0-3 of chunk 0 non-zero (BatchNorm 2 folded).  bn_st = device [8]: scale[4], shift[4].
  * az_nn_head: the FC head (fc1, network.py:48,61-66) for games with n_actions + 1 <= 8 outputs: priors [.][n_actions] =
- *   softmax(x_flat @ w[0..A-1]^T + bias), values = tanh(x_flat @ w[A]^T + bias[A]), fp32.  w is bf16 [8][(H+1)*W*64] over the
- *   flatten of one board (zero on the pad row / pad channels / unused outputs), bias fp32 [8]. */
+ *   softmax(x_flat @ w[0..A-1]^T + bias), values = tanh(x_flat @ w[A]^T + bias[A]), fp32.  w is bf16 [8][H*W*64] over the
+ *   H*W cells of one board (zero on pad channels / unused outputs; the pad row is not read), bias fp32 [8]. */
 #define AZ_NN_F_REVERSE 1 /* walk the 128-row tiles back to front (alternate per layer: the tail of the previous layer's
                              output is still in L2) */
 const char* az_nn_last_error(void);
