@@ -208,14 +208,20 @@ def run_ours(args):
                             use_graph=not args.no_graph, evaluator=args.evaluator,
                             keep_search_tree=not args.no_keep_tree, node_capacity=args.node_capacity)
     # ---- warm-up (untimed): builds the first searches so trees are in steady state.  nvidia-smi needs up to a second to
-    # deliver its first sample, so the clock sampler starts here and only the samples taken after mark() (the start of the
-    # timed region) are reported; a timed region too short for any sample reports the warm-up's last ones and says so.
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # deliver its first sample, so the clock sampler is started at the end of the warm-up and extra warm-up rounds keep the
+    # GPU under the same load until the first sample has arrived (bounded); only samples taken after mark() are reported.
     runner.round(args.warmup)
     runner.drain()
     torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 3.0:
+            runner.round(50)
+            torch.cuda.synchronize(dev)
+        runner.drain()
+        torch.cuda.synchronize(dev)
 
     def barrier():
         if world > 1:
