@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per k_conv8 launch, averaged over the nine launches of one evaluation
 # (ncu --set full, profiles/r01_conv8_full_raw.csv; Connect Four, 16,384 boards).  None until captured for another shape.
-CONV_DRAM_TRAFFIC = 250.1e6
+CONV_DRAM_TRAFFIC = 249.7e6
 FLOPS_PER_EVAL = {"connect_four": 17211600, "breakthrough(rows=6,columns=6)": 16282800, "breakthrough": 31097600}
 
 
@@ -335,10 +335,10 @@ def run_ours(args):
         # dominant kernel: k_conv8 (3x3 conv, 50->50 filters, nine launches per evaluation).  Per launch the algorithm
         # needs boards x 2*HW*50*50*9 FLOPs (30.97 GFLOP, 19 us at the bf16 peak) and reads / writes every [B][H][W][64] bf16
         # tensor it touches once: in + out (+ residual) (+ second output) = 2-4 x 88 MB, 254 MB averaged over the nine
-        # launches of one evaluation (39 us at the measured HBM peak) -> HBM is the binding roofline.
+        # launches of one evaluation (37-39 us at the measured HBM peak) -> HBM is the binding roofline.
         conv_flops = args.trees * 2.0 * rows * cols * 50 * 50 * 9
         tensor_bytes = args.trees * rows * cols * 64 * 2.0
-        n_tensors = {"conv": 2, "conv+res": 3, "conv+res+out2": 4, "conv+skip+out2": 3}
+        n_tensors = {"conv": 2, "conv+res": 3, "conv+out2": 3, "conv+res+out2": 4}
         conv_bytes = sum(n_tensors.get(k, 2) * tensor_bytes * v[1] for k, v in by_name.items() if k.startswith("conv")) / conv_n
         avg_conv_ms = conv_ms / conv_n
         ach = conv_bytes / (avg_conv_ms / 1e3) / 1e9
@@ -353,7 +353,7 @@ def run_ours(args):
                          "share_of_step": conv_ms / n_probe / (step_ms + nn_ms),
                          "launch_ms_by_kind": {k: v[0] / v[1] for k, v in sorted(by_name.items())},
                          "note": "averaged over the nine conv launches of one evaluation (4 plain, 1 +res, 3 +res+out2, "
-                                 "1 +skip+out2); traffic = dram read+write per launch averaged the same way from "
+                                 "1 +out2); traffic = dram read+write per launch averaged the same way from "
                                  "profiles/r01_conv8_full_raw.csv; the run is power-capped (see clocks), so the launch "
                                  "times are those of ~1.6 GHz SM clocks"}
     line = {
