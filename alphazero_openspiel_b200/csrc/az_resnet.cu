@@ -106,6 +106,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, LRELU_SLOPE * x); }  // slope < 1
+// LeakyReLU on two packed bf16 values (2 instructions for 2 values).  Applied AFTER the rounding to bf16: identical for
+// y >= 0, and for y < 0 the double rounding of 0.01*y is far below one bf16 ulp of the activations around it.
+__device__ __forceinline__ uint32_t lrelu_bf16x2(uint32_t w) {
+  const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(&w);
+  const __nv_bfloat162 r = __hmax2(y, __hmul2(y, __floats2bfloat162_rn(LRELU_SLOPE, LRELU_SLOPE)));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 lrelu_bf16x8(uint4 v) {
+  return make_uint4(lrelu_bf16x2(v.x), lrelu_bf16x2(v.y), lrelu_bf16x2(v.z), lrelu_bf16x2(v.w));
+}
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 o;
   o.x = pack_bf16(f[0], f[1]);
@@ -506,8 +516,9 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           f[k] = __uint_as_float(v[cb * 16 + k]) + s_bias[col0 + cb * 16 + k];
-          if (p.lrelu) f[k] = lrelu(f[k]);
+          if (p.lrelu && (has_res || (p.debug & 8))) f[k] = lrelu(f[k]);  // (activation before a residual add: keep it in fp32)
         }
+        const bool packed_act = p.lrelu && !has_res && !(p.debug & 8);   // the usual case: activate the packed result, 1 op per value
         if constexpr (STEM) {
           if (half == 1 && cb == 1) {  // channels 50..53 = columns 2..5 of this 16-column block
             f[2] = __uint_as_float(xrow.x << 16);
@@ -528,14 +539,19 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         }
         // pad columns hold don't-care values (the store clips them); the pad row is stored and must stay zero
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(io + c0) = pad_row ? z : pack8(&f[0]);
-        *reinterpret_cast<uint4*>(io + c1) = pad_row ? z : pack8(&f[8]);
+        uint4 o0 = pack8(&f[0]), o1 = pack8(&f[8]);
+        if (packed_act) {
+          o0 = lrelu_bf16x8(o0);
+          o1 = lrelu_bf16x8(o1);
+        }
+        *reinterpret_cast<uint4*>(io + c0) = pad_row ? z : o0;
+        *reinterpret_cast<uint4*>(io + c1) = pad_row ? z : o1;
         if (has_out2) {
           float g[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) g[k] = lrelu(s_s2[col0 + cb * 16 + k] * f[k] + s_t2[col0 + cb * 16 + k]);
-          *reinterpret_cast<uint4*>(o2 + c0) = pad_row ? z : pack8(&g[0]);
-          *reinterpret_cast<uint4*>(o2 + c1) = pad_row ? z : pack8(&g[8]);
+          for (int k = 0; k < 16; ++k) g[k] = fmaf(s_s2[col0 + cb * 16 + k], f[k], s_t2[col0 + cb * 16 + k]);
+          *reinterpret_cast<uint4*>(o2 + c0) = pad_row ? z : lrelu_bf16x8(pack8(&g[0]));
+          *reinterpret_cast<uint4*>(o2 + c1) = pad_row ? z : lrelu_bf16x8(pack8(&g[8]));
         }
       }
       fence_proxy_async();
