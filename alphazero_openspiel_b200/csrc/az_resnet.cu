@@ -106,6 +106,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float lrelu(float x) { return fmaxf(x, LRELU_SLOPE * x); }  // slope < 1
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2): d = a * b + c and d = a + b on two values per instruction.
+__device__ __forceinline__ uint64_t f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, uint32_t& lo, uint32_t& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
 // LeakyReLU on two packed bf16 values (2 instructions for 2 values).  Applied AFTER the rounding to bf16: identical for
 // y >= 0, and for y < 0 the double rounding of 0.01*y is far below one bf16 ulp of the activations around it.
 __device__ __forceinline__ uint32_t lrelu_bf16x2(uint32_t w) {
@@ -440,6 +459,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     const bool skip_all = (p.debug & 2) != 0;
     const int cc = lane & 7;                         // board column of this thread's row (quarters start at c = 0)
     const float w_up = (p.W == 8 && cc == 0) ? 0.f : 1.f, w_dn = (p.W == 8 && cc == 7) ? 0.f : 1.f;
+    const uint64_t w_up2 = f32x2(w_up, w_up), w_dn2 = f32x2(w_dn, w_dn);
 
     // STEM: the raw observation planes of this thread's row in item i; they ride along in the spare channels 50-53 of the
     // stem's output, where the next conv's centre tap holds the 1x1 skip projection of the block (network.py:101-103), so
@@ -487,10 +507,13 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         // partial sums of a pad cell are zero and its own output is never stored, so the weights are 1; without (W == 8)
         // the row wrap-around at c = 0 / c = 7 gets weight 0.  (The partial sums are finite, so 0 * x is exact.)
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float up = __shfl_sync(0xffffffffu, __uint_as_float(dm[k]), (lane + 31) & 31);
-          const float dn = __shfl_sync(0xffffffffu, __uint_as_float(dp[k]), (lane + 1) & 31);
-          v[cb * 16 + k] = __float_as_uint(fmaf(w_dn, dn, fmaf(w_up, up, __uint_as_float(d0[k]))));
+        for (int k = 0; k < 16; k += 2) {  // two values per FFMA2
+          const float up0 = __shfl_sync(0xffffffffu, __uint_as_float(dm[k]), (lane + 31) & 31);
+          const float up1 = __shfl_sync(0xffffffffu, __uint_as_float(dm[k + 1]), (lane + 31) & 31);
+          const float dn0 = __shfl_sync(0xffffffffu, __uint_as_float(dp[k]), (lane + 1) & 31);
+          const float dn1 = __shfl_sync(0xffffffffu, __uint_as_float(dp[k + 1]), (lane + 1) & 31);
+          const uint64_t acc2 = fma_f32x2(w_up2, f32x2(up0, up1), f32x2(__uint_as_float(d0[k]), __uint_as_float(d0[k + 1])));
+          unpack_f32x2(fma_f32x2(w_dn2, f32x2(dn0, dn1), acc2), v[cb * 16 + k], v[cb * 16 + k + 1]);
         }
       }
       }
@@ -513,12 +536,19 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       for (int cb = 0; cb < 2; ++cb) {  // 16 columns = two 16-byte chunks at a time
         const uint32_t c0 = (((uint32_t)(2 * cb)) ^ sw) * 16u, c1 = (((uint32_t)(2 * cb + 1)) ^ sw) * 16u;
         float f[16];
+        const uint64_t* bias2 = reinterpret_cast<const uint64_t*>(s_bias + col0 + cb * 16);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          f[k] = __uint_as_float(v[cb * 16 + k]) + s_bias[col0 + cb * 16 + k];
-          if (p.lrelu && (has_res || (p.debug & 8))) f[k] = lrelu(f[k]);  // (activation before a residual add: keep it in fp32)
+        for (int k = 0; k < 16; k += 2) {  // two values per FADD2
+          uint32_t lo, hi;
+          unpack_f32x2(add_f32x2(f32x2(__uint_as_float(v[cb * 16 + k]), __uint_as_float(v[cb * 16 + k + 1])), bias2[k >> 1]), lo, hi);
+          f[k] = __uint_as_float(lo);
+          f[k + 1] = __uint_as_float(hi);
         }
-        const bool packed_act = p.lrelu && !has_res && !(p.debug & 8);   // the usual case: activate the packed result, 1 op per value
+        if (p.lrelu && has_res) {  // (activation before a residual add: keep it in fp32)
+#pragma unroll
+          for (int k = 0; k < 16; ++k) f[k] = lrelu(f[k]);
+        }
+        const bool packed_act = p.lrelu && !has_res;   // the usual case: activate the packed result, 1 op per value
         if constexpr (STEM) {
           if (half == 1 && cb == 1) {  // channels 50..53 = columns 2..5 of this 16-column block
             f[2] = __uint_as_float(xrow.x << 16);
@@ -533,8 +563,11 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
           const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            f[2 * k] += __uint_as_float(rw[k] << 16);
-            f[2 * k + 1] += __uint_as_float(rw[k] & 0xffff0000u);
+            uint32_t lo, hi;
+            unpack_f32x2(add_f32x2(f32x2(f[2 * k], f[2 * k + 1]),
+                                   f32x2(__uint_as_float(rw[k] << 16), __uint_as_float(rw[k] & 0xffff0000u))), lo, hi);
+            f[2 * k] = __uint_as_float(lo);
+            f[2 * k + 1] = __uint_as_float(hi);
           }
         }
         // pad columns hold don't-care values (the store clips them); the pad row is stored and must stay zero
@@ -548,8 +581,15 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         *reinterpret_cast<uint4*>(io + c1) = pad_row ? z : o1;
         if (has_out2) {
           float g[16];
+          const uint64_t* s22 = reinterpret_cast<const uint64_t*>(s_s2 + col0 + cb * 16);
+          const uint64_t* t22 = reinterpret_cast<const uint64_t*>(s_t2 + col0 + cb * 16);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) g[k] = fmaf(s_s2[col0 + cb * 16 + k], f[k], s_t2[col0 + cb * 16 + k]);
+          for (int k = 0; k < 16; k += 2) {
+            uint32_t lo, hi;
+            unpack_f32x2(fma_f32x2(s22[k >> 1], f32x2(f[k], f[k + 1]), t22[k >> 1]), lo, hi);
+            g[k] = __uint_as_float(lo);
+            g[k + 1] = __uint_as_float(hi);
+          }
           *reinterpret_cast<uint4*>(o2 + c0) = pad_row ? z : lrelu_bf16x8(pack8(&g[0]));
           *reinterpret_cast<uint4*>(o2 + c1) = pad_row ? z : lrelu_bf16x8(pack8(&g[8]));
         }
