@@ -192,3 +192,16 @@ def test_boards_from_bitboards_breakthrough():
             boards.append(ou.replay(game, s.history())["board"])
         got = boards_from_bitboards(gid, rows, cols, np.array(bbs, dtype=np.uint64), np.array(plies, dtype=np.int32))
         assert np.array_equal(got, np.array(boards))
+
+
+def test_conv_weight_image_layout():
+    """pack_conv3x3: [ky][kx*64 + n][chunk position][8] with chunk c of row n stored at position c ^ (n & 7) (the
+    SWIZZLE_128B K-major image the conv kernel bulk-copies into shared memory); pure host code."""
+    import torch
+    from alphazero_openspiel_b200.nn_fused import pack_conv3x3
+    w = torch.arange(64 * 64 * 9, dtype=torch.float32).reshape(64, 64, 3, 3) % 251   # bf16-exact small integers
+    img = pack_conv3x3(w).float()
+    assert tuple(img.shape) == (3, 192, 8, 8)
+    for ky, kx, n, c in [(0, 0, 0, 0), (1, 2, 5, 3), (2, 1, 63, 7), (0, 2, 17, 6)]:
+        got = img[ky, kx * 64 + n, c ^ (n & 7)]
+        assert torch.equal(got, w[n, c * 8:c * 8 + 8, ky, kx])
