@@ -743,11 +743,14 @@ static int launch_conv8(const CUtensorMap& tm_in, const CUtensorMap& tm_res, con
                         const aznn::Conv8Params& p, int n_ctas, void* stream) {
   using namespace aznn;
   using L = Conv8Smem<NE, S>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in shared-memory size is a per-device attribute of the kernel
+  static unsigned long long attr_set = 0ULL;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_set >> (dev & 63)) & 1ULL)) {
     cudaError_t e = cudaFuncSetAttribute(k_conv8<STEM, NE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
-    attr_set = true;
+    attr_set |= 1ULL << (dev & 63);
   }
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid > p.n_tiles) grid = p.n_tiles;
@@ -852,11 +855,13 @@ extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float
     snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head: needs n_actions + 1 <= %d and H*W*1024 <= 100 KB", HEAD_OUT);
     return -1;
   }
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  static size_t smem_set[64] = {0};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > smem_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(k_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
-    smem_set = smem;
+    smem_set[dev & 63] = smem;
   }
   const int n_groups = (boards + HEAD_BOARDS - 1) / HEAD_BOARDS;
   int grid = n_ctas > 0 ? n_ctas : 2 * 148;

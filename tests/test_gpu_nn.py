@@ -16,7 +16,8 @@ def _nhwc(x):
     return out
 
 
-@pytest.mark.parametrize("H,W,B", [(6, 7, 37), (6, 6, 300), (8, 8, 129), (6, 7, 4096), (5, 7, 1000), (3, 2, 50), (8, 8, 3000)])
+@pytest.mark.parametrize("H,W,B", [(6, 7, 37), (6, 6, 300), (8, 8, 129), (6, 7, 4096), (5, 7, 1000), (3, 2, 50), (8, 8, 3000),
+                                   (6, 7, 1), (16, 8, 5)])
 def test_conv3x3_tcgen05_matches_torch(H, W, B):
     """out = conv3x3(in) + bias [-> LeakyReLU] [+ res], out2 = LeakyReLU(s2*out+t2) on [B,H+1,W,64] tensors; W = 8 has no
     pad column inside the SM (row wrap-around is masked in the epilogue), W < 8 has.
@@ -112,3 +113,20 @@ def test_fused_evaluator_matches_fp32_reference(game):
     assert (p3.cpu() - p[:333]).abs().max().item() < 2e-3 and (v3.cpu() - v[:333]).abs().max().item() < 1e-2
     if fe.fused_head:
         assert torch.equal(p3.cpu(), p[:333]) and torch.equal(v3.cpu(), v[:333])
+
+
+def test_fused_evaluator_is_batch_size_independent():
+    """A board's priors / value do not depend on how many other boards share the launch (1, 2, 3 boards vs 64): tiles that
+    are mostly out of range, single-CTA grids and the ragged tail of k_head."""
+    import torch
+    from alphazero_openspiel_b200 import engine as E
+    from alphazero_openspiel_b200.network import Net
+    from alphazero_openspiel_b200.nn_fused import FusedEvaluator
+    shape, A = E.game_shape("connect_four")
+    torch.manual_seed(3)
+    net = Net(shape, A).eval()
+    obs = (torch.rand((64, shape[1], shape[2], 4), device="cuda:0") > 0.5).to(torch.bfloat16)
+    p64, v64 = FusedEvaluator(net, 64, "cuda:0").eval_batch(obs)
+    for b in (1, 2, 3, 17):
+        p, v = FusedEvaluator(net, b, "cuda:0").eval_batch(obs[:b])
+        assert torch.equal(p, p64[:b]) and torch.equal(v, v64[:b]), b
