@@ -126,7 +126,8 @@ __device__ __forceinline__ void unpack_f32x2(uint64_t v, uint32_t& lo, uint32_t&
   asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
 }
 // LeakyReLU on two packed bf16 values (2 instructions for 2 values).  Applied AFTER the rounding to bf16: identical for
-// y >= 0, and for y < 0 the double rounding of 0.01*y is far below one bf16 ulp of the activations around it.
+// y >= 0; for y < 0 the slope is bf16(0.01) = 0.010009766 and the product is rounded a second time, an error of 1e-5 |y|,
+// far below one bf16 ulp of the activations around it.
 __device__ __forceinline__ uint32_t lrelu_bf16x2(uint32_t w) {
   const __nv_bfloat162 y = *reinterpret_cast<const __nv_bfloat162*>(&w);
   const __nv_bfloat162 r = __hmax2(y, __hmul2(y, __floats2bfloat162_rn(LRELU_SLOPE, LRELU_SLOPE)));
@@ -549,14 +550,6 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
           for (int k = 0; k < 16; ++k) f[k] = lrelu(f[k]);
         }
         const bool packed_act = p.lrelu && !has_res;   // the usual case: activate the packed result, 1 op per value
-        if constexpr (STEM) {
-          if (half == 1 && cb == 1) {  // channels 50..53 = columns 2..5 of this 16-column block
-            f[2] = __uint_as_float(xrow.x << 16);
-            f[3] = __uint_as_float(xrow.x & 0xffff0000u);
-            f[4] = __uint_as_float(xrow.y << 16);
-            f[5] = __uint_as_float(xrow.y & 0xffff0000u);
-          }
-        }
         if (has_res) {
           const uint4 r0 = *reinterpret_cast<const uint4*>(io + c0);
           const uint4 r1 = *reinterpret_cast<const uint4*>(io + c1);
@@ -576,6 +569,12 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         if (packed_act) {
           o0 = lrelu_bf16x8(o0);
           o1 = lrelu_bf16x8(o1);
+        }
+        if constexpr (STEM) {
+          if (half == 1 && cb == 1) {  // channels 50..53 = words 1, 2 of this block: the raw planes, untouched by the activation
+            o0.y = xrow.x;
+            o0.z = xrow.y;
+          }
         }
         *reinterpret_cast<uint4*>(io + c0) = pad_row ? z : o0;
         *reinterpret_cast<uint4*>(io + c1) = pad_row ? z : o1;
