@@ -194,6 +194,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
@@ -522,8 +523,13 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty(acc));
       if (skip_all) continue;
-      // the previous item's stores have drained their staging buffers (io[b^1] and out2) before anything overwrites them
-      if (lane == 0) bulk_wait_read0();
+      // Staging buffers must have been read by their TMA stores before they are overwritten: with a residual (prefetched
+      // into io[b^1]) or a second output (single buffer) that is the previous item's store group; otherwise only io[b] is
+      // written now, last stored two items ago, and the previous item's store may stay in flight.
+      if (lane == 0) {
+        if (has_res || has_out2) bulk_wait_read0();
+        else bulk_wait_read1();
+      }
       __syncwarp();
       const int inext = i + NEQ;
       if (inext < n_items) {
