@@ -184,4 +184,11 @@ class MCTS:
             self._eng.command(reset_tree=[1])
 
     def random_rollout(self, state):
-        raise NotImplementedError("random_rollout (mcts.py:205-223) is a 'next' row: SURVEY 8(f).4")
+        """Stand-in evaluator of mcts.py:205-223: uniform priors and the outcome of one uniformly random playout from
+        `state`, seen by the player to move there.  Host code on the caller's pyspiel state; draws from the global numpy
+        RNG in the reference's order (one `choice` per ply), so searches driven by it reproduce the reference's."""
+        playout = state.clone()
+        mover = playout.current_player()
+        while not playout.is_terminal():
+            playout.apply_action(np.random.choice(playout.legal_actions()))
+        return np.ones(self.num_distinct_actions), playout.player_return(mover)

@@ -7,6 +7,7 @@ not exist there).  It restates, with flat parallel lists instead of linked Node 
       ._pick          <- mcts.py:38-52,68-80  Node.select + get_value (PUCT branch)
       ._grow          <- mcts.py:54-66    Node.expand
       ._credit        <- mcts.py:82-89    Node.update_recursive
+    rollout_policy    <- mcts.py:205-223  MCTS.random_rollout
     strip_illegal     <- alphazerobot.py:7-18   remove_illegal_actions
     PortBot.step      <- alphazerobot.py:42-93
     selfplay_game     <- game_utils.py:148-206  play_game_self (all four `backup` targets)
@@ -169,6 +170,18 @@ class PortMCTS:
             value = self.mean[node]
             sign *= -1.0
         return value * sign
+
+
+def rollout_policy(num_distinct_actions):
+    """mcts.py:205-223 (MCTS.random_rollout) as a policy_fn: uniform priors, value = return of one random playout for the
+    player to move; one np.random.choice per ply on the global numpy RNG."""
+    def fn(state):
+        work = state.clone()
+        starter = work.current_player()
+        while not work.is_terminal():
+            work.apply_action(np.random.choice(work.legal_actions()))
+        return np.ones(num_distinct_actions), work.player_return(starter)
+    return fn
 
 
 def strip_illegal(probs, legal_actions):

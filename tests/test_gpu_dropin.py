@@ -60,6 +60,30 @@ def test_mcts_search_update_root_matches_reference_port(shim, game):
             ours.update_root(A + 5 if game == "connect_four" else 0)
 
 
+def test_mcts_with_random_rollout_evaluator_matches_port(shim):
+    """MCTS.random_rollout as policy_fn (mcts.py:205-223): the device search consumes the host rollouts in
+    the reference's order, so visit counts equal the port's from the same numpy seed."""
+    from oracle import ref_port
+    from alphazero_openspiel_b200.mcts import MCTS
+    game = "connect_four"
+    g = shim.load_game(game)
+    A = g.num_distinct_actions()
+    ours = MCTS(None, A, n_playouts=60, use_dirichlet=False, game_name=game)
+    ours.policy_fn = ours.random_rollout
+    ref = ref_port.PortMCTS(ref_port.rollout_policy(A), A, n_playouts=60, use_dirichlet=False)
+    s = g.new_initial_state()
+    for move in range(3):
+        np.random.seed(40 + move)
+        a = ours.search(s)
+        np.random.seed(40 + move)
+        b = ref.search(s)
+        assert list(a) == list(b) and ours.root.N == ref.visits[ref.root] and ours.root.Q == ref.mean[ref.root]
+        act = int(np.argmax(a))
+        ours.update_root(act)
+        ref.update_root(act)
+        s.apply_action(act)
+
+
 @pytest.mark.parametrize("game,backup", [("connect_four", "on-policy"), ("connect_four", "soft-Z"),
                                          ("connect_four", "A0C"), ("connect_four", "off-policy"),
                                          ("breakthrough(rows=6,columns=6)", "off-policy")])

@@ -221,3 +221,39 @@ def test_port_and_c_oracle_vs_live_reference():
     assert list(counts) == [m.root.children[a].N for a in range(7)]
     assert L.oz_tree_root_q(t) == m.root.Q
     L.oz_tree_free(t)
+
+
+def test_random_rollout_evaluator_matches_live_reference():
+    """MCTS.random_rollout (mcts.py:205-223): the oracle port, the drop-in's host implementation and the
+    live reference draw the same playouts from the same numpy seed; a whole search driven by it matches the port."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("/root/reference is not mounted (GPU box)")
+    pyspiel_shim.install()
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import mcts as ref_mcts
+    from alphazero_openspiel_b200.mcts import MCTS as OurMCTS
+    for game in ["connect_four", "breakthrough(rows=6,columns=6)"]:
+        g = pyspiel_shim.load_game(game)
+        A = g.num_distinct_actions()
+        ref = ref_mcts.MCTS(None, A, n_playouts=40, use_dirichlet=False)
+        ours = OurMCTS(None, A)                      # no engine is created before a search
+        port_fn = ref_port.rollout_policy(A)
+        s = g.new_initial_state()
+        for ply in range(6):
+            outs = []
+            for fn in (ref.random_rollout, ours.random_rollout, port_fn):
+                np.random.seed(100 + ply)
+                pri, v = fn(s)
+                outs.append((list(pri), v, np.random.random_sample()))   # same priors, value and RNG position
+            assert outs[0] == outs[1] == outs[2]
+            s.apply_action(s.legal_actions()[ply % len(s.legal_actions())])
+        # a search with the rollout evaluator: port vs live reference
+        s = g.new_initial_state()
+        ref.policy_fn = ref.random_rollout
+        port = ref_port.PortMCTS(port_fn, A, n_playouts=40, use_dirichlet=False)
+        np.random.seed(5)
+        a = ref.search(s)
+        np.random.seed(5)
+        b = port.search(s)
+        assert list(a) == list(b)
