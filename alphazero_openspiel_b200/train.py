@@ -53,6 +53,9 @@ class Trainer:
         self.tree_strap = False
         self.it = 0
         self.n_generations = 201
+        # Extension: keep the replay buffer as arrays (replay.ExampleBatch) instead of Python lists.
+        # Same sampling calls, duplicate merging and losses; `self.buffer` stays empty in this mode.
+        self.array_buffer = False
         for k, v in overrides.items():
             if not hasattr(self, k):
                 raise TypeError("unknown Trainer setting %r" % k)
@@ -62,6 +65,7 @@ class Trainer:
 
         self.generation = 0
         self.buffer = []
+        self.abuffer = None
         self.state_shape, self.num_distinct_actions = game_shape(self.name_game)
         self.games_played = 0
         self.start_time = datetime.now().strftime("%Y-%m-%d-%H-%M-%S")
@@ -78,6 +82,22 @@ class Trainer:
         self.last_generation_stats = {}
 
     # ------------------------------------------------------------------ optimisation (train.py:95-154)
+    def net_step_arrays(self, batch, first, pol, val):
+        """net_step on the array form of the buffer (replay.ExampleBatch after remove_duplicates): same sampling call,
+        same losses; the board planes are rebuilt for the sampled minibatch only."""
+        self.current_net.zero_grad()
+        sample_ids = np.random.randint(len(first), size=self.batch_size)
+        x = torch.from_numpy(batch.boards(first[sample_ids])).float().to(self.device)
+        p_t, v_t = self.current_net(x)
+        p_r = torch.tensor(pol[sample_ids]).float().to(self.device)
+        v_r = torch.tensor(val[sample_ids]).float().to(self.device)
+        loss_v = self.criterion_value(v_t, v_r.unsqueeze(1))
+        loss_p = -torch.sum(p_r * torch.log(p_t)) / p_r.size()[0]
+        (loss_v + loss_p).backward()
+        self.optimizer.step()
+        self.it += 1
+        return loss_p, loss_v
+
     def net_step(self, flattened_buffer):
         self.current_net.zero_grad()
         sample_ids = np.random.randint(len(flattened_buffer), size=self.batch_size)
@@ -101,10 +121,16 @@ class Trainer:
         losses = []
         if rank == 0:
             self.current_net.train()
-            flat = self.remove_duplicates([sample for game in self.buffer for sample in game])
+            if self.array_buffer:
+                first, pol, val = self.abuffer.remove_duplicates()
+            else:
+                flat = self.remove_duplicates([sample for game in self.buffer for sample in game])
             run_p = run_v = 0
             for i in range(self.n_batches_per_generation):
-                loss_p, loss_v = self.net_step(flat)
+                if self.array_buffer:
+                    loss_p, loss_v = self.net_step_arrays(self.abuffer, first, pol, val)
+                else:
+                    loss_p, loss_v = self.net_step(flat)
                 run_p += loss_p
                 run_v += loss_v
                 if i % 100 == 99:
@@ -151,14 +177,23 @@ class Trainer:
                                      dirichlet_ratio=self.dirichlet_ratio, c_puct=self.uct_train, backup=self.backup,
                                      tree_strap=self.tree_strap, n_pools=self.n_pools, n_processes=self.n_processes,
                                      **engine_kwargs)
-        games = generator.generate_examples(n_games)
+        if self.array_buffer:
+            from .replay import ExampleBatch
+            new = generator.generate_batch(n_games)
+            n_new = new.n_games
+            self.abuffer = new if self.abuffer is None else ExampleBatch.concat([self.abuffer, new])
+        else:
+            games = generator.generate_examples(n_games)
+            n_new = len(games)
+            for examples in games:
+                self.buffer.append(examples)
         self.games_played += self.n_games_per_generation
-        for examples in games:
-            self.buffer.append(examples)
-        self.last_generation_stats = dict(generator.last_stats, seconds=time.time() - start, games=len(games))
+        self.last_generation_stats = dict(generator.last_stats, seconds=time.time() - start, games=n_new)
         logger.info("Finished Generating Data. Took: " + str(time.time() - start) + " seconds")
         self.update_buffer_size()
-        if len(self.buffer) > self.n_games_buffer:
+        if self.array_buffer:
+            self.abuffer = self.abuffer.last_games(self.n_games_buffer)
+        elif len(self.buffer) > self.n_games_buffer:
             del self.buffer[:len(self.buffer) - self.n_games_buffer]
 
     def update_buffer_size(self):

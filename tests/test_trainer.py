@@ -101,3 +101,117 @@ def test_trainer_generations_end_to_end():
     assert any(not torch.equal(before[k].cpu(), after[k].cpu()) for k in before if "weight" in k)
     assert all(torch.isfinite(v).all() for v in after.values())
     assert tr.last_generation_stats["overflow"] == 0 and not tr.current_net.training
+
+
+@pytest.mark.gpu
+def test_array_buffer_generations_match_the_list_buffer():
+    """Trainer(array_buffer=True): the same two generations as the list-buffer Trainer from the same seeds -- same games in
+    the buffer (device self-play is deterministic for a seed), same number of optimisation steps."""
+    from alphazero_openspiel_b200.train import Trainer
+    nets = []
+    for array_buffer in (False, True):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        tr = Trainer(n_games_per_generation=24, n_batches_per_generation=6, batch_size=32, n_playouts_train=20,
+                     n_generations=2, backup="on-policy", array_buffer=array_buffer)
+        tr.run(n_trees=24, seed=11)
+        assert tr.generation == 2 and tr.it == 12
+        if array_buffer:
+            assert tr.abuffer.n_games == 48 and tr.buffer == []
+            games = tr.abuffer.to_games()
+        else:
+            games = tr.buffer
+        # generation 1's games are identical (same initial weights, same seed); their targets are not compared because
+        # remove_duplicates has merged them in place with generation 2's, which depends on the (noisy) GPU training
+        nets.append((copy.deepcopy(tr.current_net.state_dict()), [[ex[0] for ex in g] for g in games[:24]]))
+    assert nets[0][1] == nets[1][1]
+    # (cuDNN's backward kernels are not bit-reproducible from run to run on the GPU, and Adam amplifies the last-bit
+    # differences: the CPU test below pins the array path bit for bit; here both trainings must simply have happened)
+    for sd, _ in nets:
+        assert all(torch.isfinite(v.float()).all() for v in sd.values())
+
+
+def _oracle_records(n_games=6, game="connect_four", playouts=20, seed=9):
+    """Device-format training records synthesised from the C oracle's self-play (as in test_cabi_and_host)."""
+    from alphazero_openspiel_b200.engine import record_dtype
+    from tests import oracle_util as ou
+    cfg = ou.selfplay_cfg(game, playouts, use_dirichlet=2, sample_moves=1, seed=seed)
+    dt = record_dtype(7, (72 + 6 * 7 + 7) // 8 * 8)
+    rows = []
+    for t in range(n_games):
+        plies, ret, _ = ou.selfplay_game(cfg, t % 3)       # trees 0..2 twice: duplicate histories across games
+        hist = []
+        for r in plies:
+            rec = np.zeros((), dtype=dt)
+            rec["tree"], rec["game_seq"], rec["ply"], rec["action"] = t, 0, r["ply"], r["action"]
+            rec["n_legal"], rec["kind"], rec["root_n"] = r["n_legal"], 0, r["root_n"]
+            rec["bb"] = r["bb"]
+            rec["root_q"], rec["v_a0c"], rec["v_offpolicy"] = r["root_q"], r["v_a0c"], r["v_offpolicy"]
+            rec["counts"][:r["n_legal"]] = r["counts"]
+            rec["actions"][:] = -1
+            rec["actions"][:r["n_legal"]] = ou.replay(game, hist)["legal"]
+            rows.append(rec)
+            hist.append(r["action"])
+        end = np.zeros((), dtype=dt)
+        end["tree"], end["kind"], end["ply"], end["root_q"] = t, 1, len(plies), ret[0]
+        rows.append(end)
+    recs = np.array(rows, dtype=dt)
+    return recs[np.random.RandomState(1).permutation(len(recs))]
+
+
+def test_example_batch_is_a_lossless_form_of_the_reference_examples():
+    """replay.ExampleBatch (SURVEY 8(f) rank 3): from_records + to_games == records_to_games for every value target;
+    concat / last_games follow the buffer list semantics."""
+    from alphazero_openspiel_b200.examplegenerator import records_to_games
+    from alphazero_openspiel_b200.replay import ExampleBatch
+    recs = _oracle_records()
+    for backup in ["on-policy", "soft-Z", "A0C", "off-policy"]:
+        want = records_to_games(recs, "connect_four", backup)
+        b = ExampleBatch.from_records(recs, "connect_four", backup)
+        got = b.to_games()
+        assert b.n_games == len(want) == 6 and len(b) == sum(len(g) for g in want)
+        for gw, gg in zip(want, got):
+            assert len(gw) == len(gg)
+            for x, y in zip(gw, gg):
+                assert x[0] == y[0] and np.array_equal(x[1], y[1]) and x[2] == y[2] and x[3] == y[3]
+    b = ExampleBatch.from_records(recs, "connect_four")
+    two = ExampleBatch.concat([b, b])
+    assert two.n_games == 12 and len(two) == 2 * len(b)
+    tail = two.last_games(5)
+    assert tail.n_games == 5
+    for gx, gy in zip(tail.to_games(), two.to_games()[-5:]):
+        assert len(gx) == len(gy)
+        assert all(x[0] == y[0] and np.array_equal(x[1], y[1]) and x[2] == y[2] and x[3] == y[3] for x, y in zip(gx, gy))
+    assert ExampleBatch.from_records(recs[recs["kind"] == 0], "connect_four").n_games == 0   # unfinished games dropped
+
+
+def test_array_remove_duplicates_and_net_step_match_the_list_path():
+    """Same merged examples (order, averaged targets bit-equal, first example of a key updated in place) and, from the same
+    seeds and initial weights, the same losses and weights after a few optimisation steps."""
+    from alphazero_openspiel_b200.replay import ExampleBatch
+    from alphazero_openspiel_b200.train import Trainer
+    recs = _oracle_records(n_games=9)
+    batch = ExampleBatch.from_records(recs, "connect_four")
+    games = batch.to_games()
+    flat = [ex for g in games for ex in g]
+    merged = Trainer.remove_duplicates(flat)
+    first, pol, val = batch.remove_duplicates()
+    assert len(merged) == len(first) < len(flat)                    # the oracle games share their opening positions
+    for m, i, p, v in zip(merged, first, pol, val):
+        assert m[0] == batch.key(i) and m[2] == p.tolist() and m[3] == v
+        assert m is flat[i]                                          # reference: the first example IS the accumulator
+        assert batch.policy[i].tolist() == m[2] and batch.value[i] == m[3]
+    torch.manual_seed(3)
+    a = Trainer(device="cpu", batch_size=16, use_gpu=False)
+    b = Trainer(device="cpu", batch_size=16, use_gpu=False, array_buffer=True)
+    b.current_net.load_state_dict(a.current_net.state_dict())
+    a.current_net.train()
+    b.current_net.train()
+    for step in range(3):
+        np.random.seed(20 + step)
+        la = a.net_step(merged)
+        np.random.seed(20 + step)
+        lb = b.net_step_arrays(batch, first, pol, val)
+        assert float(la[0]) == float(lb[0]) and float(la[1]) == float(lb[1])
+    for x, y in zip(a.current_net.parameters(), b.current_net.parameters()):
+        assert torch.equal(x, y)
