@@ -10,6 +10,7 @@ F_KEEP_TREE, F_AUTO_RESTART, F_MANUAL, F_SAMPLE_MOVES = 1 << 0, 1 << 1, 1 << 2, 
 F_RECORDS, F_OFFPOLICY, F_PRIORS_F64, F_RANDOM_START = 1 << 4, 1 << 5, 1 << 6, 1 << 7
 F_ASYNC_COMPACT = 1 << 8
 F_EAGER_COMPACT = 1 << 9
+F_UCT = 1 << 10
 NOISE_NONE, NOISE_DIRICHLET, NOISE_HOST, NOISE_COUNTER = 0, 1, 2, 3
 EVAL_EXTERNAL, EVAL_UNIFORM, EVAL_HASH = 0, 1, 2
 OBS_NONE, OBS_F32_NCHW, OBS_BF16_NHWC = 0, 1, 2

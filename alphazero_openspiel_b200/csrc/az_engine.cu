@@ -32,6 +32,7 @@
 #include <string.h>
 #include <math.h>
 #include <new>
+#include <vector>
 
 #include "../../include/az_b200.h"
 #include "az_games.cuh"
@@ -56,7 +57,7 @@ struct __align__(16) TreeHdr {
   int32_t pend_ply;
   int32_t root_ply;
   int32_t game_seq;
-  uint8_t phase, half, err, pad;
+  uint8_t phase, half, err, uct;  // uct: this tree scores with the use_puct=False formula (see fresh_tree)
   int32_t pad2[3];
 };
 static_assert(sizeof(TreeHdr) == 80, "TreeHdr size");
@@ -73,6 +74,8 @@ struct Params {
   int* compact_list;   // trees waiting for re-root compaction (k_compact work list)
   int* compact_count;  // [0] = entries, [1] = CTAs done
   long long* dbg;      // optional [n_trees][4]: cycles, phase in, sims this step, flags (az_debug_timing)
+  const double* logtab;  // AZ_F_UCT: log(n) for n < LOGTAB_N, computed on the host with the C library's log() -- the same
+                         // function CPython's math.log calls, so the UCT scores are bit-equal to the reference's
   long long rec_cap;
   int max_games;
   int rec_stride;
@@ -289,11 +292,14 @@ __device__ __forceinline__ bool expand_node(const Params& p, const StepIO& io, c
   return true;
 }
 
-// One PUCT descent (mcts.py:139-142).  On return: node/depth/state of the childless node reached; path in spath.
-template <class GM, int G>
+constexpr int LOGTAB_N = 1 << 20;  // parent visit counts covered by the AZ_F_UCT log table (a game has < 1e5 simulations)
+
+// One PUCT (or, UCT = true, use_puct=False) descent (mcts.py:139-142).  On return: node/depth/state of the childless node
+// reached; path in spath.
+template <class GM, int G, bool UCT>
 __device__ __forceinline__ void sim_select(const Params& p, const Arena& a, int root, St& s, int& node, int& depth,
                                            int32_t* spath, int lane, unsigned gm, unsigned long long& n_children,
-                                           bool& depth_overflow) {
+                                           bool& depth_overflow, bool tree_uct) {
   node = root;
   depth = 0;
   if (lane == 0) spath[0] = root;
@@ -304,6 +310,9 @@ __device__ __forceinline__ void sim_select(const Params& p, const Arena& a, int 
     if (depth + 1 >= GM::MAXD) { depth_overflow = true; break; }
     const int fc = (int)(cur.y >> 8);
     const double sq = __dsqrt_rn((double)cur.x);
+    // UCT: log(N_parent); a parent beyond the table (never in practice) is treated like the last entry and flagged
+    const double lg_np = (UCT && tree_uct) ? p.logtab[cur.x < (unsigned)LOGTAB_N ? cur.x : (unsigned)(LOGTAB_N - 1)] : 0.0;
+    if (UCT && tree_uct && cur.x >= (unsigned)LOGTAB_N) depth_overflow = true;
     double best = 0.0;
     int bi = 0x7fffffff;
     uint2 bnl = make_uint2(0u, 0u);
@@ -314,9 +323,16 @@ __device__ __forceinline__ void sim_select(const Params& p, const Arena& a, int 
         const uint2 nl = a.nl(fc + i);
         const double q = a.q(fc + i);
         const double pp = a.p(fc + i);
-        // Q + (((c_puct * P) * sqrt(N_parent)) / (N + 1))      mcts.py:78
-        const double u = __ddiv_rn(__dmul_rn(__dmul_rn(p.c_puct, pp), sq), (double)(nl.x + 1u));
-        const double sc = __dadd_rn(q, u);
+        double sc;
+        if (UCT && tree_uct) {
+          // inf if N == 0 else Q + ((c_puct * P) * sqrt(log(N_parent) / N))      mcts.py:80
+          sc = nl.x == 0u ? __longlong_as_double(0x7ff0000000000000LL)
+                          : __dadd_rn(q, __dmul_rn(__dmul_rn(p.c_puct, pp), __dsqrt_rn(__ddiv_rn(lg_np, (double)nl.x))));
+        } else {
+          // Q + (((c_puct * P) * sqrt(N_parent)) / (N + 1))      mcts.py:78
+          const double u = __ddiv_rn(__dmul_rn(__dmul_rn(p.c_puct, pp), sq), (double)(nl.x + 1u));
+          sc = __dadd_rn(q, u);
+        }
         if (bi == 0x7fffffff || sc > best) { best = sc; bi = i; bnl = nl; }
       }
     }
@@ -417,7 +433,11 @@ __device__ void reroot_compact(const Params& p, TreeHdr& h, int tree, int child,
 }
 
 template <int G>
-__device__ __forceinline__ void fresh_tree(const Params& p, TreeHdr& h, int tree, int lane, unsigned gm) {
+// uct_root: the reference keeps use_puct on every Node, children inherit it from their parent (mcts.py:64), and only the root
+// that update_root creates for a leaf root (mcts.py:199-200) gets the MCTS object's flag -- the root of MCTS.__init__
+// (mcts.py:122) is built without it.  So the formula is a property of the tree, decided when its root is created.
+__device__ __forceinline__ void fresh_tree(const Params& p, TreeHdr& h, int tree, int lane, unsigned gm, bool uct_root = false) {
+  h.uct = uct_root ? 1 : 0;
   const Arena a = arena_of(p, tree, h.half);
   if (lane == 0) {
     a.nl(0) = make_uint2(0u, 0u);  // Node(None, 0.0)  mcts.py:122
@@ -646,7 +666,7 @@ __device__ void finish_move(const Params& p, TreeHdr& h, int tree, int lane, uns
 }
 
 // ---------------------------------------------------------------- the step kernel
-template <class GM>
+template <class GM, bool UCT>
 __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params p, const StepIO io) {
   constexpr int G = GM::G;
   __shared__ int32_t s_path[BLOCK / G][GM::MAXD];
@@ -785,7 +805,7 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
       s.ply = h.root_ply;
       int node, depth;
       bool dovf = false;
-      sim_select<GM, G>(p, a, h.root_node, s, node, depth, spath, lane, gm, c_children, dovf);
+      sim_select<GM, G, UCT>(p, a, h.root_node, s, node, depth, spath, lane, gm, c_children, dovf, h.uct != 0);
       if (dovf) {
         h.err = 1;
         h.phase = AZ_PH_ERROR;
@@ -973,7 +993,8 @@ __global__ void k_command(const Params p, const int32_t* upd, const int32_t* rst
     TreeHdr h = p.hdr[tree];
     bool dirty = false;
     if (rst && rst[tree]) {
-      fresh_tree<G>(p, h, tree, lane, gm);
+      // 1: the root of MCTS.__init__ (mcts.py:122); 2: the root update_root builds for a leaf root (mcts.py:199-200)
+      fresh_tree<G>(p, h, tree, lane, gm, rst[tree] == 2 && (p.flags & AZ_F_UCT) != 0);
       h.phase = AZ_PH_IDLE;
       dirty = true;
     }
@@ -988,7 +1009,8 @@ __global__ void k_command(const Params p, const int32_t* upd, const int32_t* rst
       const int k = GM::outcome(s, p.geo) >= 0 ? -1 : GM::rank_of(lg, s, p.geo, action);
       const uint2 rnl = a.nl(h.root_node);
       if ((rnl.y & 0xffu) == 0) {
-        fresh_tree<G>(p, h, tree, lane, gm);  // root is a leaf -> Node(None, 0.0)   mcts.py:198-199
+        // root is a leaf -> Node(None, 0.0, use_puct=self.use_puct)   mcts.py:198-200
+        fresh_tree<G>(p, h, tree, lane, gm, (p.flags & AZ_F_UCT) != 0);
       } else if (k < 0) {
         if (lane == 0) atomicAdd(bad, 1);     // KeyError in the reference (mcts.py:202)
       } else {
@@ -1365,6 +1387,18 @@ int az_create(const az_config* cfg_in, az_engine** out) {
     az_destroy(e);
     return -2;
   }
+  if (cfg.flags & AZ_F_UCT) {
+    double* tab = nullptr;
+    if ((err = alloc((void**)&tab, sizeof(double) * LOGTAB_N)) != cudaSuccess) {
+      fail(-2, "cudaMalloc failed (log table): %s", cudaGetErrorString(err));
+      az_destroy(e);
+      return -2;
+    }
+    p.logtab = tab;
+    std::vector<double> host(LOGTAB_N);
+    for (int n = 0; n < LOGTAB_N; ++n) host[n] = log((double)n);  // log(0) = -inf is never used (a visited child has a visited parent)
+    CK(cudaMemcpy(tab, host.data(), sizeof(double) * LOGTAB_N, cudaMemcpyHostToDevice));
+  }
   e->bytes = (int64_t)bytes;
   CK(cudaMemset(p.rec_count, 0, sizeof(unsigned long long)));
   CK(cudaMemset(p.ctr, 0, sizeof(unsigned long long) * AZ_CTR_COUNT));
@@ -1390,6 +1424,7 @@ int az_destroy(az_engine* e) {
   cudaFree(p.compact_list);
   cudaFree(p.compact_count);
   if (p.dbg) cudaFree(p.dbg);
+  if (p.logtab) cudaFree(const_cast<double*>(p.logtab));
   cudaFree(e->d_cmd);
   cudaFree(e->d_bad);
   delete e;
@@ -1494,7 +1529,8 @@ int az_step(az_engine* e, const void* priors_dev, const void* values_dev, const 
   }
   dispatch_game(e->cfg.game_id, [&](auto gm) {
     using GM = decltype(gm);
-    k_step<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
+    if (p.flags & AZ_F_UCT) k_step<GM, true><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
+    else k_step<GM, false><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
     return 0;
   });
   CK(cudaGetLastError());

@@ -46,8 +46,6 @@ def _game_name_of(state, kwargs):
 class MCTS:
     def __init__(self, policy_fn, num_distinct_actions, c_puct=2.5, n_playouts=100, use_dirichlet=True,
                  dirichlet_ratio=0.25, use_puct=True, **kwargs):
-        if not use_puct:
-            raise NotImplementedError("use_puct=False (mcts.py:80) is not on the accelerated path")
         self.policy_fn = policy_fn
         self.num_distinct_actions = num_distinct_actions
         self.c_puct = c_puct
@@ -60,13 +58,14 @@ class MCTS:
         self._eng = None
         self._hist = None       # action history the engine's root position corresponds to
         self._root_cache = None
+        self._leaf_root_updated = False
         self.evaluations = 0
 
     # ---- engine plumbing
     def _engine(self, state):
         if self._eng is None:
             name = _game_name_of(state, self.kwargs)
-            flags = L.F_MANUAL | L.F_PRIORS_F64 | L.F_KEEP_TREE
+            flags = L.F_MANUAL | L.F_PRIORS_F64 | L.F_KEEP_TREE | (0 if self.use_puct else L.F_UCT)
             self._eng = Engine(name, 1, n_playouts=self.n_playouts, c_puct=self.c_puct,
                                dirichlet_ratio=self.dirichlet_ratio,
                                noise_mode=L.NOISE_HOST if self.use_dirichlet else L.NOISE_NONE,
@@ -79,6 +78,8 @@ class MCTS:
             self._priors = torch.zeros((1, self.num_distinct_actions), dtype=torch.float64, device=dev)
             self._values = torch.zeros((1,), dtype=torch.float64, device=dev)
             self._noise = torch.zeros((1, self._eng.max_children), dtype=torch.float64, device=dev)
+            if self._leaf_root_updated:
+                self._eng.command(reset_tree=[2])   # the root update_root built for the leaf root (carries use_puct)
         return self._eng
 
     def _sync_position(self, eng, state):
@@ -169,7 +170,10 @@ class MCTS:
         """Re-root at the child of `action`, or a fresh root when the root is a leaf (mcts.py:192-203)."""
         self._root_cache = None
         if self._eng is None:
-            return  # untouched tree: the root is a leaf and stays a fresh node
+            # untouched tree: the root is a leaf and is replaced by Node(None, 0.0, use_puct=self.use_puct) (mcts.py:199-200);
+            # remembered until the engine exists
+            self._leaf_root_updated = True
+            return
         try:
             self._eng.command(update_root=[int(action)])
         except RuntimeError as e:
@@ -180,6 +184,7 @@ class MCTS:
     def reset(self):
         """self.mcts = MCTS(...) (alphazerobot.py:66-68): fresh root, same engine."""
         self._root_cache = None
+        self._leaf_root_updated = False
         if self._eng is not None:
             self._eng.command(reset_tree=[1])
 

@@ -60,6 +60,10 @@ extern "C" {
 #define AZ_F_ASYNC_COMPACT  (1u << 8) /* the caller runs az_compact() itself (e.g. on a side stream next to the evaluator) */
 #define AZ_F_EAGER_COMPACT  (1u << 9) /* compact the kept subtree after EVERY move; default: re-root in place and compact
                                          only when the arena half cannot hold another worst-case search */
+#define AZ_F_UCT            (1u << 10) /* use_puct=False (mcts.py:80): score = inf if N == 0 else
+                                          Q + c_puct * P * sqrt(log(N_parent) / N); log() from a host-built table.  Exactly
+                                          as in the reference the formula belongs to the nodes: only a tree whose root was
+                                          created by update_root on a leaf root (mcts.py:199-200) uses it */
 
 /* root noise (mcts.py:182-190) */
 #define AZ_NOISE_NONE      0 /* use_dirichlet=False */
@@ -165,7 +169,8 @@ int az_set_positions(az_engine* e, const int32_t* hist_host, const int32_t* len_
 
 /* Manual mode commands, one per tree (host arrays, -1 / 0 = no-op):
  *   update_root_host[i] >= 0 : MCTS.update_root(action) mcts.py:192-203 (also advances the tree's position)
- *   reset_tree_host[i] != 0  : self.mcts = MCTS(...) (alphazerobot.py:66-68) -- fresh root
+ *   reset_tree_host[i] != 0  : self.mcts = MCTS(...) (alphazerobot.py:66-68) -- fresh root; the value 2 builds the root that
+ *                              update_root creates for a leaf root instead (it carries use_puct, see AZ_F_UCT)
  *   begin_host[i] != 0       : MCTS.search(state) mcts.py:164-180 -- start n_playouts simulations
  * Order applied: reset, update_root, begin. */
 int az_command(az_engine* e, const int32_t* update_root_host, const int32_t* reset_tree_host,

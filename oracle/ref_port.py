@@ -4,7 +4,7 @@ This is the CPU baseline that travels to the GPU box (the reference is Python an
 not exist there).  It restates, with flat parallel lists instead of linked Node objects:
 
     PortMCTS          <- mcts.py:92-203   (search / playout / expand_root_dirichlet / update_root)
-      ._pick          <- mcts.py:38-52,68-80  Node.select + get_value (PUCT branch)
+      ._pick          <- mcts.py:38-52,68-80  Node.select + get_value (PUCT and use_puct=False branches)
       ._grow          <- mcts.py:54-66    Node.expand
       ._credit        <- mcts.py:82-89    Node.update_recursive
     rollout_policy    <- mcts.py:205-223  MCTS.random_rollout
@@ -28,8 +28,7 @@ import numpy as np
 class PortMCTS:
     def __init__(self, policy_fn, num_distinct_actions, c_puct=2.5, n_playouts=100, use_dirichlet=True,
                  dirichlet_ratio=0.25, use_puct=True, **_ignored):
-        if not use_puct:
-            raise NotImplementedError("UCT mode (mcts.py:80) is a 'next' row, SURVEY 8(f).4")
+        self.use_puct = use_puct
         self.policy_fn = policy_fn
         self.num_distinct_actions = num_distinct_actions
         self.c_puct = c_puct
@@ -37,10 +36,14 @@ class PortMCTS:
         self.use_dirichlet = use_dirichlet
         self.dirichlet_ratio = dirichlet_ratio
         self.stats = {"sims": 0, "depth": 0, "children": 0, "expand": 0, "legal": 0, "terminal": 0, "root_evals": 0}
-        self.fresh()
+        # The reference stores use_puct per Node, children inherit it from their parent (mcts.py:64) and the first root is
+        # built WITHOUT the flag (mcts.py:122): a tree scores with the UCT formula only if its root was created by
+        # update_root on a leaf root (mcts.py:199-200).  One flag per tree reproduces that.
+        self.fresh(uct=False)
 
     # flat storage: index 0.. ; kids[i] is None (leaf) or (actions, ids) in insertion (= legal) order
-    def fresh(self):
+    def fresh(self, uct):
+        self.tree_uct = uct
         self.visits = [0]
         self.mean = [0]
         self.prior = [0.0]
@@ -73,7 +76,12 @@ class PortMCTS:
         root_term = math.sqrt(self.visits[node])
         best_k, best_v = 0, None
         for k, j in enumerate(ids):
-            v = self.mean[j] + self.c_puct * self.prior[j] * root_term / (self.visits[j] + 1)
+            if not self.tree_uct:
+                v = self.mean[j] + self.c_puct * self.prior[j] * root_term / (self.visits[j] + 1)
+            elif self.visits[j] == 0:      # mcts.py:80: unvisited children first, in insertion order
+                v = float("inf")
+            else:
+                v = self.mean[j] + self.c_puct * self.prior[j] * math.sqrt(math.log(self.visits[node]) / self.visits[j])
             if best_v is None or v > best_v:
                 best_k, best_v = k, v
         return ids[best_k], acts[best_k]
@@ -140,7 +148,7 @@ class PortMCTS:
 
     def update_root(self, action):
         if self.kids[self.root] is None:
-            self.fresh()
+            self.fresh(uct=not self.use_puct)
             return
         acts, ids = self.kids[self.root]
         self.root = ids[acts.index(action)]  # ValueError here == the reference's KeyError

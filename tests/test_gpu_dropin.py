@@ -60,6 +60,42 @@ def test_mcts_search_update_root_matches_reference_port(shim, game):
             ours.update_root(A + 5 if game == "connect_four" else 0)
 
 
+@pytest.mark.parametrize("game", ["connect_four", "breakthrough(rows=6,columns=6)"])
+def test_mcts_use_puct_false_matches_reference_port(shim, game):
+    """use_puct=False (mcts.py:80) with the reference's actual semantics (the port is pinned to the live
+    reference in test_oracle_golden): a freshly constructed MCTS still searches with PUCT, a tree whose root was created by
+    update_root on a leaf root searches with the UCT formula -- visit counts, Q and tree reuse equal the port's."""
+    from oracle import ref_port
+    from alphazero_openspiel_b200.mcts import MCTS
+    g = shim.load_game(game)
+    A = g.num_distinct_actions()
+    fn = _hash_policy(5)
+    seen = []
+    for leaf_update_first in (False, True):
+        ours = MCTS(fn, A, n_playouts=90, use_dirichlet=True, use_puct=False, game_name=game)
+        ref = ref_port.PortMCTS(fn, A, n_playouts=90, use_dirichlet=True, use_puct=False)
+        s = g.new_initial_state()
+        if leaf_update_first:
+            first = s.legal_actions()[1]       # what a second player's bot does before its first search
+            s.apply_action(first)
+            ours.update_root(first)
+            ref.update_root(first)
+        for move in range(3):
+            np.random.seed(60 + move)
+            a = ours.search(s)
+            np.random.seed(60 + move)
+            b = ref.search(s)
+            assert list(a) == list(b)
+            assert ours.root.N == ref.visits[ref.root] and ours.root.Q == ref.mean[ref.root]
+            if move == 0:
+                seen.append(list(a))
+            act = int(np.argmax(a))
+            ours.update_root(act)
+            ref.update_root(act)
+            s.apply_action(act)
+        assert ref.tree_uct == leaf_update_first
+
+
 def test_mcts_with_random_rollout_evaluator_matches_port(shim):
     """MCTS.random_rollout as policy_fn (mcts.py:205-223): the device search consumes the host rollouts in
     the reference's order, so visit counts equal the port's from the same numpy seed."""

@@ -257,3 +257,42 @@ def test_random_rollout_evaluator_matches_live_reference():
         np.random.seed(5)
         b = port.search(s)
         assert list(a) == list(b)
+
+
+def test_uct_mode_port_vs_live_reference():
+    """use_puct=False (mcts.py:80) exactly as the reference behaves: the flag lives on the nodes, the first
+    root is built without it (mcts.py:122), so only a tree whose root came from update_root on a leaf root (mcts.py:199-200)
+    scores with the UCT formula.  The port follows the unmodified live reference through both kinds of tree."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("/root/reference is not mounted (GPU box)")
+    pyspiel_shim.install()
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import mcts as ref_mcts
+    fn = _hash_policy(31)
+    for game in ["connect_four", "breakthrough(rows=6,columns=6)"]:
+        g = pyspiel_shim.load_game(game)
+        A = g.num_distinct_actions()
+        for dirichlet in (False, True):
+            for leaf_update_first in (False, True):
+                ref = ref_mcts.MCTS(fn, A, n_playouts=80, use_dirichlet=dirichlet, use_puct=False)
+                port = ref_port.PortMCTS(fn, A, n_playouts=80, use_dirichlet=dirichlet, use_puct=False)
+                s = g.new_initial_state()
+                if leaf_update_first:     # what a second player's bot does before its first search: the UCT tree
+                    first = s.legal_actions()[1]
+                    s.apply_action(first)
+                    ref.update_root(first)
+                    port.update_root(first)
+                    assert ref.root.use_puct is False and port.tree_uct
+                uct_counts = None
+                for move in range(3):
+                    np.random.seed(70 + move)
+                    a = ref.search(s)
+                    np.random.seed(70 + move)
+                    b = port.search(s)
+                    assert list(a) == list(b) and ref.root.Q == port.mean[port.root]
+                    uct_counts = uct_counts or list(a)
+                    act = int(np.argmax(a))
+                    ref.update_root(act)
+                    port.update_root(act)
+                    s.apply_action(act)
