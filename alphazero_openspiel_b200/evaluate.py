@@ -1,5 +1,7 @@
-"""Batched strength check of the search + evaluator: AlphaZeroBot against a uniform-random opponent (SURVEY 8(f) rank 2,
-the `test_zero_vs_random` match-up of game_utils.py:51-63, all games at once on the GPU).
+"""Batched strength checks, all games at once on the GPU:
+  zero_vs_random   AlphaZeroBot against a uniform-random opponent   (`test_zero_vs_random`, game_utils.py:51-63)
+  net_vs_random    NeuralNetBot (argmax of the network policy over the legal moves, no search; alphazerobot.py:96-118)
+                   against a uniform-random opponent                 (`test_net_vs_random`, game_utils.py:100-112)
 
 Every game is one manual-mode tree (AZ_F_MANUAL): on AlphaZero's turn the tree runs `n_playouts` simulations with the
 batched evaluator (no Dirichlet noise, argmax move -- AlphaZeroBot with self_play=False, alphazerobot.py:81-86), the chosen
@@ -71,4 +73,45 @@ def zero_vs_random(net, game_name, n_pairs, n_playouts=100, c_puct=2.5, device="
             raise RuntimeError("search arena overflow during evaluation")
     finally:
         eng.close()
+    return float(score[:n_pairs].mean()), float(score[n_pairs:].mean())
+
+
+@torch.no_grad()
+def net_vs_random(net, game_name, n_pairs, device="cuda:0", seed=0):
+    """`test_net_vs_random` for n_pairs games with the network moving first and n_pairs with the random bot moving first:
+    the network side plays argmax(policy restricted to the legal moves), exactly NeuralNetBot.step.  Returns the two mean
+    scores from the network's point of view."""
+    from .alphazerobot import remove_illegal_actions
+    dev = torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    n = 2 * n_pairs
+    ev = FusedEvaluator(net, n, torch.device("cuda", index))
+    rng = np.random.RandomState(seed)
+    net_player = np.array([0] * n_pairs + [1] * n_pairs)
+    hist = [[] for _ in range(n)]
+    score = np.zeros(n)
+    alive = np.ones(n, dtype=bool)
+    while alive.any():
+        rep = game_replay(game_name, hist, L.OBS_BF16_NHWC, device=index)
+        status = rep["status"].cpu().numpy()
+        ret0 = rep["return0"].cpu().numpy()
+        n_legal = rep["n_legal"].cpu().numpy()
+        legal = rep["legal"].cpu().numpy()
+        for i in np.flatnonzero(alive & ((status & 1) == 1)):
+            score[i] = ret0[i] if net_player[i] == 0 else -ret0[i]
+            alive[i] = False
+        if not alive.any():
+            break
+        to_move = np.array([len(h) % 2 for h in hist])
+        net_turn = alive & (to_move == net_player)
+        if net_turn.any():
+            priors, _ = ev.eval_batch(rep["obs"])
+            priors = priors.double().cpu().numpy()
+        for i in np.flatnonzero(alive):
+            if net_turn[i]:
+                acts = [int(a) for a in legal[i, :n_legal[i]]]
+                a = int(np.argmax(remove_illegal_actions(priors[i].copy(), acts)))
+            else:
+                a = int(legal[i, rng.randint(n_legal[i])])
+            hist[i].append(a)
     return float(score[:n_pairs].mean()), float(score[n_pairs:].mean())

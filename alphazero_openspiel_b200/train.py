@@ -6,7 +6,8 @@ PyTorch (MSE value loss + cross-entropy against the visit-count targets, Adam lr
 With torch.distributed initialised (one process per GPU): every rank plays its share of the games, the records are
 all-gathered, rank 0 trains and the new weights are broadcast over NCCL (parallel.broadcast_weights) -- the reference
 "broadcasts" by pickling a deepcopy of the net into every handler process (examplegenerator.py:121).
-Strength evaluation (test_agent, train.py:238-270) is the match-up harness, out of scope.
+Strength evaluation (test_agent, train.py:238-270): the matches against a uniform-random player run batched on the GPU
+(evaluate.py); the ones against OpenSpiel's MCTSBot are not reproduced.
 """
 import logging
 import time
@@ -201,7 +202,22 @@ class Trainer:
             self.n_games_buffer += self.n_games_per_generation
 
     def test_agent(self):
-        logger.info("test_agent: the strength-evaluation harness is out of scope of the self-play engine (SURVEY 8(f).2)")
+        """train.py:238-270, the opponents that need no OpenSpiel bot: the network alone and the full AlphaZero bot against
+        a uniform-random player, n_tests games each way, batched on the GPU (evaluate.py).  The reference's matches against
+        OpenSpiel's MCTSBot are not reproduced."""
+        from . import evaluate
+        if self.device.type != "cuda":
+            logger.info("test_agent needs the GPU engine; skipped on %s" % self.device)
+            return None
+        start = time.time()
+        logger.info("Testing...")
+        s1, s2 = evaluate.net_vs_random(self.current_net, self.name_game, self.n_tests, device=self.device)
+        logger.info("Average score vs random (net only):" + str((s1 + s2) / 2))
+        z1, z2 = evaluate.zero_vs_random(self.current_net, self.name_game, self.n_tests, n_playouts=self.n_playouts_train,
+                                         c_puct=self.uct_test, device=self.device)
+        logger.info("Average score vs random:" + str((z1 + z2) / 2))
+        logger.info("Testing took: " + str(time.time() - start) + "seconds")
+        return {"net_vs_random": (s1 + s2) / 2, "zero_vs_random": (z1 + z2) / 2}
 
     def run(self, **engine_kwargs):
         """Main loop (train.py:272-293): generate -> train -> (save)."""

@@ -288,3 +288,27 @@ def test_shipped_checkpoint_beats_random_through_the_whole_stack(shim):
     blank = Net([3, 6, 7], 7).eval()
     b_first, b_second = zero_vs_random(blank, "connect_four", n_pairs=64, n_playouts=8, seed=3)
     assert b_first <= 0.85 and b_second <= 0.85, (b_first, b_second)
+
+
+def test_net_only_match_up_and_trainer_test_agent(shim):
+    """evaluate.net_vs_random (`test_net_vs_random`, game_utils.py:100-112: NeuralNetBot = argmax of the policy over the legal
+    moves, no search): the reference's trained checkpoint beats a random player clearly and beats what an untrained network
+    scores; Trainer.test_agent runs both batched match-ups."""
+    import os
+    import torch
+    from alphazero_openspiel_b200.evaluate import net_vs_random
+    from alphazero_openspiel_b200.network import Net
+    from alphazero_openspiel_b200.train import Trainer
+    ck = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example_model_connect_four.pth")
+    net = Net([3, 6, 7], 7)
+    net.load_state_dict(torch.load(ck, map_location="cpu", weights_only=True))
+    net.eval()
+    t1, t2 = net_vs_random(net, "connect_four", n_pairs=128, seed=1)
+    torch.manual_seed(0)
+    b1, b2 = net_vs_random(Net([3, 6, 7], 7).eval(), "connect_four", n_pairs=128, seed=1)
+    assert t1 + t2 > 1.2 and t1 + t2 > b1 + b2 + 0.4, (t1, t2, b1, b2)
+    tr = Trainer(n_tests=8, n_playouts_train=8)
+    tr.current_net.load_state_dict(net.state_dict())
+    out = tr.test_agent()
+    assert set(out) == {"net_vs_random", "zero_vs_random"} and all(-1.0 <= v <= 1.0 for v in out.values())
+    assert out["zero_vs_random"] >= 0.75
