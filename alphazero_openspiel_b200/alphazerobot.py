@@ -5,6 +5,7 @@
       .step(state) -> (policy, action)      alphazerobot.py:42-93
       .restart()                            (north star) fresh tree == constructing a new bot per game
       .mcts                                 the MCTS object callers read (.root, game_utils.py:174-194)
+  NeuralNetBot(game, player, policy_fn).step(state) -> (policy, action)   alphazerobot.py:96-118 (no search, host only)
 
 Host glue (masking, temperature, np.random.choice on the global numpy RNG) follows the reference expression
 by expression so that policy targets and sampled actions are bit-identical for the same seed.
@@ -81,3 +82,20 @@ class AlphaZeroBot(_BotBase):
             action = np.argmax(action_probabilities)
         policy = [(act, visit_probs_legal[act]) for act in legal_actions]
         return policy, action
+
+
+class NeuralNetBot(_BotBase):
+    """The network's policy without search (alphazerobot.py:96-118): mask the illegal moves, renormalise, play the first
+    maximum.  Pure host code on the caller's pyspiel state."""
+
+    def __init__(self, game, player, policy_fn):
+        if _GameType is not None and type(game) is _GameType:
+            super().__init__(game, player)
+        self.policy_fn = policy_fn
+
+    def step(self, state):
+        priors, _value = self.policy_fn(state)
+        legal = state.legal_actions(state.current_player())
+        probs = remove_illegal_actions(np.array(priors), legal)
+        action = np.argmax(probs)
+        return [(a, probs[a]) for a in legal], action

@@ -1,4 +1,5 @@
-"""Drop-in for the self-play driver of the reference's game_utils.py: play_game_self (game_utils.py:148-206).
+"""Drop-in for the self-play driver of the reference's game_utils.py: play_game_self (game_utils.py:148-206), plus the
+two-bot loop play_game (game_utils.py:16-35) for callers that run their own match-ups with AlphaZeroBot / NeuralNetBot.
 
 One game, one AlphaZeroBot for both sides, host-side `policy_fn(state)`; emits per ply
 [information_state string, state_to_board planes, dense policy list, value] with the value target chosen by
@@ -6,8 +7,25 @@ One game, one AlphaZeroBot for both sides, host-side `policy_fn(state)`; emits p
 (az_root_stats) instead of walking Python Node objects.  Needs `pyspiel` for the State objects, exactly like
 the reference; the batched, pyspiel-free path is examplegenerator.ExampleGenerator.
 """
+import copy
+
 from .alphazerobot import AlphaZeroBot
 from .network import state_to_board
+
+
+def play_game(game, player1, player2, generate_statistics=False):
+    """One game between two bots (game_utils.py:16-35): player1 moves on even plies; returns player 0's return, and with
+    generate_statistics the roots both bots held after every move."""
+    stats = {"player1": [], "player2": []}
+    state = game.new_initial_state()
+    while not state.is_terminal():
+        mover = player1 if len(state.history()) % 2 == 0 else player2
+        _, action = mover.step(state)
+        state.apply_action(action)
+        if generate_statistics:
+            stats["player1"].append({"root": copy.deepcopy(player1.mcts.root)})
+            stats["player2"].append({"root": copy.deepcopy(player2.mcts.root)})
+    return (state.returns()[0], stats) if generate_statistics else state.returns()[0]
 
 
 def play_game_self(policy_fn, game_name, **kwargs):

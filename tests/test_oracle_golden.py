@@ -296,3 +296,28 @@ def test_uct_mode_port_vs_live_reference():
                     ref.update_root(act)
                     port.update_root(act)
                     s.apply_action(act)
+
+
+def test_neuralnetbot_and_play_game_match_live_reference():
+    """The host-only pieces of the match-up harness (alphazerobot.py:96-118, game_utils.py:16-35): same policies, actions and
+    game results as the unmodified reference for the same policy function."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("/root/reference is not mounted (GPU box)")
+    pyspiel_shim.install()
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import alphazerobot as ref_bot
+    import game_utils as ref_gu
+    from alphazero_openspiel_b200 import alphazerobot as our_bot, game_utils as our_gu
+    for game in ["connect_four", "breakthrough(rows=6,columns=6)"]:
+        g = pyspiel_shim.load_game(game)
+        fa, fb = _hash_policy(3), _hash_policy(4)
+        s = g.new_initial_state()
+        for _ in range(5):
+            pr, ar = ref_bot.NeuralNetBot(g, 0, fa).step(s)
+            po, ao = our_bot.NeuralNetBot(g, 0, fa).step(s)
+            assert ar == ao and [(int(a), float(p)) for a, p in pr] == [(int(a), float(p)) for a, p in po]
+            s.apply_action(int(ar))
+        want = ref_gu.play_game(g, ref_bot.NeuralNetBot(g, 0, fa), ref_bot.NeuralNetBot(g, 1, fb))
+        got = our_gu.play_game(g, our_bot.NeuralNetBot(g, 0, fa), our_bot.NeuralNetBot(g, 1, fb))
+        assert want == got
