@@ -56,6 +56,12 @@ class AlphaZeroBot(_BotBase):
         self.mcts.reset()
 
     def step(self, state):
+        """One move.  (1) bring the tree to `state`: with tree reuse the moves played since the last search re-root it -- one
+        move in self-play, where this bot plays both sides, two otherwise (alphazerobot.py:53-64); without reuse a new MCTS
+        object is built, i.e. the tree is reset (alphazerobot.py:66-68).  (2) search on the device.  (3) host glue, kept
+        expression by expression so that targets and sampled moves are bit-identical for a numpy seed: mask + renormalise
+        the visit distribution (the returned policy, alphazerobot.py:75-78,89-93), temper it, then draw / argmax
+        (alphazerobot.py:79-86)."""
         if self.keep_search_tree:
             history = state.history()
             if self.self_play:
@@ -73,6 +79,8 @@ class AlphaZeroBot(_BotBase):
         tempered = visit_probs_legal ** (1. / self.temperature)
         action_probabilities = tempered / sum(tempered)
 
+        # exploration schedule: uniformly random or visit-proportional moves during the first num_probabilistic_actions
+        # plies (global numpy RNG, one draw per move, after the search's Dirichlet draw: SURVEY A.10-A.11), greedy afterwards
         n_moves = len(state.history())
         if self.use_random_actions and n_moves < self.num_probabilistic_actions:
             action = np.random.choice(legal_actions)
