@@ -174,9 +174,11 @@ __device__ __forceinline__ double eval_value(const Params& p, const StepIO& io, 
 __device__ double gamma_draw(double alpha, uint64_t seed, uint64_t tree, uint64_t gseq, uint64_t ply, int child) {
   const double d = alpha + 1.0 - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
   for (int att = 0; att < 64; ++att) {
-    const uint64_t r0 = counter(seed, tree, gseq, ply, (uint64_t)child * 256 + att * 3 + 0, 5);
-    const uint64_t r1 = counter(seed, tree, gseq, ply, (uint64_t)child * 256 + att * 3 + 1, 5);
-    const uint64_t r2 = counter(seed, tree, gseq, ply, (uint64_t)child * 256 + att * 3 + 2, 5);
+    // four draws per attempt, 64 attempts: 256 counter indices per child, no overlap between children or attempts
+    const uint64_t base = (uint64_t)child * 256 + (uint64_t)att * 4;
+    const uint64_t r0 = counter(seed, tree, gseq, ply, base + 0, 5);
+    const uint64_t r1 = counter(seed, tree, gseq, ply, base + 1, 5);
+    const uint64_t r2 = counter(seed, tree, gseq, ply, base + 2, 5);
     const double u0 = ((double)(r0 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
     const double u1 = ((double)(r1 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
     const double u2 = ((double)(r2 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
@@ -184,7 +186,7 @@ __device__ double gamma_draw(double alpha, uint64_t seed, uint64_t tree, uint64_
     double v = 1.0 + c * x;
     if (v <= 0.0) continue;
     v = v * v * v;
-    const uint64_t r3 = counter(seed, tree, gseq, ply, (uint64_t)child * 256 + att * 3 + 200, 5);
+    const uint64_t r3 = counter(seed, tree, gseq, ply, base + 3, 5);
     const double u3 = ((double)(r3 >> 11) + 1.0) * (1.0 / 9007199254740992.0);
     if (log(u3) < 0.5 * x * x + d - d * v + d * log(v)) return d * v * pow(u2, 1.0 / alpha);
   }
@@ -1471,10 +1473,15 @@ int az_set_positions(az_engine* e, const int32_t* hist_host, const int32_t* len_
   if (!e || !len_host) return fail(-1, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const Params p = e->p;
-  int32_t *d_hist = nullptr, *d_len = nullptr;
   const size_t hn = (size_t)p.n_trees * (size_t)(max_len > 0 ? max_len : 1);
-  CK(cudaMalloc((void**)&d_hist, sizeof(int32_t) * hn));
-  CK(cudaMalloc((void**)&d_len, sizeof(int32_t) * (size_t)p.n_trees));
+  // one temporary holding lengths + histories; released on every path out of this function
+  int32_t* d_tmp = nullptr;
+  CK(cudaMalloc((void**)&d_tmp, sizeof(int32_t) * (hn + (size_t)p.n_trees)));
+  int32_t *d_len = d_tmp, *d_hist = d_tmp + p.n_trees;
+  struct Free {
+    int32_t* ptr;
+    ~Free() { cudaFree(ptr); }
+  } guard{d_tmp};
   if (max_len > 0 && hist_host) CK(cudaMemcpyAsync(d_hist, hist_host, sizeof(int32_t) * hn, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_len, len_host, sizeof(int32_t) * (size_t)p.n_trees, cudaMemcpyHostToDevice, st));
   dispatch_game(e->cfg.game_id, [&](auto gm) {
@@ -1483,10 +1490,7 @@ int az_set_positions(az_engine* e, const int32_t* hist_host, const int32_t* len_
     return 0;
   });
   CK(cudaGetLastError());
-  int rc = check_bad(e, st, "az_set_positions");
-  cudaFree(d_hist);
-  cudaFree(d_len);
-  return rc;
+  return check_bad(e, st, "az_set_positions");   // synchronises the stream: the temporary is idle when the guard frees it
 }
 
 int az_command(az_engine* e, const int32_t* update_root_host, const int32_t* reset_tree_host, const int32_t* begin_host,

@@ -118,6 +118,12 @@ def records_to_games(records, game_name, backup="on-policy"):
             continue  # unfinished game
         history = []
         game = []
+        # A game that did not start at the initial position (random_start_mod > 0: k random plies first) has no action
+        # history for its first k plies: its start position goes into the key instead, so that remove_duplicates
+        # (train.py:176-198 keys on example[0]) never merges different positions.  The reference always starts at ply 0
+        # (game_utils.py:150-154), where the key is exactly its information_state string.
+        prefix = start_key_prefix(recs["bb"][s], recs["ply"][s])
+        reward = float(recs["root_q"][e - 1])  # kind-1 record carries returns()[0]
         for i in range(s, e - 1):
             r = recs[i]
             pol = pols[pol_rows[i]].tolist()
@@ -128,16 +134,20 @@ def records_to_games(records, game_name, backup="on-policy"):
             elif backup == "off-policy":
                 value = float(r["v_offpolicy"])
             else:
-                value = None
-            game.append([", ".join(str(a) for a in history), boards[i], pol, value])
+                # on-policy (game_utils.py:168-169,200-204): returns()[0] for player 0 to move, negated for player 1.  The
+                # sign comes from the position's real ply, not from the index of the example inside the game.
+                value = reward if (int(r["ply"]) & 1) == 0 else -reward
+            game.append([prefix + ", ".join(str(a) for a in history), boards[i], pol, value])
             history.append(int(r["action"]))
-        if backup == "on-policy":
-            reward = float(recs["root_q"][e - 1])  # kind-1 record carries returns()[0]
-            for ex in game:
-                ex[3] = reward
-                reward *= -1
         games.append(game)
     return games
+
+
+def start_key_prefix(bb, ply):
+    """'' for a game from the initial position, else a tag of the position the game started from."""
+    if int(ply) == 0:
+        return ""
+    return "start=%x/%x/%d; " % (int(bb[0]), int(bb[1]), int(ply))
 
 
 class SelfPlayRunner:
@@ -249,7 +259,10 @@ class SelfPlayRunner:
         return self.engine.drain_records()
 
     def all_idle(self):
-        return int((self.engine.phases() != L.PH_IDLE).sum().item()) == 0
+        """Every tree finished (or is stuck in AZ_PH_ERROR after an arena / depth overflow, which never leaves that phase:
+        counters()['overflow'] tells the two apart)."""
+        ph = self.engine.phases()
+        return int(((ph != L.PH_IDLE) & (ph != L.PH_ERROR)).sum().item()) == 0
 
     def close(self):
         self.engine.close()
@@ -268,6 +281,7 @@ class ExampleGenerator:
         self.device = torch.device(device) if not isinstance(device, torch.device) else device
         self.game_name = game_name
         self.kwargs = kwargs
+        self.rank0_only = bool(self.kwargs.pop("rank0_only", False))
         self.last_stats = {}
 
     def generate_examples(self, n_games):
@@ -280,7 +294,8 @@ class ExampleGenerator:
         if world > 1:
             records = parallel.gather_records(records, self.device)
         backup = str(self.kwargs.get("backup", "on-policy"))
-        games = records_to_games(records, self.game_name, backup)
+        # rank0_only (Trainer: only rank 0 trains): the other ranks skip the host-side conversion and return no games
+        games = [] if (self.rank0_only and rank != 0) else records_to_games(records, self.game_name, backup)
         stats["seconds"] = time.time() - t0
         self.last_stats = stats
         logger.info("Generated " + str(len(games)) + " games")
@@ -298,6 +313,8 @@ class ExampleGenerator:
         records, stats = self._play(share, seed_offset=rank)
         if world > 1:
             records = parallel.gather_records(records, self.device)
+        if self.rank0_only and rank != 0:
+            records = records[:0]
         batch = ExampleBatch.from_records(records, self.game_name, str(self.kwargs.get("backup", "on-policy")))
         stats["seconds"] = time.time() - t0
         self.last_stats = stats
@@ -318,10 +335,16 @@ class ExampleGenerator:
         runner = SelfPlayRunner(self.net, self.game_name, self.device, n_trees, seed=seed, max_games=n_games,
                                 auto_restart=True, records=True, **kw)
         chunks = []
-        # drain the device record buffer before it can fill: ~1.5 * n_trees / n_playouts records arrive per round
+        # Drain the device record buffer before it can fill.  A tree emits one record per move (two when the game ends) and
+        # runs at most max(1, max_sims_per_step) simulations per round, so at most 2 * n_trees * sims_per_round / n_playouts
+        # records arrive per round; drain when half the capacity could be used.
         n_playouts = max(1, int(kw.get("n_playouts", 100)))
+        sims_per_round = max(1, int(kw.get("max_sims_per_step", 8)))
         capacity = int(runner.engine.cfg.record_capacity)
-        drain_every = max(64, int(capacity * n_playouts / (4.0 * n_trees)) // 64 * 64)
+        drain_every = max(64, int(capacity * n_playouts / (4.0 * sims_per_round * n_trees)) // 64 * 64)
+        # upper bound on the round trips a generation can need: every game <= max plies, every ply <= n_playouts + 2 rounds
+        max_plies = 42 if runner.engine.game_id == L.GAME_CONNECT_FOUR else 8 * runner.engine.rows * runner.engine.cols
+        max_rounds = (n_games // n_trees + 2) * max_plies * (n_playouts + 3) + 1024
         since_drain = 0
         try:
             while True:
@@ -332,6 +355,10 @@ class ExampleGenerator:
                 if since_drain >= drain_every:
                     chunks.append(runner.drain())
                     since_drain = 0
+                    if runner.counters()["overflow"]:
+                        break                # raised below: a tree in AZ_PH_ERROR never finishes
+                if runner.rounds > max_rounds:
+                    raise RuntimeError("self-play did not finish within %d round trips" % max_rounds)
             chunks.append(runner.drain())
             stats = runner.counters()
             stats["rounds"] = runner.rounds

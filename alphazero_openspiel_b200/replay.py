@@ -23,14 +23,18 @@ class ExampleBatch:
     bb [N,2] uint64, ply [N] int32            position (canonical bitboards), enough to rebuild the board planes
     hist [N,Lmax] int16 (-1 padded), hist_len [N]   actions played before the position == the info-state key
     policy [N,A] float64, value [N] float64   targets (policy rows sum to 1)
+    start [N,3] uint64                        (bb0, bb1, ply) of the position the example's game started from when that
+                                              was not the initial position (random_start_mod > 0), else zeros: part of
+                                              the key, because such a game has no action history for its first plies
     """
 
-    def __init__(self, game_name, game_ptr, bb, ply, hist, hist_len, policy, value):
+    def __init__(self, game_name, game_ptr, bb, ply, hist, hist_len, policy, value, start=None):
         self.game_name = game_name
         self.game_id, self.rows, self.cols = parse_game_name(game_name)
         self.game_ptr = np.asarray(game_ptr, dtype=np.int64)
         self.bb, self.ply, self.hist, self.hist_len = bb, ply, hist, hist_len
         self.policy, self.value = policy, value
+        self.start = np.zeros((len(ply), 3), np.uint64) if start is None else start
 
     def __len__(self):
         return int(self.bb.shape[0])
@@ -43,7 +47,8 @@ class ExampleBatch:
     @staticmethod
     def empty(game_name, num_actions):
         return ExampleBatch(game_name, np.zeros(1, np.int64), np.zeros((0, 2), np.uint64), np.zeros(0, np.int32),
-                            np.full((0, 1), -1, np.int16), np.zeros(0, np.int32), np.zeros((0, num_actions)), np.zeros(0))
+                            np.full((0, 1), -1, np.int16), np.zeros(0, np.int32), np.zeros((0, num_actions)), np.zeros(0),
+                            np.zeros((0, 3), np.uint64))
 
     @staticmethod
     def from_records(records, game_name, backup="on-policy"):
@@ -76,16 +81,22 @@ class ExampleBatch:
             value = ex["v_a0c"].astype(np.float64)
         elif backup == "off-policy":
             value = ex["v_offpolicy"].astype(np.float64)
-        else:  # on-policy: the final return from player 0's view, sign alternating from the first ply (game_utils.py:198-203)
+        else:  # on-policy: returns()[0] for player 0 to move, negated for player 1 (game_utils.py:168-169,198-203); the sign
+            # comes from the position's real ply (a random-start game may begin with player 1 to move)
             reward = recs["root_q"][ends - 1].astype(np.float64)[g_of]
-            value = np.where(k_of % 2 == 0, reward, -reward)
+            value = np.where((ex["ply"] & 1) == 0, reward, -reward)
         # action history before every position: row i holds the first k_of[i] actions of its game
         lmax = max(int(n_ply.max()) - 1, 1)
         cols_ = np.arange(lmax)[None, :]
         take = np.minimum(starts[g_of][:, None] + cols_, len(recs) - 1)
         hist = np.where(cols_ < k_of[:, None], recs["action"][take].astype(np.int16), np.int16(-1))
+        first = recs[starts[g_of]]                                   # first record of every example's game
+        late = first["ply"] > 0
+        start = np.zeros((n, 3), np.uint64)
+        start[late, 0:2] = first["bb"][late]
+        start[late, 2] = first["ply"][late].astype(np.uint64)
         return ExampleBatch(game_name, game_ptr, ex["bb"].copy(), ex["ply"].astype(np.int32), hist,
-                            k_of.astype(np.int32), policy, value)
+                            k_of.astype(np.int32), policy, value, start)
 
     @staticmethod
     def concat(batches):
@@ -102,7 +113,7 @@ class ExampleBatch:
         return ExampleBatch(f.game_name, np.concatenate(ptr), np.concatenate([b.bb for b in batches]),
                             np.concatenate([b.ply for b in batches]), np.concatenate(hists),
                             np.concatenate([b.hist_len for b in batches]), np.concatenate([b.policy for b in batches]),
-                            np.concatenate([b.value for b in batches]))
+                            np.concatenate([b.value for b in batches]), np.concatenate([b.start for b in batches]))
 
     def last_games(self, n_games):
         """The most recent n_games games (the reference trims its buffer list from the front, train.py:232-234)."""
@@ -111,7 +122,7 @@ class ExampleBatch:
         g0 = self.n_games - n_games
         lo = int(self.game_ptr[g0])
         return ExampleBatch(self.game_name, self.game_ptr[g0:] - lo, self.bb[lo:], self.ply[lo:], self.hist[lo:],
-                            self.hist_len[lo:], self.policy[lo:], self.value[lo:])
+                            self.hist_len[lo:], self.policy[lo:], self.value[lo:], self.start[lo:])
 
     # ------------------------------------------------------------------ views
     def boards(self, ids=None):
@@ -120,8 +131,11 @@ class ExampleBatch:
         return boards_from_bitboards(self.game_id, self.rows, self.cols, self.bb[ids], self.ply[ids])
 
     def key(self, i):
-        """The reference's info-state string of example i (the action history, ', '-joined)."""
-        return ", ".join(str(int(a)) for a in self.hist[i, :self.hist_len[i]])
+        """The reference's info-state string of example i (the action history, ', '-joined); games that did not start at
+        the initial position carry their start position in front (examplegenerator.start_key_prefix)."""
+        from .examplegenerator import start_key_prefix
+        return start_key_prefix(self.start[i, 0:2], self.start[i, 2]) + \
+            ", ".join(str(int(a)) for a in self.hist[i, :self.hist_len[i]])
 
     def to_games(self):
         """Loss-less conversion to the reference's format: list of games of [key str, board ndarray, policy list, value]."""
@@ -142,7 +156,8 @@ class ExampleBatch:
         n = len(self)
         if n == 0:
             return np.zeros(0, np.int64), self.policy[:0], self.value[:0]
-        keyed = np.concatenate([self.hist_len[:, None].astype(np.int16), self.hist], axis=1)
+        keyed = np.concatenate([self.hist_len[:, None].astype(np.int16), self.hist,
+                                np.ascontiguousarray(self.start).view(np.int16).reshape(n, 12)], axis=1)
         _, first, inverse = np.unique(keyed, axis=0, return_index=True, return_inverse=True)
         inverse = inverse.reshape(-1)
         rank = np.empty(len(first), np.int64)                  # unique-order group -> first-occurrence order

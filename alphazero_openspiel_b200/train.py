@@ -31,7 +31,7 @@ class Trainer:
         self.name_game = name_game
         self.name_run = name
         self.model_path = "models/"
-        self.save = False
+        self.save = True
         self.save_n_gens = 10
         self.test_n_gens = 10
         self.n_tests = 200
@@ -57,6 +57,8 @@ class Trainer:
         # Extension: keep the replay buffer as arrays (replay.ExampleBatch) instead of Python lists.
         # Same sampling calls, duplicate merging and losses; `self.buffer` stays empty in this mode.
         self.array_buffer = False
+        # Extension: keep the array buffer on the device and build minibatches there (device_replay.py)
+        self.device_training = False
         for k, v in overrides.items():
             if not hasattr(self, k):
                 raise TypeError("unknown Trainer setting %r" % k)
@@ -177,7 +179,7 @@ class Trainer:
                                      n_playouts=self.n_playouts_train, temperature=self.temperature,
                                      dirichlet_ratio=self.dirichlet_ratio, c_puct=self.uct_train, backup=self.backup,
                                      tree_strap=self.tree_strap, n_pools=self.n_pools, n_processes=self.n_processes,
-                                     **engine_kwargs)
+                                     rank0_only=True, **engine_kwargs)
         if self.array_buffer:
             from .replay import ExampleBatch
             new = generator.generate_batch(n_games)
@@ -206,6 +208,8 @@ class Trainer:
         a uniform-random player, n_tests games each way, batched on the GPU (evaluate.py).  The reference's matches against
         OpenSpiel's MCTSBot are not reproduced."""
         from . import evaluate
+        if parallel.rank_world()[0] != 0:
+            return None
         if self.device.type != "cuda":
             logger.info("test_agent needs the GPU engine; skipped on %s" % self.device)
             return None
@@ -221,10 +225,15 @@ class Trainer:
 
     def run(self, **engine_kwargs):
         """Main loop (train.py:272-293): generate -> train -> (save)."""
+        import os
         rank, _ = parallel.rank_world()
+        self.test_agent()                                       # train.py:275 (before the loop)
         while self.generation < self.n_generations:
             self.generation += 1
             self.generate_examples(self.n_games_per_generation, **engine_kwargs)
             self.train_network()
-            if self.save and rank == 0 and self.generation % self.save_n_gens == 0:
+            if self.save and rank == 0 and self.generation % self.save_n_gens == 0:     # train.py:285-288
+                os.makedirs(self.model_path, exist_ok=True)
                 torch.save(self.current_net.state_dict(), self.model_path + self.name_run + str(self.generation) + ".pth")
+            if self.generation % self.test_n_gens == 0:         # train.py:290-291
+                self.test_agent()

@@ -5,11 +5,16 @@
     python bench.py --impl reference [--steps K] [--warmup W]      # CPU arm: the oracle port of the reference
     torchrun ... bench.py --gpus N ...                             # one rank per GPU, NCCL
 
-Workload (BASELINE.json configs[2]): Connect Four, 800 sims/move, 16,384 concurrent trees per GPU, Dirichlet
-root noise, tree reuse, synthetic start positions (k = counter % 21 random plies), random-init ResNet of the
-reference architecture in bf16.  One "step" = one evaluator round trip for every tree: az_step (consume +
-PUCT simulations + move bookkeeping + observation encode) followed by the batched ResNet forward.  Weak
-scaling: every GPU runs its own independent 16,384-tree pool; there is no data-path collective.
+Default workload (BASELINE.json configs[2], `--config c4`): Connect Four, 800 sims/move, 16,384 concurrent trees per GPU,
+Dirichlet root noise, tree reuse, synthetic start positions (k = counter % 21 random plies), random-init ResNet of the
+reference architecture in bf16.  `--config bt6 | bt8 | train` select BASELINE configs [1], [3], [4].
+
+One evaluator ROUND TRIP for every tree = az_step (consume + PUCT simulations + move bookkeeping + observation encode)
+followed by the batched ResNet forward, one CUDA-graph replay.  One bench "step" = ROUNDS_PER_STEP (50) round trips, so
+that the driver's `--steps 20` times 1,000 round trips (~0.7 s), not 14 ms.  Before the warm-up an untimed SETTLE phase
+runs the pool into steady state whatever --warmup says (at least 1,500 round trips and until every tree has moved twice
+on average and games are finishing): the first searches of a fresh pool run in lock step and are ~40 % faster than the
+steady state.  Weak scaling: every GPU runs its own independent pool; there is no data-path collective.
 
 One JSON line on stdout (rank 0).  `value` = simulations completed in the timed region (device counters,
 summed over ranks) / max-over-ranks CUDA-event time.
@@ -26,9 +31,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per k_conv8 launch, averaged over the nine launches of one evaluation
-# (ncu --set full, profiles/r01_conv8_full_raw.csv; Connect Four, 16,384 boards).  None until captured for another shape.
-CONV_DRAM_TRAFFIC = 249.7e6
+ROUNDS_PER_STEP = 50
+SETTLE_MIN_ROUNDS, SETTLE_MAX_ROUNDS = 1500, 12000
+# BASELINE.json configs by index; trees = concurrent games per GPU
+CONFIGS = {
+    "c4": {"index": 2, "game": "connect_four", "playouts": 800, "trees": 16384},
+    "bt6": {"index": 1, "game": "breakthrough(rows=6,columns=6)", "playouts": 200, "trees": 1024,
+            "checkpoint": os.path.join("tests", "golden", "example_model_breakthrough_6x6.pth")},
+    "bt8": {"index": 3, "game": "breakthrough", "playouts": 800, "trees": 8192},
+    "train": {"index": 4, "game": "connect_four", "playouts": 100, "trees": 0},
+}
+
+
+def conv_dram_traffic(game, trees):
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv launch (averaged over the conv launches of one evaluation)
+    from the committed `ncu --set full` capture of this shape: profiles/conv_traffic.json is written by
+    scripts/summarize_ncu_traffic.py from the raw csv.  None when no capture of this (game, trees) exists."""
+    path = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("%s/%d" % (game, trees), {}).get("bytes_per_launch")
+    except Exception:
+        return None
+
 FLOPS_PER_EVAL = {"connect_four": 17211600, "breakthrough(rows=6,columns=6)": 16282800, "breakthrough": 31097600}
 
 
@@ -171,7 +196,43 @@ def run_reference(args):
 
 
 def workload_name(args):
-    return "%s batched self-play, %d sims/move, %d concurrent trees per GPU" % (args.game, args.playouts, args.trees)
+    return "BASELINE configs[%d]: %s batched self-play, %d sims/move, %d concurrent trees per GPU" % (
+        CONFIGS[args.config]["index"], args.game, args.playouts, args.trees)
+
+
+def build_net(args, shape, n_actions):
+    """Random-init weights of the reference architecture (no checkpoints off-box), except where BASELINE names a shipped
+    model that travels as a test fixture (config [1]: tests/golden/example_model_breakthrough_6x6.pth)."""
+    import torch
+    from alphazero_openspiel_b200.network import Net
+    torch.manual_seed(0)
+    net = Net(shape, n_actions)
+    weights = "random-init weights"
+    ck = CONFIGS[args.config].get("checkpoint")
+    if ck and args.game == CONFIGS[args.config]["game"] and os.path.exists(os.path.join(ROOT, ck)):
+        net.load_state_dict(torch.load(os.path.join(ROOT, ck), map_location="cpu", weights_only=True))
+        weights = "shipped checkpoint " + os.path.basename(ck)
+    net.eval()
+    return net, weights
+
+
+def settle(runner, n_trees, dev):
+    """Untimed: run the pool into steady state (see the module docstring).  Returns the round trips spent."""
+    import torch
+    rounds = 0
+    while True:
+        runner.round(250)
+        rounds += 250
+        if rounds % 1000 == 0:
+            runner.drain()
+        c = runner.counters()
+        torch.cuda.synchronize(dev)
+        if rounds >= SETTLE_MIN_ROUNDS and c["moves"] >= 2 * n_trees and c["games"] > 0:
+            break
+        if rounds >= SETTLE_MAX_ROUNDS:
+            break
+    runner.drain()
+    return rounds
 
 
 def run_ours(args):
@@ -195,9 +256,7 @@ def run_ours(args):
     game = args.game
     shape, n_actions = game_shape(game)
     _, rows, cols = parse_game_name(game)
-    torch.manual_seed(0)
-    net = Net(shape, n_actions)  # random-init weights of the reference architecture (no checkpoints off-box)
-    net.eval()
+    net, weights = build_net(args, shape, n_actions)
     if world > 1:
         from alphazero_openspiel_b200 import parallel
         parallel.broadcast_weights(net, src=0, device=dev)  # NCCL: the per-generation weight broadcast
@@ -206,19 +265,23 @@ def run_ours(args):
                             dirichlet_ratio=0.25, temperature=1.0, backup="on-policy", seed=0xC4 + rank,
                             auto_restart=True, random_start_mod=21, max_sims_per_step=args.sim_cap, records=True,
                             use_graph=not args.no_graph, evaluator=args.evaluator,
-                            keep_search_tree=not args.no_keep_tree, node_capacity=args.node_capacity)
-    # ---- warm-up (untimed): builds the first searches so trees are in steady state.  nvidia-smi needs up to a second to
-    # deliver its first sample, so the clock sampler is started at the end of the warm-up and extra warm-up rounds keep the
-    # GPU under the same load until the first sample has arrived (bounded); only samples taken after mark() are reported.
-    runner.round(args.warmup)
-    runner.drain()
-    torch.cuda.synchronize(dev)
+                            keep_search_tree=not args.no_keep_tree, node_capacity=args.node_capacity,
+                            virtual_loss=args.virtual_loss)
+    rps = ROUNDS_PER_STEP
+    n_rounds = args.steps * rps
+    # ---- settle (untimed, steady state) + warm-up (untimed, W steps).  nvidia-smi needs up to a second to deliver its
+    # first sample, so the clock sampler is started before the warm-up; only samples taken after mark() are reported.
+    settle_rounds = 0 if args.no_settle else settle(runner, args.trees, dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    runner.round(args.warmup * rps)
+    runner.drain()
+    torch.cuda.synchronize(dev)
+    if rank == 0:
         t_wait = time.time()
         while not sampler.rows and time.time() - t_wait < 3.0:
-            runner.round(50)
+            runner.round(rps)
             torch.cuda.synchronize(dev)
         runner.drain()
         torch.cuda.synchronize(dev)
@@ -228,13 +291,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- timed region: K rounds, CUDA events on the launching stream
+    # ---- timed region: K steps = K * 50 round trips, CUDA events on the launching stream
     c0 = runner.counters()
     barrier()
     sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    runner.round(args.steps)
+    runner.round(n_rounds)
     ev1.record()
     torch.cuda.synchronize(dev)
     barrier()
@@ -243,7 +306,7 @@ def run_ours(args):
     c1 = runner.counters()
     d = {k: c1[k] - c0[k] for k in c1}
 
-    # ---- e2e: same metric through the public API with HOST buffers: host weights -> device (H2D), K rounds,
+    # ---- e2e: same metric through the public API with HOST buffers: host weights -> device (H2D), K steps,
     # training records + counters back to host memory (D2H), wall clock around all of it
     host_net = Net(shape, n_actions)
     host_net.load_state_dict(net.state_dict())
@@ -255,7 +318,7 @@ def run_ours(args):
     e0 = runner.counters()
     t0 = time.perf_counter()
     runner.load_weights(host_net)
-    runner.round(args.steps)
+    runner.round(n_rounds)
     recs = runner.drain()
     e1 = runner.counters()
     torch.cuda.synchronize(dev)
@@ -264,7 +327,7 @@ def run_ours(args):
     e2e_sims = e1["sims"] - e0["sims"]
 
     # ---- per-launch durations of the hand-written kernels, live, CUDA events around each launch (un-graphed pass)
-    n_probe = min(args.steps, 200)
+    n_probe = min(n_rounds, 200)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
     nn_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
     p0 = runner.counters()
@@ -290,14 +353,14 @@ def run_ours(args):
     conv_ms, conv_n, stem_ms = 0.0, 0, 0.0
     by_name = {}
     if fused:
-        for name, e0, e1 in ev.timing:
+        for name, e0_, e1_ in ev.timing:
             acc = by_name.setdefault(name, [0.0, 0])
-            acc[0] += e0.elapsed_time(e1)
+            acc[0] += e0_.elapsed_time(e1_)
             acc[1] += 1
             if name == "stem":
-                stem_ms += e0.elapsed_time(e1)
+                stem_ms += e0_.elapsed_time(e1_)
             elif name.startswith("conv"):
-                conv_ms += e0.elapsed_time(e1)
+                conv_ms += e0_.elapsed_time(e1_)
                 conv_n += 1
         ev.timing = None
 
@@ -313,6 +376,8 @@ def run_ours(args):
         ms, t_e2e = float(stats[0]), float(stats[5])
     sims, moves, games, overflow, e2e_sims = float(stats[1]), float(stats[2]), float(stats[3]), float(stats[4]), \
         float(stats[6])
+    node_bytes, node_cap = runner.engine.device_bytes, int(runner.engine.cfg.node_capacity)
+    rows_per_round = runner.evaluator.batch if hasattr(runner.evaluator, "batch") else args.trees
     runner.close()
     if rank != 0:
         if world > 1:
@@ -321,10 +386,10 @@ def run_ours(args):
 
     peaks = load_peaks()
     value = sims / (ms / 1e3)
-    evals_per_s = args.trees * world * args.steps / (ms / 1e3)
+    evals_per_s = rows_per_round * world * n_rounds / (ms / 1e3)
     flops = FLOPS_PER_EVAL.get(game, 0)
     hbm_ach = alg_bytes_per_launch / (step_ms / 1e3) / 1e9
-    nn_tflops = args.trees * flops / (nn_ms / 1e3) / 1e12
+    nn_tflops = rows_per_round * flops / (nn_ms / 1e3) / 1e12
     tree_roofline = {"kernel": "k_step (select/expand/backup/advance/encode)", "bound": "hbm",
                      "achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
                      "traffic": None, "peak_source": peaks["source"], "avg_launch_ms": step_ms,
@@ -333,51 +398,54 @@ def run_ours(args):
     conv_roofline = None
     if fused and conv_n:
         # dominant kernel: k_conv8 (3x3 conv, 50->50 filters, nine launches per evaluation).  Per launch the algorithm
-        # needs boards x 2*HW*50*50*9 FLOPs (30.97 GFLOP, 19 us at the bf16 peak) and reads / writes every [B][H][W][64] bf16
-        # tensor it touches once: in + out (+ residual) (+ second output) = 2-4 x 88 MB, 254 MB averaged over the nine
-        # launches of one evaluation (37-39 us at the measured HBM peak) -> HBM is the binding roofline.
-        conv_flops = args.trees * 2.0 * rows * cols * 50 * 50 * 9
-        tensor_bytes = args.trees * rows * cols * 64 * 2.0
+        # needs boards x 2*HW*50*50*9 FLOPs and reads / writes every [B][H][W][64] bf16 tensor it touches once:
+        # in + out (+ residual) (+ second output) = 2-4 tensors -> HBM is the binding roofline of the launch.
+        conv_flops = rows_per_round * 2.0 * rows * cols * 50 * 50 * 9
+        tensor_bytes = rows_per_round * rows * cols * 64 * 2.0
         n_tensors = {"conv": 2, "conv+res": 3, "conv+out2": 3, "conv+res+out2": 4}
         conv_bytes = sum(n_tensors.get(k, 2) * tensor_bytes * v[1] for k, v in by_name.items() if k.startswith("conv")) / conv_n
         avg_conv_ms = conv_ms / conv_n
         ach = conv_bytes / (avg_conv_ms / 1e3) / 1e9
         conv_roofline = {"kernel": "k_conv8 (tcgen05 implicit-GEMM 3x3 conv, TMA in/out, fused BN/LeakyReLU/residual epilogue)",
                          "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": CONV_DRAM_TRAFFIC, "peak_source": peaks["source"],
-                         "avg_launch_ms": avg_conv_ms, "launches_per_step": conv_n / n_probe,
+                         "frac": ach / peaks["hbm_gbs"], "traffic": conv_dram_traffic(game, rows_per_round),
+                         "peak_source": peaks["source"],
+                         "avg_launch_ms": avg_conv_ms, "launches_per_step": rps * conv_n / n_probe,
                          "algorithmic_bytes_per_launch": conv_bytes, "algorithmic_flops_per_launch": conv_flops,
                          "tensor_tflops": conv_flops / (avg_conv_ms / 1e3) / 1e12,
                          "tensor_frac_of_burst_peak": conv_flops / (avg_conv_ms / 1e3) / 1e12 / peaks["bf16_tflops"],
                          "stem_avg_launch_ms": stem_ms / n_probe,
                          "share_of_step": conv_ms / n_probe / (step_ms + nn_ms),
                          "launch_ms_by_kind": {k: v[0] / v[1] for k, v in sorted(by_name.items())},
-                         "note": "averaged over the nine conv launches of one evaluation (4 plain, 1 +res, 3 +res+out2, "
-                                 "1 +out2); traffic = dram read+write per launch averaged the same way from "
-                                 "profiles/r01_conv8_full_raw.csv; the run is power-capped (see clocks), so the launch "
-                                 "times are those of ~1.6 GHz SM clocks"}
+                         "note": "averaged over the conv launches of one evaluation; traffic = dram read+write per "
+                                 "launch averaged the same way from the committed ncu --set full capture "
+                                 "(profiles/conv_traffic.json), null when this shape was not captured"}
+    launches_per_round = (2 if not args.no_keep_tree else 1) + (len(by_name) and sum(v[1] for v in by_name.values()) // n_probe)
     line = {
         "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "game": game, "n_playouts": args.playouts,
                    "trees_per_gpu": args.trees, "parallelism": "independent game pool per GPU (x%d)" % world,
-                   "evaluator": ("ResNet 5x50 bf16, hand-written tcgen05 implicit-GEMM convs + FC head kernel (az_resnet.cu)"
+                   "rounds_per_step": rps, "settle_rounds": settle_rounds,
+                   "step": "%d evaluator round trips (az_step + ResNet forward, one CUDA graph replay each)" % rps,
+                   "evaluator": ("ResNet 5x50 bf16, hand-written tcgen05 implicit-GEMM convs + FC head kernels (az_resnet.cu)"
                                  if args.evaluator == "fused" else "ResNet 5x50 bf16 channels-last via PyTorch")
-                   + ", random-init weights",
+                   + ", " + weights,
                    "noise": "device Dirichlet(0.3), ratio 0.25", "start": "counter % 21 random plies",
                    "sim_cap_per_step": args.sim_cap, "cuda_graph": not args.no_graph,
-                   "l2_policy": "working set (%.1f GB node arenas + %.0f MB activations per step) exceeds the 126 MB L2"
-                                % (runner.engine.device_bytes / 1e9, args.trees * rows * cols * 64 * 2 * 3 / 1e6)},
+                   "virtual_loss_leaves": args.virtual_loss,
+                   "l2_policy": "working set (%.1f GB node arenas + %.0f MB activations per round trip) exceeds the 126 MB L2"
+                                % (node_bytes / 1e9, rows_per_round * rows * cols * 64 * 2 * 3 / 1e6)},
+        "ms_per_round_trip": ms / n_rounds,
         "games_per_sec": games / (ms / 1e3), "moves_per_sec": moves / (ms / 1e3), "evals_per_sec": evals_per_s,
-        "sims_per_eval_slot": sims / (args.trees * world * args.steps), "overflow": overflow,
-        "peak_nodes_per_tree": c1.get("peak_nodes"), "node_capacity": int(runner.engine.cfg.node_capacity),
+        "sims_per_eval_slot": sims / (rows_per_round * world * n_rounds), "overflow": overflow,
+        "peak_nodes_per_tree": c1.get("peak_nodes"), "node_capacity": node_cap,
         "e2e": {"value": e2e_sims / t_e2e, "unit": "sims/s", "h2d_bytes_per_step": h2d / args.steps,
                 "d2h_bytes_per_step": d2h / args.steps,
-                "what": "SelfPlayRunner.load_weights(host net) + round(K) + drain()/counters() to host, wall clock"},
-        # our kernels per round trip: k_step, k_compact, stem + 9 convs + k_head (larger action spaces: cuBLAS FC head)
-        "gpu_launches": args.steps * world * ((2 if not args.no_keep_tree else 1) +
-                                              ((11 if getattr(ev, "fused_head", False) else 10) if fused else 0)),
+                "what": "SelfPlayRunner.load_weights(host net) + round(K*50) + drain()/counters() to host, wall clock"},
+        # our kernels per round trip: k_step, k_compact, stem + 9 convs + FC head
+        "gpu_launches": n_rounds * world * launches_per_round,
         "roofline": conv_roofline if fused else tree_roofline,
         "tree_roofline": tree_roofline,
         "nn_roofline": {"kernel": "ResNet forward (%s): stem + 9 convs + FC head" % args.evaluator, "bound": "tensor",
@@ -399,28 +467,131 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE configs[4]: the reference's full train.py loop (train.py:272-293) with the Trainer defaults of
+    train.py:24-49 -- 500 games / generation at 100 sims/move, 500 optimisation steps of batch 256 (Adam 1e-3, wd 1e-4) --
+    self-play generation sharded over the GPUs (one process per GPU), records all-gathered, rank 0 trains, NCCL weight
+    broadcast.  One bench "step" = one generation (generate -> train -> broadcast); wall clock with device synchronisation
+    on both sides (the loop is host-driven by nature), max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from alphazero_openspiel_b200 import _lib as L, parallel
+    from alphazero_openspiel_b200.train import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L.load()
+    torch.manual_seed(0)
+    np.random.seed(rank)
+    tr = Trainer(name="bench", name_game=args.game, device=dev, save=False, n_playouts_train=args.playouts,
+                 array_buffer=not args.list_buffer, device_training=not args.list_buffer)
+    gens = max(1, args.generations)
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def one_generation():
+        sync()
+        t0 = time.perf_counter()
+        tr.generation += 1
+        tr.generate_examples(tr.n_games_per_generation)
+        sync()
+        t1 = time.perf_counter()
+        tr.train_network()
+        sync()
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, dict(tr.last_generation_stats)
+
+    one_generation()  # warm-up generation (CUDA graph capture, cuDNN autotune, allocator)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.mark()
+    gen_s, train_s, sims, games = [], [], 0, 0
+    for _ in range(gens):
+        g, t, st = one_generation()
+        gen_s.append(g)
+        train_s.append(t)
+        sims += st.get("sims", 0)
+        games += st.get("games", 0)
+    # the weight broadcast alone (it is the tail of train_network): NCCL broadcast of one flat fp32 bucket
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        parallel.broadcast_weights(tr.current_net, src=0, device=dev)
+    sync()
+    bcast_ms = (time.perf_counter() - t0) / 10 * 1e3
+    tot = torch.tensor([sum(gen_s), sum(train_s), float(sims)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        tot = torch.stack([mx[0], mx[1], sm[2]])
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        gen_t, train_t, all_sims = float(tot[0]), float(tot[1]), float(tot[2])
+        wall = gen_t + train_t
+        line = {"metric": "selfplay_games_per_sec_full_train_loop", "value": games / wall, "unit": "games/s",
+                "n_gpus": world, "steps": gens, "warmup": 1, "ms_per_step": 1e3 * wall / gens, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64 search / bf16 evaluator / fp32 training",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE configs[4]: full train.py loop, %s, Trainer defaults (%d games/generation, "
+                                       "%d sims/move, %d x batch %d Adam steps), generation on %d GPU(s) + NCCL weight broadcast"
+                                       % (args.game, tr.n_games_per_generation, args.playouts, tr.n_batches_per_generation,
+                                          tr.batch_size, world),
+                           "step": "one generation: generate_examples -> train_network -> broadcast"},
+                "generation_s": gen_t / gens, "train_s": train_t / gens, "broadcast_ms": bcast_ms,
+                "sims_per_sec_in_generation": all_sims / gen_t if gen_t > 0 else None,
+                "games_per_generation": games / gens, "buffer": "arrays on device" if not args.list_buffer else "python lists",
+                "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=1500)
+    ap.add_argument("--steps", type=int, default=20, help="timed steps; one step = %d evaluator round trips" % ROUNDS_PER_STEP)
+    ap.add_argument("--warmup", type=int, default=5, help="untimed warm-up steps after the settle phase")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--game", default="connect_four")
-    ap.add_argument("--trees", type=int, default=16384)
-    ap.add_argument("--playouts", type=int, default=800)
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS), help="BASELINE.json config (default: configs[2])")
+    ap.add_argument("--game", default=None)
+    ap.add_argument("--trees", type=int, default=None)
+    ap.add_argument("--playouts", type=int, default=None)
     ap.add_argument("--sim-cap", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-settle", action="store_true", help="profiling runs: skip the steady-state settle phase")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--ref-repeat", action="store_true")
     ap.add_argument("--evaluator", default="fused", choices=["fused", "torch"])
     ap.add_argument("--node-capacity", type=int, default=0)
+    ap.add_argument("--virtual-loss", type=int, default=0, help="K leaves in flight per tree (non-bit-exact mode); 0 = off")
+    ap.add_argument("--generations", type=int, default=3, help="--config train: generations timed")
+    ap.add_argument("--list-buffer", action="store_true", help="--config train: the reference's Python-list replay buffer")
     ap.add_argument("--no-keep-tree", action="store_true", help="experiment: fresh tree every move (no re-root compaction)")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.game = args.game or cfg["game"]
+    args.trees = args.trees or cfg["trees"]
+    args.playouts = args.playouts or cfg["playouts"]
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "train":
+        run_train(args)
     else:
         run_ours(args)
 

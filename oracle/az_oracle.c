@@ -213,6 +213,29 @@ void oz_synth_eval(const oz_state* s, int kind, uint64_t seed, int shift, double
   *value = (double)((int)((k >> 20) & 31) - 16) / 16.0;
 }
 
+/* Batched form over canonical bitboards (what az_request_info returns): row i gets the evaluator outputs of the position
+ * (bb[2i], bb[2i+1], side to move = ply[i] & 1) as fp32 -- the values are small dyadic rationals, exact in fp32.  Rows with
+ * ply[i] < 0 (no request pending) are left untouched.  Used by the AZ_EVAL_EXTERNAL parity test. */
+void oz_synth_eval_bb(int num_actions, int n, const uint64_t* bb, const int32_t* ply, int kind, uint64_t seed, int shift,
+                      float* priors, float* values) {
+  const double scale = ldexp(1.0, -(10 + shift));
+  for (int i = 0; i < n; ++i) {
+    if (ply[i] < 0) continue;
+    float* pr = priors + (size_t)i * (size_t)num_actions;
+    if (kind == 0) {
+      for (int a = 0; a < num_actions; ++a) pr[a] = (float)(1.0 / (double)num_actions);
+      values[i] = 0.0f;
+      continue;
+    }
+    const uint64_t k = oz_mix64(bb[2 * i] ^ oz_mix64(bb[2 * i + 1] ^ oz_mix64(seed + (uint64_t)(ply[i] & 1))));
+    for (int a = 0; a < num_actions; ++a) {
+      const uint64_t ha = oz_mix64(k + (uint64_t)(a + 1) * 0xD1B54A32D192ED03ULL);
+      pr[a] = (float)((double)(1 + (int)((ha >> 40) & 0x3FF)) * scale);
+    }
+    values[i] = (float)((double)((int)((k >> 20) & 31) - 16) / 16.0);
+  }
+}
+
 /* ===================================================================================
  * MCTS (mcts.py).  Flat node arrays; children of a node are one contiguous block in
  * legal-action (ascending) order == the reference's dict insertion order (A.2).

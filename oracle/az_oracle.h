@@ -72,6 +72,10 @@ uint64_t oz_counter(uint64_t seed, uint64_t tree, uint64_t game_seq, uint64_t pl
 /* kind 0: uniform 1/A, value 0.  kind 1: hash priors (1+r10)*2^-(10+shift), value on a 1/16 grid */
 void oz_synth_eval(const oz_state* s, int kind, uint64_t seed, int shift, double* priors, double* value);
 
+/* the same evaluator for n positions given as canonical bitboards + ply (fp32 out; rows with ply < 0 untouched) */
+void oz_synth_eval_bb(int num_actions, int n, const uint64_t* bb, const int32_t* ply, int kind, uint64_t seed, int shift,
+                      float* priors, float* values);
+
 /* ---- MCTS ---- */
 typedef void (*oz_eval_fn)(const oz_state* s, double* priors, double* value, void* user);
 typedef struct oz_tree oz_tree;

@@ -84,6 +84,8 @@ def lib():
         "oz_mix64": (C.c_uint64, [C.c_uint64]),
         "oz_counter": (C.c_uint64, [C.c_uint64] * 6),
         "oz_synth_eval": (None, [P(OzState), C.c_int, C.c_uint64, C.c_int, P(C.c_double), P(C.c_double)]),
+        "oz_synth_eval_bb": (None, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_void_p,
+                                    C.c_void_p]),
         "oz_tree_new": (C.c_void_p, [C.c_int, C.c_double, C.c_int, C.c_int, C.c_double]),
         "oz_tree_free": (None, [C.c_void_p]),
         "oz_tree_reset": (None, [C.c_void_p]),

@@ -270,3 +270,65 @@ def test_async_compaction_on_side_stream_is_bit_exact(eager):
         for r, g in zip(ref, plies):
             assert list(g["counts"][:r["n_legal"]]) == r["counts"] and g["action"] == r["action"]
             assert g["root_q"] == r["root_q"] and g["v_offpolicy"] == r["v_offpolicy"] and g["root_n"] == r["root_n"]
+
+
+@pytest.mark.parametrize("game,n_trees,n_playouts", [("connect_four", 256, 60), ("breakthrough(rows=6,columns=6)", 256, 24)])
+def test_batched_external_evaluator_path_bit_exact(game, n_trees, n_playouts):
+    """The path the benchmark runs: AZ_EVAL_EXTERNAL with fp32 `priors[tree*A + a]` / `values[tree]` rows for n_trees >> 1
+    (az_engine.cu eval_prior / eval_value).  The host answers every request from the oracle's evaluator on the
+    az_request_info bitboards; the records must equal the in-kernel AZ_EVAL_HASH run AND the C oracle ply by ply
+    (visit counts, root N / Q, targets, actions, positions) -- north_star: "bit-exact given the same evaluator outputs"
+    (mcts.py:146 policy_fn call, network.py:66-80 fp32 outputs widened to Python floats)."""
+    import torch
+    from oracle import cbind
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    seed = 2024
+    flags = L.F_RECORDS | L.F_OFFPOLICY | L.F_KEEP_TREE | L.F_SAMPLE_MOVES
+    eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=L.NOISE_COUNTER, eval_mode=L.EVAL_EXTERNAL, flags=flags,
+                   seed=seed)
+    A = eng.num_actions
+    shift = 2 if game == "connect_four" else 4
+    olib = cbind.lib()
+    pri_h = torch.zeros((n_trees, A), dtype=torch.float32).pin_memory()
+    val_h = torch.zeros((n_trees,), dtype=torch.float32).pin_memory()
+    pri_d = torch.zeros((n_trees, A), dtype=torch.float32, device=eng.device)
+    val_d = torch.zeros((n_trees,), dtype=torch.float32, device=eng.device)
+    eng.step()                       # produces the first requests (nothing to consume yet)
+    answered = 0
+    for it in range(200000):
+        info = eng.request_info(max_depth=1)
+        bb = np.ascontiguousarray(info["bb"])
+        ply = np.ascontiguousarray(info["ply"])
+        if int((ply >= 0).sum()) == 0 and int((eng.phases() != L.PH_IDLE).sum()) == 0:
+            break                    # (a step without any request is possible: every live tree waits for k_compact)
+        answered += int((ply >= 0).sum())
+        # rows of trees without a request keep stale values on purpose: the engine must ignore them
+        olib.oz_synth_eval_bb(A, n_trees, bb.ctypes.data, ply.ctypes.data, 1, seed, shift, pri_h.data_ptr(), val_h.data_ptr())
+        pri_d.copy_(pri_h, non_blocking=True)
+        val_d.copy_(val_h, non_blocking=True)
+        eng.step(pri_d, val_d)
+        torch.cuda.synchronize()     # the pinned rows are rewritten next iteration
+    recs = eng.drain_records()
+    ctr = eng.counters()
+    eng.close()
+    assert ctr["overflow"] == 0 and int((recs["kind"] == 1).sum()) == n_trees
+    assert answered == ctr["expansions"] + ctr["root_evals"]      # one evaluator row per expansion / root evaluation
+    recs_h, ctr_h = _run_engine_selfplay(game, n_trees, n_playouts, seed, L.NOISE_COUNTER, 1, 1)
+    key = lambda r: np.lexsort((r["kind"], r["ply"], r["tree"]))  # noqa: E731
+    a, b = recs[key(recs)], recs_h[key(recs_h)]
+    assert len(a) == len(b)
+    for f in ["tree", "ply", "action", "n_legal", "kind", "root_n", "bb", "root_q", "v_a0c", "v_offpolicy", "counts", "actions"]:
+        assert np.array_equal(a[f], b[f]), f
+    for k in ["sims", "depth", "children", "expansions", "legal", "terminal", "root_evals", "moves", "games"]:
+        assert ctr[k] == ctr_h[k], k
+    cfg = ou.selfplay_cfg(game, n_playouts, use_dirichlet=2, sample_moves=1, keep_tree=1, seed=seed)
+    for t in range(n_trees):
+        plies = recs[(recs["tree"] == t) & (recs["kind"] == 0)]
+        plies = plies[np.argsort(plies["ply"])]
+        ref, ret, _ = ou.selfplay_game(cfg, t)
+        assert len(plies) == len(ref)
+        for r, g in zip(ref, plies):
+            assert list(g["counts"][:r["n_legal"]]) == r["counts"] and g["action"] == r["action"], (t, r["ply"])
+            assert g["root_q"] == r["root_q"] and g["root_n"] == r["root_n"]
+            assert g["v_a0c"] == r["v_a0c"] and g["v_offpolicy"] == r["v_offpolicy"]
+            assert (int(g["bb"][0]), int(g["bb"][1])) == r["bb"]

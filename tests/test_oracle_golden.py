@@ -164,6 +164,33 @@ def test_encoding_pins_with_shipped_checkpoint():
     assert pins["bt6_legal_mass_mean"] > 0.98
 
 
+def test_breakthrough_encoding_pins_with_shipped_checkpoint():
+    """Same pin for Breakthrough 6x6 (tests/golden/make_golden_bt6.py): the reference Net with its shipped 6x6 checkpoint on
+    64 positions -> priors [432] / value reproduced by the oracle's RefNet over the oracle's planes (plane order black /
+    white / empty, row 0 = black's home row, action id = ((r*C + c)*6 + dir)*2 + capture); the legal-move lists
+    of the game restatement carry 0.98 of the trained policy mass, which no other numbering does."""
+    import torch
+    from oracle import ref_net
+    pins = np.load(os.path.join(HERE, "golden", "bt6_pins.npz"))
+    sd = torch.load(os.path.join(HERE, "golden", "example_model_breakthrough_6x6.pth"), map_location="cpu",
+                    weights_only=True)
+    net = ref_net.RefNet([3, 6, 6], 432).eval()
+    net.load_state_dict(sd)
+    game = "breakthrough(rows=6,columns=6)"
+    boards, mass = [], []
+    for i, h in enumerate(pins["histories"]):
+        st = _state(game, [int(a) for a in h if a >= 0])
+        boards.append(ref_port.board_planes(st, [3, 6, 6]))
+        legal = st.legal_actions()
+        assert legal == [int(a) for a in pins["legal"][i] if a >= 0]
+        mass.append(float(pins["p"][i, legal].sum()))
+    with torch.no_grad():
+        p, v = net(torch.from_numpy(np.array(boards)).float())
+    assert np.abs(p.numpy() - pins["p"]).max() < 1e-5
+    assert np.abs(v.numpy()[:, 0] - pins["v"]).max() < 1e-5
+    assert np.mean(mass) > 0.97
+
+
 def test_game_rules_properties():
     """Random playouts: legal lists ascending, terminal <=> no legal moves, returns zero-sum, C4 draw only at 42."""
     rng = np.random.RandomState(1)

@@ -131,11 +131,11 @@ def test_array_buffer_generations_match_the_list_buffer():
         assert all(torch.isfinite(v.float()).all() for v in sd.values())
 
 
-def _oracle_records(n_games=6, game="connect_four", playouts=20, seed=9):
+def _oracle_records(n_games=6, game="connect_four", playouts=20, seed=9, start_mod=0):
     """Device-format training records synthesised from the C oracle's self-play (as in test_cabi_and_host)."""
     from alphazero_openspiel_b200.engine import record_dtype
     from tests import oracle_util as ou
-    cfg = ou.selfplay_cfg(game, playouts, use_dirichlet=2, sample_moves=1, seed=seed)
+    cfg = ou.selfplay_cfg(game, playouts, use_dirichlet=2, sample_moves=1, seed=seed, start_mod=start_mod)
     dt = record_dtype(7, (72 + 6 * 7 + 7) // 8 * 8)
     rows = []
     for t in range(n_games):
@@ -149,11 +149,15 @@ def _oracle_records(n_games=6, game="connect_four", playouts=20, seed=9):
             rec["root_q"], rec["v_a0c"], rec["v_offpolicy"] = r["root_q"], r["v_a0c"], r["v_offpolicy"]
             rec["counts"][:r["n_legal"]] = r["counts"]
             rec["actions"][:] = -1
-            rec["actions"][:r["n_legal"]] = ou.replay(game, hist)["legal"]
+            if start_mod == 0:
+                rec["actions"][:r["n_legal"]] = ou.replay(game, hist)["legal"]
+            else:   # random-start games have no history from the initial position: Connect Four legal = non-full columns
+                occ = int(r["bb"][0]) | int(r["bb"][1])
+                rec["actions"][:r["n_legal"]] = [c for c in range(7) if not (occ >> (35 + c)) & 1]
             rows.append(rec)
             hist.append(r["action"])
         end = np.zeros((), dtype=dt)
-        end["tree"], end["kind"], end["ply"], end["root_q"] = t, 1, len(plies), ret[0]
+        end["tree"], end["kind"], end["ply"], end["root_q"] = t, 1, plies[-1]["ply"] + 1, ret[0]
         rows.append(end)
     recs = np.array(rows, dtype=dt)
     return recs[np.random.RandomState(1).permutation(len(recs))]
@@ -215,3 +219,37 @@ def test_array_remove_duplicates_and_net_step_match_the_list_path():
         assert float(la[0]) == float(lb[0]) and float(la[1]) == float(lb[1])
     for x, y in zip(a.current_net.parameters(), b.current_net.parameters()):
         assert torch.equal(x, y)
+
+
+def test_random_start_games_get_signs_from_the_ply_and_keys_from_the_start_position():
+    """with random_start_mod > 0 a game may begin with player 1 to move and has no action history for
+    its first plies.  The on-policy value is returns()[0] for player 0 to move and its negation for player 1
+    (game_utils.py:168-169,200-204) -- from the position's real ply -- and the de-duplication key carries the start
+    position so that different positions never share a key.  Both example forms agree."""
+    from alphazero_openspiel_b200.examplegenerator import records_to_games
+    from alphazero_openspiel_b200.replay import ExampleBatch
+    recs = _oracle_records(n_games=12, start_mod=9, seed=3)
+    games = records_to_games(recs, "connect_four", "on-policy")
+    batch = ExampleBatch.from_records(recs, "connect_four", "on-policy")
+    assert len(games) == 12 and batch.n_games == 12
+    odd_starts = 0
+    keys = set()
+    for g, gb in zip(games, batch.to_games()):
+        ret0 = None
+        for ex, exb in zip(g, gb):
+            board = ex[1]
+            player = int(board[3, 0, 0])                     # current-player plane (network.py:16-17)
+            n_pieces = int(board[1].sum() + board[2].sum())
+            assert player == n_pieces % 2
+            if ret0 is None:
+                ret0 = ex[3] if player == 0 else -ex[3]
+                odd_starts += player
+                assert (n_pieces == 0) == (not ex[0].startswith("start="))
+            assert ex[3] == (ret0 if player == 0 else -ret0)
+            assert ex[0] == exb[0] and ex[3] == exb[3] and np.array_equal(ex[1], exb[1])
+            keys.add((ex[0], board.tobytes()))
+    assert odd_starts > 0                                    # the case the old index-based sign got wrong
+    # one key never names two different positions
+    assert len({k for k, _ in keys}) == len(keys)
+    first, _, _ = batch.remove_duplicates()
+    assert len(first) == len({k for k, _ in keys})
