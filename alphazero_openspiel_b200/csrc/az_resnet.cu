@@ -18,14 +18,16 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "../../include/az_b200.h"
 
 namespace aznn {
 
-constexpr int CH = 64;            // padded channel count (50 filters -> 64)
+constexpr int CH = 64;            // padded channel count in memory (50 filters -> 64): the K dimension of the convs
+constexpr int NF = 50;            // real filters (network.py:22 n_filters): the output channels a conv computes
 constexpr int TILE_M = 128;       // output rows per MMA tile
-constexpr int W_BYTES = 9 * CH * CH * 2;            // 73,728: one layer's weights, resident in smem for the whole launch
+constexpr int W_BYTES = 9 * CH * CH * 2;            // 73,728: smem reserved for one layer's weights (the dx-packed image uses 61,440)
 constexpr float LRELU_SLOPE = 0.01f;
 
 // ---------------------------------------------------------------- PTX helpers
@@ -94,6 +96,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {  // exactly one lane of a converged warp
@@ -209,7 +214,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int 
 
 constexpr int C8_GROUPS = 18;                 // 8-row groups per slab: 16 of the tile + one above + one below
 constexpr int C8_A_ST = C8_GROUPS * 1024;     // 18,432 B per stage
-constexpr int C8_N = 192;
+// MMA N dimension: the three dx taps of a kernel row side by side, 50 output channels each, packed without padding
+// (n = dx*50 + co; columns 150..159 are zero weights): N = 160 instead of 3 x 64 = 192 -> 17 % fewer MMA columns and
+// B-operand bytes, and three accumulators fit in the 512 TMEM columns.
+constexpr int C8_N = 160;
+constexpr int C8_ACC = 3;                     // TMEM accumulator stages (3 x 160 columns)
 // The stem's tensor-core work is tiny (K = 16), so it keeps nine row-shifted views of N = 64 and the cheap epilogue: no
 // dx recombination.  Its slab has two groups of halo on each side (a tap reaches 9 rows back) and exists in three copies,
 // one per dx, because without a pad column (W = 8) the dx = -1 / +1 views must not see the cell that wraps around from
@@ -226,8 +235,8 @@ struct Conv8Smem {
   static constexpr int BIAS_OFF = STG_OFF + NE * STG_WARP;
   static constexpr int S2_OFF = BIAS_OFF + 256;
   static constexpr int T2_OFF = S2_OFF + 256;
-  static constexpr int BAR_OFF = T2_OFF + 256;       // full[S] empty[S] tfull[2] tempty[2] w resbar[NE][2]
-  static constexpr int N_BARS = 2 * S + 5 + 2 * NE;
+  static constexpr int BAR_OFF = T2_OFF + 256;       // full[S] empty[S] tfull[ACC] tempty[ACC] w resbar[NE][2]
+  static constexpr int N_BARS = 2 * S + 2 * C8_ACC + 1 + 2 * NE;
   static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
@@ -239,9 +248,9 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
   using L = Conv8Smem<NE, S>;
   constexpr int NPROD = STEM ? 4 : 1;                    // producer warps; the MMA issuer is warp NPROD, then the epilogue
   constexpr int K_STEPS = 4;                             // 16-channel k-steps per kernel row
-  constexpr int W_ROW_BYTES = C8_N * 16 * 2 * K_STEPS;   // one kernel row (dy) of weights: 24,576 B
+  constexpr int W_ROW_BYTES = C8_N * 16 * 2 * K_STEPS;   // one kernel row (dy) of weights: 160 rows x 128 B = 20,480 B
   constexpr int STEM_TAP_BYTES = 2 * CH * 16;            // stem: one tap = [2 k-chunks][64 n][8] bf16
-  constexpr int ACC = 2;
+  constexpr int ACC = C8_ACC;
   constexpr uint32_t TMEM_COLS = 512u;
   static_assert(!STEM || S == 4, "one stem producer warp per stage");
   constexpr int NEQ = NE / 4;                            // epilogue warps per TMEM lane quarter
@@ -258,9 +267,9 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
   auto bar_full = [&](int s) { return s_bar + 8u * s; };
   auto bar_empty = [&](int s) { return s_bar + 8u * (S + s); };
   auto bar_tfull = [&](int a) { return s_bar + 8u * (2 * S + a); };
-  auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * S + 2 + a); };
-  auto bar_w = [&]() { return s_bar + 8u * (2 * S + 4); };
-  auto bar_res = [&](int e, int b) { return s_bar + 8u * (2 * S + 5 + 2 * e + b); };
+  auto bar_tempty = [&](int a) { return s_bar + 8u * (2 * S + ACC + a); };
+  auto bar_w = [&]() { return s_bar + 8u * (2 * S + 2 * ACC); };
+  auto bar_res = [&](int e, int b) { return s_bar + 8u * (2 * S + 2 * ACC + 1 + 2 * e + b); };
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + L::N_BARS * 8);
 
   if (warp == NPROD && lane == 0) {
@@ -376,7 +385,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       }
     } else if (lane == 0) {
       // =========================== TMA producer ===========================
-      mbar_expect_tx(bar_w(), (uint32_t)W_BYTES);
+      mbar_expect_tx(bar_w(), (uint32_t)(3 * W_ROW_BYTES));
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         bulk_g2s(s_w + (uint32_t)i * W_ROW_BYTES, reinterpret_cast<const uint8_t*>(p.wpack) + i * W_ROW_BYTES, W_ROW_BYTES, bar_w());
@@ -491,33 +500,47 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       const bool pad_row = (g0 + (lane >> 3)) % p.HP == p.H;      // this thread's row lies in a board's zero pad row
       mbar_wait(bar_tfull(acc), (uint32_t)(it / ACC) & 1u);
       tc_fence_after();
+      // Channels of this item: half 0 = 0..31; half 1 = 32..49 (18 real filters; 50..63 are written as zeros, the stem
+      // puts the raw planes into 50..53).  A 16-channel block therefore carries NV = 16 or, for the last block of half 1 of
+      // a conv, NV = 2 live values: its TMEM loads, shuffles and epilogue arithmetic shrink accordingly.
       uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C8_N + col0);
+      const bool short_blk = !STEM && half == 1;      // block cb = 1 of this item has only 2 live channels (48, 49)
       if constexpr (STEM) {
         tmem_ld16(taddr, &v[0]);
         tmem_ld16(taddr + 16u, &v[16]);
         tmem_ld_wait();
       } else {
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
-        uint32_t dm[16], d0[16], dp[16];
-        tmem_ld16(taddr + (uint32_t)(cb * 16), dm);
-        tmem_ld16(taddr + (uint32_t)(64 + cb * 16), d0);
-        tmem_ld16(taddr + (uint32_t)(128 + cb * 16), dp);
-        tmem_ld_wait();
+        // accumulator columns: D_-1 at [0, 50), D_0 at [50, 100), D_+1 at [100, 150)   (n = dx*50 + co)
         // Rotating shuffles: lane 0 receives lane 31's D_-1 and lane 31 lane 0's D_+1.  With pad columns (W < 8) the
         // partial sums of a pad cell are zero and its own output is never stored, so the weights are 1; without (W == 8)
         // the row wrap-around at c = 0 / c = 7 gets weight 0.  (The partial sums are finite, so 0 * x is exact.)
+        auto combine = [&](auto nv_tag, int cb) {
+          constexpr int NV = decltype(nv_tag)::value;
+          uint32_t dm[NV], d0[NV], dp[NV];
+          if constexpr (NV == 16) {
+            tmem_ld16(taddr + (uint32_t)(cb * 16), dm);
+            tmem_ld16(taddr + (uint32_t)(NF + cb * 16), d0);
+            tmem_ld16(taddr + (uint32_t)(2 * NF + cb * 16), dp);
+          } else {
+            tmem_ld2(taddr + (uint32_t)(cb * 16), dm);
+            tmem_ld2(taddr + (uint32_t)(NF + cb * 16), d0);
+            tmem_ld2(taddr + (uint32_t)(2 * NF + cb * 16), dp);
+          }
+          tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 16; k += 2) {  // two values per FFMA2
-          const float up0 = __shfl_sync(0xffffffffu, __uint_as_float(dm[k]), (lane + 31) & 31);
-          const float up1 = __shfl_sync(0xffffffffu, __uint_as_float(dm[k + 1]), (lane + 31) & 31);
-          const float dn0 = __shfl_sync(0xffffffffu, __uint_as_float(dp[k]), (lane + 1) & 31);
-          const float dn1 = __shfl_sync(0xffffffffu, __uint_as_float(dp[k + 1]), (lane + 1) & 31);
-          const uint64_t acc2 = fma_f32x2(w_up2, f32x2(up0, up1), f32x2(__uint_as_float(d0[k]), __uint_as_float(d0[k + 1])));
-          unpack_f32x2(fma_f32x2(w_dn2, f32x2(dn0, dn1), acc2), v[cb * 16 + k], v[cb * 16 + k + 1]);
-        }
-      }
+          for (int k = 0; k < NV; k += 2) {  // two values per FFMA2
+            const float up0 = __shfl_sync(0xffffffffu, __uint_as_float(dm[k]), (lane + 31) & 31);
+            const float up1 = __shfl_sync(0xffffffffu, __uint_as_float(dm[k + 1]), (lane + 31) & 31);
+            const float dn0 = __shfl_sync(0xffffffffu, __uint_as_float(dp[k]), (lane + 1) & 31);
+            const float dn1 = __shfl_sync(0xffffffffu, __uint_as_float(dp[k + 1]), (lane + 1) & 31);
+            const uint64_t acc2 = fma_f32x2(w_up2, f32x2(up0, up1), f32x2(__uint_as_float(d0[k]), __uint_as_float(d0[k + 1])));
+            unpack_f32x2(fma_f32x2(w_dn2, f32x2(dn0, dn1), acc2), v[cb * 16 + k], v[cb * 16 + k + 1]);
+          }
+        };
+        combine(std::integral_constant<int, 16>{}, 0);
+        if (short_blk) combine(std::integral_constant<int, 2>{}, 1);
+        else combine(std::integral_constant<int, 16>{}, 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -539,13 +562,17 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       if (has_res) mbar_wait(bar_res(e, b), (uint32_t)(n >> 1) & 1u);
       uint8_t* io = stg + b * 2048 + row_off;
       uint8_t* o2 = stg + 4096 + row_off;
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {  // 16 columns = two 16-byte chunks at a time
+      const bool packed_act = p.lrelu && !has_res;   // the usual case: activate the packed result, 1 op per value
+      // pad columns hold don't-care values (the store clips them); the pad row is stored and must stay zero
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      // one 16-channel block (two 16-byte chunks of this thread's staging row) with NV live values
+      auto finish = [&](auto nv_tag, int cb) {
+        constexpr int NV = decltype(nv_tag)::value;
         const uint32_t c0 = (((uint32_t)(2 * cb)) ^ sw) * 16u, c1 = (((uint32_t)(2 * cb + 1)) ^ sw) * 16u;
         float f[16];
         const uint64_t* bias2 = reinterpret_cast<const uint64_t*>(s_bias + col0 + cb * 16);
 #pragma unroll
-        for (int k = 0; k < 16; k += 2) {  // two values per FADD2
+        for (int k = 0; k < NV; k += 2) {  // two values per FADD2
           uint32_t lo, hi;
           unpack_f32x2(add_f32x2(f32x2(__uint_as_float(v[cb * 16 + k]), __uint_as_float(v[cb * 16 + k + 1])), bias2[k >> 1]), lo, hi);
           f[k] = __uint_as_float(lo);
@@ -553,15 +580,15 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
         }
         if (p.lrelu && has_res) {  // (activation before a residual add: keep it in fp32)
 #pragma unroll
-          for (int k = 0; k < 16; ++k) f[k] = lrelu(f[k]);
+          for (int k = 0; k < NV; ++k) f[k] = lrelu(f[k]);
         }
-        const bool packed_act = p.lrelu && !has_res;   // the usual case: activate the packed result, 1 op per value
         if (has_res) {
           const uint4 r0 = *reinterpret_cast<const uint4*>(io + c0);
-          const uint4 r1 = *reinterpret_cast<const uint4*>(io + c1);
+          uint4 r1 = z;
+          if constexpr (NV == 16) r1 = *reinterpret_cast<const uint4*>(io + c1);
           const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
+          for (int k = 0; k < NV / 2; ++k) {
             uint32_t lo, hi;
             unpack_f32x2(add_f32x2(f32x2(f[2 * k], f[2 * k + 1]),
                                    f32x2(__uint_as_float(rw[k] << 16), __uint_as_float(rw[k] & 0xffff0000u))), lo, hi);
@@ -569,12 +596,17 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
             f[2 * k + 1] = __uint_as_float(hi);
           }
         }
-        // pad columns hold don't-care values (the store clips them); the pad row is stored and must stay zero
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        uint4 o0 = pack8(&f[0]), o1 = pack8(&f[8]);
-        if (packed_act) {
-          o0 = lrelu_bf16x8(o0);
-          o1 = lrelu_bf16x8(o1);
+        uint4 o0, o1 = z;
+        if constexpr (NV == 16) {
+          o0 = pack8(&f[0]);
+          o1 = pack8(&f[8]);
+          if (packed_act) {
+            o0 = lrelu_bf16x8(o0);
+            o1 = lrelu_bf16x8(o1);
+          }
+        } else {
+          o0 = make_uint4(pack_bf16(f[0], f[1]), 0u, 0u, 0u);
+          if (packed_act) o0.x = lrelu_bf16x2(o0.x);
         }
         if constexpr (STEM) {
           if (half == 1 && cb == 1) {  // channels 50..53 = words 1, 2 of this block: the raw planes, untouched by the activation
@@ -589,16 +621,24 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
           const uint64_t* s22 = reinterpret_cast<const uint64_t*>(s_s2 + col0 + cb * 16);
           const uint64_t* t22 = reinterpret_cast<const uint64_t*>(s_t2 + col0 + cb * 16);
 #pragma unroll
-          for (int k = 0; k < 16; k += 2) {
+          for (int k = 0; k < NV; k += 2) {
             uint32_t lo, hi;
             unpack_f32x2(fma_f32x2(s22[k >> 1], f32x2(f[k], f[k + 1]), t22[k >> 1]), lo, hi);
             g[k] = __uint_as_float(lo);
             g[k + 1] = __uint_as_float(hi);
           }
-          *reinterpret_cast<uint4*>(o2 + c0) = pad_row ? z : lrelu_bf16x8(pack8(&g[0]));
-          *reinterpret_cast<uint4*>(o2 + c1) = pad_row ? z : lrelu_bf16x8(pack8(&g[8]));
+          if constexpr (NV == 16) {
+            *reinterpret_cast<uint4*>(o2 + c0) = pad_row ? z : lrelu_bf16x8(pack8(&g[0]));
+            *reinterpret_cast<uint4*>(o2 + c1) = pad_row ? z : lrelu_bf16x8(pack8(&g[8]));
+          } else {
+            *reinterpret_cast<uint4*>(o2 + c0) = pad_row ? z : make_uint4(lrelu_bf16x2(pack_bf16(g[0], g[1])), 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(o2 + c1) = z;
+          }
         }
-      }
+      };
+      finish(std::integral_constant<int, 16>{}, 0);
+      if (short_blk) finish(std::integral_constant<int, 2>{}, 1);
+      else finish(std::integral_constant<int, 16>{}, 1);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
@@ -692,6 +732,235 @@ k_head(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __
       if (2 * t + 1 == A) values[bb] = tanhf(l1);
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// FC head for LARGE action spaces (fc1 of network.py:48,60-64 with A + 1 = 433 / 769 outputs: Breakthrough 6x6 / 8x8):
+// logits[b][n] = sum_k X[b][k] * Wfc[n][k] + bias[n] is a real GEMM, M = boards, K = H*W*64, N = A + 1, so it runs on the
+// tensor cores: A operand = the last activation tensor viewed as [boards][(H+1)*W*64] (only the first K columns, i.e. the
+// board cells, are read; the zero pad row is skipped), B operand = the bf16 weight rows [A+1][(H+1)*W*64], both K-major
+// through SWIZZLE_128B TMA boxes of 64 k; tcgen05.mma M128 x N=NC x K16 into one TMEM accumulator; 4-stage smem ring.
+// A CTA owns one (128-board tile, NC-column chunk) of the logits.  Its epilogue adds the bias, writes the raw fp32 logits of
+// the action columns into `priors`, tanh of column A into `values`, and (max, sum exp) of its chunk into `stats`.  The LAST
+// chunk-CTA of a board tile to finish (device counter) turns the tile's logits into the softmax in place:
+// p = exp(l - M) / S with M, S combined from the chunk statistics -- softmax over ALL A actions like the reference
+// (network.py:62, no legal-move masking), fp32 logits, one kernel.
+//   warp 0: TMA producer    warp 1: TMEM alloc + MMA issuer    warps 2-5: epilogue (one TMEM lane quarter each)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+struct HeadMmaParams {
+  const float* bias;   // [A + 1]
+  float* priors;       // [boards][A]
+  float* values;       // [boards]
+  float2* stats;       // [boards][n_chunks]: (max, sum exp(l - max)) over the action columns of the chunk
+  int* counters;       // [board tiles]: chunk-CTAs finished (self-resetting)
+  int boards, A, n_chunks, NC, KB;   // NC = columns per chunk (multiple of 16, <= 256), KB = K / 64
+};
+
+constexpr int HM_STAGES = 4;
+constexpr int HM_THREADS = 192;
+constexpr int HM_A_BYTES = TILE_M * 128;  // one k-block of the A operand: 128 rows x 64 bf16
+
+__global__ void __launch_bounds__(HM_THREADS, 1)
+k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const HeadMmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = (int)blockIdx.x % p.n_chunks, mtile = (int)blockIdx.x / p.n_chunks;   // chunks of a tile run side by side
+  const uint32_t b_bytes = (uint32_t)p.NC * 128u;
+  const uint32_t stage_bytes = (uint32_t)HM_A_BYTES + b_bytes;
+  const uint32_t s_base = smem_u32(smem);
+  uint8_t* tail = smem + HM_STAGES * stage_bytes;
+  float* s_bias = reinterpret_cast<float*>(tail);                 // [256]
+  const uint32_t s_bar = smem_u32(tail + 1024);
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(tail + 1024 + 128);
+  volatile int* s_last = reinterpret_cast<volatile int*>(tail + 1024 + 132);
+  auto bar_full = [&](int s) { return s_bar + 8u * s; };
+  auto bar_empty = [&](int s) { return s_bar + 8u * (HM_STAGES + s); };
+  const uint32_t bar_tfull = s_bar + 8u * (2 * HM_STAGES);
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.NC) tmem_cols <<= 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < HM_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 256; i += HM_THREADS) {
+    const int n = chunk * p.NC + i;
+    s_bias[i] = (i < p.NC && n <= p.A) ? p.bias[n] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const int stage = kb % HM_STAGES;
+        mbar_wait(bar_empty(stage), ((uint32_t)(kb / HM_STAGES) & 1u) ^ 1u);
+        mbar_expect_tx(bar_full(stage), stage_bytes);
+        const uint32_t dst = s_base + (uint32_t)stage * stage_bytes;
+        // boards past the end of the batch and weight rows past A + 1 are out of range: they arrive as zeros
+        tma_load_2d(dst, &tm_x, kb * 64, mtile * TILE_M, bar_full(stage));
+        tma_load_2d(dst + HM_A_BYTES, &tm_w, kb * 64, chunk * p.NC, bar_full(stage));
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)p.NC);
+    for (int kb = 0; kb < p.KB; ++kb) {
+      const int stage = kb % HM_STAGES;
+      mbar_wait(bar_full(stage), (uint32_t)(kb / HM_STAGES) & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a0 = s_base + (uint32_t)stage * stage_bytes;
+        const uint64_t ad = umma_desc_sw128(a0), bd = umma_desc_sw128(a0 + HM_A_BYTES);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(tmem_base, ad + (uint64_t)(j * 2), bd + (uint64_t)(j * 2), idesc, (kb | j) != 0 ? 1u : 0u);
+        umma_commit(bar_empty(stage));
+        if (kb == p.KB - 1) umma_commit(bar_tfull);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== epilogue: one TMEM lane quarter (32 boards) per warp ===========================
+    const int q = warp & 3;
+    const int board = mtile * TILE_M + q * 32 + lane;
+    const bool live = board < p.boards;
+    const int n0 = chunk * p.NC;
+    float* prow = p.priors + (size_t)(live ? board : 0) * p.A;
+    const bool vec_ok = (p.A & 3) == 0;
+    mbar_wait(bar_tfull, 0u);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float mx = -3.0e38f;
+    for (int c0 = 0; c0 < p.NC; c0 += 16) {   // pass 1: logits out, row maximum
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      tmem_ld_wait();
+      float x[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        x[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+        if (n0 + c0 + j < p.A) mx = fmaxf(mx, x[j]);
+      }
+      if (live) {
+        if (vec_ok && n0 + c0 + 16 <= p.A) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(prow + n0 + c0 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < p.A) prow[n] = x[j];
+            else if (n == p.A) p.values[board] = tanhf(x[j]);   // network.py:63
+          }
+        }
+      }
+    }
+    float se = 0.f;
+    for (int c0 = 0; c0 < p.NC; c0 += 16) {   // pass 2: sum exp(l - max) (TMEM reads are cheap)
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n0 + c0 + j < p.A) se += __expf(__uint_as_float(v[j]) + s_bias[c0 + j] - mx);
+    }
+    if (live) p.stats[(size_t)board * p.n_chunks + chunk] = make_float2(mx, se);
+    tc_fence_before();
+    __threadfence();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane == 0) {
+      const int done = atomicAdd(p.counters + mtile, 1);
+      *s_last = done == p.n_chunks - 1;
+      if (done == p.n_chunks - 1) p.counters[mtile] = 0;   // ready for the next launch (graph replay)
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (*s_last) {
+      // ---- softmax over all A actions of the 128 boards of this tile (network.py:62), in place.  Each lane combines the
+      // chunk statistics of one of its warp's 32 boards; the element-wise pass then runs over the 32 x A block as one flat,
+      // fully coalesced index space with several independent loads in flight per lane (the logits sit in L2).
+      __threadfence();
+      const int base = mtile * TILE_M + q * 32;
+      const int nrows = min(32, p.boards - base);
+      float M_l = -3.0e38f, S_l = 0.f;
+      if (lane < nrows) {
+        const float2* st = p.stats + (size_t)(base + lane) * p.n_chunks;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const float2 v = __ldcg(st + c);
+          if (v.y > 0.f) {
+            const float Mn = fmaxf(M_l, v.x);
+            S_l = S_l * __expf(M_l - Mn) + v.y * __expf(v.x - Mn);
+            M_l = Mn;
+          }
+        }
+      }
+      const float inv_l = S_l > 0.f ? 1.f / S_l : 0.f;
+      if (nrows > 0) {
+        float* blk = p.priors + (size_t)base * p.A;
+        constexpr int UN = 4;
+        if (vec_ok) {
+          const int a4 = p.A >> 2, total = nrows * a4;
+          for (int i0 = 0; i0 < total; i0 += 32 * UN) {
+            float4 l[UN];
+            int row[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+              const int idx = i0 + u * 32 + lane;
+              row[u] = idx < total ? idx / a4 : 0;
+              l[u] = idx < total ? __ldcg(reinterpret_cast<const float4*>(blk) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+              const int idx = i0 + u * 32 + lane;
+              const float M = __shfl_sync(0xffffffffu, M_l, row[u]), inv = __shfl_sync(0xffffffffu, inv_l, row[u]);
+              if (idx < total)
+                reinterpret_cast<float4*>(blk)[idx] = make_float4(__expf(l[u].x - M) * inv, __expf(l[u].y - M) * inv,
+                                                                  __expf(l[u].z - M) * inv, __expf(l[u].w - M) * inv);
+            }
+          }
+        } else {
+          const int total = nrows * p.A;
+          for (int i0 = 0; i0 < total; i0 += 32 * UN) {
+            float l[UN];
+            int row[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+              const int idx = i0 + u * 32 + lane;
+              row[u] = idx < total ? idx / p.A : 0;
+              l[u] = idx < total ? __ldcg(blk + idx) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+              const int idx = i0 + u * 32 + lane;
+              const float M = __shfl_sync(0xffffffffu, M_l, row[u]), inv = __shfl_sync(0xffffffffu, inv_l, row[u]);
+              if (idx < total) blk[idx] = __expf(l[u] - M) * inv;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
 }  // namespace aznn
@@ -878,5 +1147,101 @@ extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float
                                                              chunks, (H + 1) * W * CH / 8, (int)n_actions);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_head launch", e);
+  return 0;
+}
+
+// ---- FC head for large action spaces ----
+static PFN_tmapEncodeTiled tmap_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess) fn = (PFN_tmapEncodeTiled)f;
+  }
+  return fn;
+}
+
+// 2-D K-major bf16 operand [rows][row_elems] read through (64 k, box_rows) SWIZZLE_128B boxes over the first k_elems columns
+static int make_tmap_kmajor(CUtensorMap* m, const void* base, long long rows, long long row_elems, long long k_elems, int box_rows) {
+  PFN_tmapEncodeTiled fn = tmap_encode_fn();
+  if (!fn) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "cuTensorMapEncodeTiled unavailable");
+    return -2;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)k_elems, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)row_elems * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t est[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "cuTensorMapEncodeTiled (2-D) failed (%d)", (int)r);
+    return -2;
+  }
+  return 0;
+}
+
+// chunking of the N = A + 1 output columns: as few chunks as the 256-column MMA limit allows when the board tiles alone fill
+// the GPU, more (down to 64 columns) when the batch is small
+static void head_chunks(int boards, int n_actions, int* n_chunks, int* nc) {
+  const int n_tot = n_actions + 1, tiles = (boards + aznn::TILE_M - 1) / aznn::TILE_M;
+  int chunks = (n_tot + 255) / 256;
+  const int max_chunks = (n_tot + 63) / 64;
+  while (chunks < max_chunks && tiles * chunks < 148) ++chunks;
+  int w = ((n_tot + chunks - 1) / chunks + 15) / 16 * 16;
+  if (w > 256) w = 256;
+  *n_chunks = (n_tot + w - 1) / w;
+  *nc = w;
+}
+
+extern "C" int64_t az_nn_head_large_scratch_bytes(int32_t boards, int32_t n_actions) {
+  if (boards <= 0 || n_actions <= 0) return -1;
+  int chunks, nc;
+  head_chunks(boards, n_actions, &chunks, &nc);
+  const int tiles = (boards + aznn::TILE_M - 1) / aznn::TILE_M;
+  return (int64_t)boards * chunks * 8 + (((int64_t)tiles * 4 + 7) & ~(int64_t)7);
+}
+
+extern "C" int az_nn_head_large(const void* x, const void* w, const float* bias, float* priors, float* values, void* scratch,
+                                int32_t boards, int32_t H, int32_t W, int32_t n_actions, void* stream) {
+  using namespace aznn;
+  if (!x || !w || !bias || !priors || !values || !scratch) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head_large: null argument");
+    return -1;
+  }
+  if (boards <= 0 || H < 3 || H > 16 || W < 2 || W > 8 || n_actions < 1) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_head_large: needs boards > 0, 3 <= H <= 16, 2 <= W <= 8, n_actions >= 1");
+    return -1;
+  }
+  int chunks, nc;
+  head_chunks(boards, n_actions, &chunks, &nc);
+  const int tiles = (boards + TILE_M - 1) / TILE_M;
+  const long long row_elems = (long long)(H + 1) * W * CH, k_elems = (long long)H * W * CH;
+  HeadMmaParams p;
+  p.bias = bias;
+  p.priors = priors;
+  p.values = values;
+  p.counters = reinterpret_cast<int*>(scratch);                        // [tiles] first (zeroed once by the caller)
+  p.stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + (((size_t)tiles * 4 + 7) & ~(size_t)7));
+  p.boards = boards;
+  p.A = n_actions;
+  p.n_chunks = chunks;
+  p.NC = nc;
+  p.KB = (int)(k_elems / 64);
+  CUtensorMap tm_x, tm_w;
+  if (make_tmap_kmajor(&tm_x, x, boards, row_elems, k_elems, TILE_M)) return -2;
+  if (make_tmap_kmajor(&tm_w, w, n_actions + 1, row_elems, k_elems, nc)) return -2;
+  const size_t smem = (size_t)HM_STAGES * (HM_A_BYTES + (size_t)nc * 128) + 1024 + 256;
+  static size_t smem_set[64] = {0};  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (smem > smem_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_head_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute(k_head_mma)", e);
+    smem_set[dev & 63] = smem;
+  }
+  k_head_mma<<<tiles * chunks, HM_THREADS, smem, (cudaStream_t)stream>>>(tm_x, tm_w, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return nn_fail(-2, "k_head_mma launch", e);
   return 0;
 }

@@ -5,8 +5,8 @@ fp32 [B] -- but the ten 3x3 convolutions run as tcgen05 implicit GEMMs with Batc
 fused into their epilogues (11 launches instead of ~45 PyTorch kernels), on NHWC bf16 activations [B,H+1,W,64] (row H
 of every board is a zero pad row)
 (see az_resnet.cu).  Host code here only folds/packs weights and sequences the launches.  The FC head is the streaming
-k_head kernel (FC + softmax + tanh in one launch, fp32 logits) when A + 1 <= 8 (Connect Four); for larger action spaces
-it is a plain [B, (H+1)*W*64] x [(H+1)*W*64, A+1] GEMM and stays a cuBLAS call through torch, with softmax/tanh on its output.
+k_head kernel (FC + softmax + tanh in one launch, fp32 logits) when A + 1 <= 8 (Connect Four) and the tcgen05 GEMM head
+k_head_mma (same fusion, N = A + 1 = 433 / 769 columns) for the larger action spaces of Breakthrough.
 
 Per evaluation:   stem(obs) -> U (channels 50-53: the raw planes)
                   X = conv(U) [+ conv1x1(obs) through those channels], T = lrelu(bn1_2(X))      (block 1, conv2)
@@ -26,17 +26,23 @@ CH = 64
 SKIP_CH = 50   # first of the four spare channels that carry the raw observation planes out of the stem
 
 
+N_PACK = 160   # MMA N dimension of az_nn_conv3x3: 3 kx taps x 50 filters, padded to a multiple of 16
+
+
 def pack_conv3x3(w):
-    """[64 out][64 in][3][3] (any float dtype, already zero-padded) -> bf16 [3 ky][192 = kx*64 + n][8 chunks][8]: the UMMA
-    B operand image of az_nn_conv3x3, SWIZZLE_128B K-major: row (kx, n) is the 128 B of input channels, its 16-byte chunk
-    c is stored at chunk position c ^ (n & 7)."""
+    """[64 out][64 in][3][3] (any float dtype; only the first 50 output channels are used -- the conv computes the
+    network's 50 filters, network.py:22 -- all 64 input channels are) -> bf16 [3 ky][160][8 chunks][8]: the UMMA B operand
+    image of az_nn_conv3x3, SWIZZLE_128B K-major.  Row r = kx*50 + co holds the 128 B of input channels of output channel
+    co under tap (ky, kx) (rows 150..159 are zero); its 16-byte chunk c is stored at chunk position c ^ (r & 7)."""
     co, ci = w.shape[0], w.shape[1]
     assert co == CH and ci == CH
-    t = w.permute(2, 3, 0, 1).reshape(3, 3 * co, 8, 8)       # [ky][kx*64 + n][chunk][k%8]
-    n = torch.arange(3 * co).view(1, 3 * co, 1)
+    t = torch.zeros((3, N_PACK, 8, 8), dtype=w.dtype, device=w.device)
+    # [ky][kx][co < 50][ci] -> rows kx*50 + co
+    t[:, :3 * N_FILTERS] = w[:N_FILTERS].permute(2, 3, 0, 1).reshape(3, 3 * N_FILTERS, 8, 8)
+    r = torch.arange(N_PACK).view(1, N_PACK, 1)
     c = torch.arange(8).view(1, 1, 8)
-    src_chunk = (c ^ (n & 7)).expand(3, 3 * co, 8)           # position p holds chunk p ^ (n & 7)
-    out = torch.gather(t, 2, src_chunk.unsqueeze(-1).expand(3, 3 * co, 8, 8).to(t.device))
+    src_chunk = (c ^ (r & 7)).expand(3, N_PACK, 8)           # position p holds chunk p ^ (r & 7)
+    out = torch.gather(t, 2, src_chunk.unsqueeze(-1).expand(3, N_PACK, 8, 8).to(t.device))
     return out.contiguous().to(torch.bfloat16)
 
 
@@ -59,9 +65,15 @@ class FusedEvaluator:
         self.priors = torch.zeros((batch, self.A), dtype=torch.float32, device=dev)
         self.values = torch.zeros((batch,), dtype=torch.float32, device=dev)
         self.par = None
-        # small action spaces (Connect Four) finish with the streaming k_head kernel; larger ones with a cuBLAS GEMM
-        self.fused_head = self.A + 1 <= 8 and 8 * (self.h * self.w * 8 + 4) * 16 <= 100 * 1024 and \
-            os.environ.get("AZ_NN_HEAD", "1") != "0"
+        # FC head: small action spaces (Connect Four) finish with the streaming k_head kernel, larger ones (Breakthrough)
+        # with the tcgen05 GEMM head k_head_mma -- both FC + softmax + tanh in ONE launch of our own kernels.
+        # (AZ_NN_HEAD=0: cuBLAS + torch softmax/tanh, kept only as a numerics cross-check.)
+        self.small_head = self.A + 1 <= 8 and 8 * (self.h * self.w * 8 + 4) * 16 <= 100 * 1024
+        self.fused_head = os.environ.get("AZ_NN_HEAD", "1") != "0"
+        self.head_scratch = None
+        if self.fused_head and not self.small_head:
+            n = int(self.lib.az_nn_head_large_scratch_bytes(batch, self.A))
+            self.head_scratch = torch.zeros((n + 3) // 4, dtype=torch.int32, device=dev)
         self.timing = None   # set to a list to collect (kernel, start_event, end_event) per launch (bench.py roofline)
         self.load(net)
 
@@ -120,7 +132,7 @@ class FusedEvaluator:
         fwp[:, :self.h, :, :N_FILTERS] = fw.permute(0, 2, 3, 1)
         new["fw"] = fwp.reshape(self.A + 1, -1).to(torch.bfloat16)
         new["fb"] = net.fc1.bias.double().cpu().float()
-        if self.fused_head:   # k_head operand: [8 outputs][H*W*64] bf16 (unused outputs zero), bias [8]
+        if self.fused_head and self.small_head:   # k_head operand: [8 outputs][H*W*64] bf16 (unused outputs zero), bias [8]
             hw = torch.zeros((8, self.h * self.w * CH), dtype=torch.float64)
             hw[:self.A + 1] = fwp[:, :self.h].reshape(self.A + 1, -1)
             hb = torch.zeros(8, dtype=torch.float64)
@@ -174,12 +186,18 @@ class FusedEvaluator:
             self._conv(self.U, P_["w2_%d" % k], P_["b2_%d" % k], self.X, self.X, None if last else self.T,
                        None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False,
                        flags=L.NN_F_REVERSE)
-        if self.fused_head:
+        if self.fused_head and self.small_head:
             rc = self._timed("head", lambda: self.lib.az_nn_head(
                 p(self.X), p(P_["hw"]), p(P_["hb"]), p(self.priors), p(self.values), self.batch, self.h, self.w, self.A,
                 self.n_ctas, self._stream()))
             if rc:
                 raise RuntimeError("az_nn_head: " + self.lib.az_nn_last_error().decode())
+        elif self.fused_head:
+            rc = self._timed("head", lambda: self.lib.az_nn_head_large(
+                p(self.X), p(P_["fw"]), p(P_["fb"]), p(self.priors), p(self.values), p(self.head_scratch), self.batch,
+                self.h, self.w, self.A, self._stream()))
+            if rc:
+                raise RuntimeError("az_nn_head_large: " + self.lib.az_nn_last_error().decode())
         else:
             out = F.linear(self.X.view(self.batch, -1), P_["fw"]).float() + P_["fb"]
             torch.softmax(out[:, :self.A], dim=1, out=self.priors)

@@ -246,10 +246,12 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  * 2 <= W <= 8.
  *
  * az_nn_conv3x3: out = conv3x3(in) + bias, optional LeakyReLU, optional + res; optional second output
- *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  wpack is bf16 [3 ky][192 = kx*64 + n][8][8]:
- *   per kernel row the three kx taps side by side, each row n = 64 input channels (128 B) in the SWIZZLE_128B K-major UMMA
- *   image (16-byte chunk c stored at position c ^ (n & 7)).  tcgen05 implicit GEMM, 12 MMAs of M128 N192 K16 per 128-row
- *   tile; n_ctas <= 0 -> one CTA per SM.  res may alias out (in-place residual stream).  flags: AZ_NN_F_*.
+ *   out2 = LeakyReLU(s2*out + t2) (the next block's BatchNorm, network.py:100).  The conv computes the network's 50 filters
+ *   (network.py:22) from all 64 input channels; channels 50..63 of out / out2 are written as zeros.
+ *   wpack is bf16 [3 ky][160][8][8]: per kernel row the three kx taps side by side without padding, row r = kx*50 + co =
+ *   the 64 input channels (128 B) of output channel co, rows 150..159 zero, in the SWIZZLE_128B K-major UMMA image (16-byte
+ *   chunk c stored at position c ^ (r & 7)).  tcgen05 implicit GEMM, 12 MMAs of M128 N160 K16 per 128-row tile, three
+ *   TMEM accumulator stages; n_ctas <= 0 -> one CTA per SM.  res may alias out (in-place residual stream).  flags: AZ_NN_F_*.
  * az_nn_stem: the first conv of resblock1 on the 4 observation planes, slab built from the az_step AZ_OBS_BF16_NHWC batch
  *   [boards][H][W][4]: u[0..49] = LeakyReLU(conv1(LeakyReLU(s*x+t)) + b1) (network.py:99-100) and u[50..53] = x, the raw
  *   planes: the block's 1x1 skip projection (resblock1.conv3, network.py:101-103) is then four extra input channels of the
@@ -268,6 +270,15 @@ int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float*
                int32_t W, int32_t n_ctas, void* stream);
 int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t boards, int32_t H,
                int32_t W, int32_t n_actions, int32_t n_ctas, void* stream);
+/* az_nn_head_large: the same FC head (fc1 + softmax over ALL n_actions + tanh, network.py:48,60-64) for large action spaces
+ *   (Breakthrough: 433 / 769 outputs) as a tcgen05 GEMM: M = boards, K = H*W*64 (the board cells of x; the pad row is
+ *   skipped), N = n_actions + 1, fp32 accumulation and fp32 logits.  w is bf16 [n_actions + 1][(H+1)*W*64] (row n = the
+ *   weights of output n in the NHWC cell order of x, zero on pad channels; the last (H+1)-th row group is never read),
+ *   bias fp32 [n_actions + 1].  scratch: az_nn_head_large_scratch_bytes(boards, n_actions) bytes of device memory, zeroed
+ *   once by the caller before the first use (chunk statistics + self-resetting tile counters). */
+int64_t az_nn_head_large_scratch_bytes(int32_t boards, int32_t n_actions);
+int az_nn_head_large(const void* x, const void* w, const float* bias, float* priors, float* values, void* scratch,
+                     int32_t boards, int32_t H, int32_t W, int32_t n_actions, void* stream);
 
 #ifdef __cplusplus
 }

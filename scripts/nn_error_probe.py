@@ -33,4 +33,35 @@ out["c4_pins"] = pins("connect_four", [3, 6, 7], 7, "example_model_connect_four.
 z = np.load(os.path.join(G, "bt6_pins.npz"))
 out["bt6_pins"] = pins("breakthrough(rows=6,columns=6)", [3, 6, 6], 432, "example_model_breakthrough_6x6.pth",
                        [[int(a) for a in h if a >= 0] for h in z["histories"]], z["p"], z["v"])
+
+
+def random_init(game):
+    """The construction of tests/test_gpu_nn.py::test_fused_evaluator_matches_fp32_reference."""
+    from oracle import ref_net
+    shape, A = E.game_shape(game)
+    torch.manual_seed(11)
+    ref = ref_net.RefNet(shape, A).eval()
+    with torch.no_grad():
+        for m in ref.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.uniform_(-0.3, 0.3)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    net = Net(shape, A).eval()
+    net.load_state_dict(ref.state_dict())
+    B = 1000
+    hist, lens = E.game_random_playouts(game, B, seed=5, max_plies=24)
+    x32 = E.game_replay_dev(game, hist, lens, L.OBS_F32_NCHW)["obs"]
+    xbf = E.game_replay_dev(game, hist, lens, L.OBS_BF16_NHWC)["obs"]
+    with torch.no_grad():
+        p_ref, v_ref = ref(x32.cpu())
+    p, v = FusedEvaluator(net, B, "cuda:0").eval_batch(xbf)
+    p, v = p.cpu(), v.cpu()
+    return {"max_dp": float((p - p_ref).abs().max()), "max_dv": float((v - v_ref[:, 0]).abs().max()),
+            "argmax_agree": float((p.argmax(1) == p_ref.argmax(1)).float().mean())}
+
+
+for game in ["connect_four", "breakthrough(rows=6,columns=6)", "breakthrough"]:
+    out["random_init/" + game] = random_init(game)
 print(json.dumps(out))

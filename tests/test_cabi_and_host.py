@@ -195,13 +195,15 @@ def test_boards_from_bitboards_breakthrough():
 
 
 def test_conv_weight_image_layout():
-    """pack_conv3x3: [ky][kx*64 + n][chunk position][8] with chunk c of row n stored at position c ^ (n & 7) (the
-    SWIZZLE_128B K-major image the conv kernel bulk-copies into shared memory); pure host code."""
+    """pack_conv3x3: [ky][kx*50 + co][chunk position][8] (160 rows, 150 used) with chunk c of row r stored at position
+    c ^ (r & 7) (the SWIZZLE_128B K-major image the conv kernel bulk-copies into shared memory); pure host code."""
     import torch
     from alphazero_openspiel_b200.nn_fused import pack_conv3x3
     w = torch.arange(64 * 64 * 9, dtype=torch.float32).reshape(64, 64, 3, 3) % 251   # bf16-exact small integers
     img = pack_conv3x3(w).float()
-    assert tuple(img.shape) == (3, 192, 8, 8)
-    for ky, kx, n, c in [(0, 0, 0, 0), (1, 2, 5, 3), (2, 1, 63, 7), (0, 2, 17, 6)]:
-        got = img[ky, kx * 64 + n, c ^ (n & 7)]
-        assert torch.equal(got, w[n, c * 8:c * 8 + 8, ky, kx])
+    assert tuple(img.shape) == (3, 160, 8, 8)
+    for ky, kx, co, c in [(0, 0, 0, 0), (1, 2, 5, 3), (2, 1, 49, 7), (0, 2, 17, 6), (2, 2, 49, 0)]:
+        r = kx * 50 + co
+        got = img[ky, r, c ^ (r & 7)]
+        assert torch.equal(got, w[co, c * 8:c * 8 + 8, ky, kx])
+    assert float(img[:, 150:].abs().max()) == 0.0      # padding rows of the N dimension

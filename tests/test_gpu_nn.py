@@ -33,6 +33,8 @@ def test_conv3x3_tcgen05_matches_torch(H, W, B):
     x = torch.randn((B, 64, H, W), generator=g).to(dev).to(torch.bfloat16).float()
     w = (torch.randn((64, 64, 3, 3), generator=g) * 0.05).to(dev).to(torch.bfloat16).float()
     bias = torch.randn((64,), generator=g).to(dev)
+    w[50:] = 0.0       # the conv computes the network's 50 filters from all 64 input channels;
+    bias[50:] = 0.0    # output channels 50..63 are written as zeros (whatever the residual holds there)
     res = torch.randn((B, 64, H, W), generator=g).to(dev).to(torch.bfloat16).float()
     s2 = (torch.rand((64,), generator=g) + 0.5).to(dev)
     t2 = torch.randn((64,), generator=g).to(dev)
@@ -54,6 +56,8 @@ def test_conv3x3_tcgen05_matches_torch(H, W, B):
             want = F.leaky_relu(want)
         if use_res:
             want = want + res
+        want = want.clone()
+        want[:, 50:] = 0.0
         got = out[:, :H].float().permute(0, 3, 1, 2)
         assert float(out[:, H].float().abs().max()) == 0.0   # the pad row is (re)written as zeros
         err = (got - want).abs()
@@ -61,6 +65,7 @@ def test_conv3x3_tcgen05_matches_torch(H, W, B):
         assert bool((err <= tol).all()), (lrelu, use_res, float(err.max()))
         if use_out2:
             want2 = F.leaky_relu(want * s2.view(1, -1, 1, 1) + t2.view(1, -1, 1, 1))
+            want2[:, 50:] = 0.0
             err2 = (out2[:, :H].float().permute(0, 3, 1, 2) - want2).abs()
             assert float(out2[:, H].float().abs().max()) == 0.0
             assert bool((err2 <= 2.0 ** -6 * want2.abs() + 4e-2).all()), float(err2.max())
@@ -98,21 +103,28 @@ def test_fused_evaluator_matches_fp32_reference(game):
     p, v = p.cpu(), v.cpu()
     assert torch.isfinite(p).all() and torch.isfinite(v).all()
     assert (p.sum(1) - 1).abs().max().item() < 1e-3
-    assert (p - p_ref).abs().max().item() < 3e-2
-    assert (v - v_ref[:, 0]).abs().max().item() < 6e-2
-    assert (p.argmax(1) == p_ref.argmax(1)).float().mean().item() > 0.9
+    # bf16 bounds = 2x the maxima observed on B200 (scripts/nn_error_probe.py, r02: |dp| 8.5e-4 / 2.9e-5 / 1.8e-5,
+    # |dv| 3.6e-3 / 5.9e-3 / 4.2e-3 for Connect Four / Breakthrough 6x6 / 8x8; priors of the large action spaces are ~1/A)
+    tol_p, tol_v = {"connect_four": (1.7e-3, 7.2e-3), "breakthrough(rows=6,columns=6)": (6e-5, 1.2e-2),
+                    "breakthrough": (3.6e-5, 8.5e-3)}[game]
+    assert (p - p_ref).abs().max().item() < tol_p
+    assert (v - v_ref[:, 0]).abs().max().item() < tol_v
+    assert (p.argmax(1) == p_ref.argmax(1)).float().mean().item() > 0.97
     pe, ve = BatchedEvaluator(net, B, "cuda:0").eval_batch(xbf)
-    assert (p - pe.cpu()).abs().max().item() < 3e-2 and (v - ve.cpu()).abs().max().item() < 6e-2
+    assert (p - pe.cpu()).abs().max().item() < 2 * tol_p and (v - ve.cpu()).abs().max().item() < 2 * tol_v
     # weights can be reloaded in place (new generation) and a second call is deterministic
     p2, v2 = fe.eval_batch(xbf)
     assert torch.equal(p2.cpu(), p) and torch.equal(v2.cpu(), v)
     # a differently sized batch gives the same per-board results (boards never see each other)
     p3, v3 = FusedEvaluator(net, 333, "cuda:0").eval_batch(xbf[:333])
-    # (the cuBLAS FC head of the larger games rounds its logits to bf16 and may pick a different kernel for a different
-    # row count -> differences of one bf16 ulp of the logit, 2^-8 at |logit| ~ 1; k_head is batch-independent)
-    assert (p3.cpu() - p[:333]).abs().max().item() < 2e-3 and (v3.cpu() - v[:333]).abs().max().item() < 1e-2
-    if fe.fused_head:
-        assert torch.equal(p3.cpu(), p[:333]) and torch.equal(v3.cpu(), v[:333])
+    # (both FC heads accumulate a board's logits in a fixed order that does not depend on the batch; the softmax of the
+    # large head combines per-chunk statistics whose chunk width depends on the batch size -> last-bit differences there)
+    assert fe.fused_head
+    assert torch.equal(v3.cpu(), v[:333])
+    if fe.small_head:
+        assert torch.equal(p3.cpu(), p[:333])
+    else:
+        assert (p3.cpu() - p[:333]).abs().max().item() < 1e-6
 
 
 def test_fused_evaluator_is_batch_size_independent():
@@ -153,11 +165,12 @@ def _golden_pins(which):
     return game, net, hists, p_ref, v_ref
 
 
-@pytest.mark.parametrize("which,tol_p,tol_v", [("c4", 3e-2, 6e-2), ("bt6", 3e-2, 6e-2)])
+@pytest.mark.parametrize("which,tol_p,tol_v", [("c4", 2.3e-2, 6e-2), ("bt6", 2.4e-2, 4.6e-2)])
 def test_fused_evaluator_matches_reference_net_outputs_of_shipped_checkpoints(which, tol_p, tol_v):
     """The tcgen05 evaluator with the reference's SHIPPED checkpoints on the golden positions vs the priors / values the
     unmodified reference `Net` (network.py:48-64, fp32) produced for them (tests/golden/make_golden*.py): the bf16 bound
-    is stated here and is <= 2x the maximum observed on B200 (scripts/nn_error_probe.py)."""
+    is stated here and is <= 2x the maximum observed on B200 (scripts/nn_error_probe.py, r02: Connect Four |dp| 0.0113,
+    |dv| 0.0297; Breakthrough 6x6 |dp| 0.0121, |dv| 0.0229; the trained networks are much sharper than random ones)."""
     from alphazero_openspiel_b200 import engine as E, _lib as L
     from alphazero_openspiel_b200.nn_fused import FusedEvaluator
     game, net, hists, p_ref, v_ref = _golden_pins(which)
@@ -171,3 +184,45 @@ def test_fused_evaluator_matches_reference_net_outputs_of_shipped_checkpoints(wh
     dp, dv = np.abs(p - p_ref).max(), np.abs(v - v_ref).max()
     assert dp < tol_p and dv < tol_v, (dp, dv)
     assert (p.argmax(1) == p_ref.argmax(1)).mean() >= 0.9
+
+
+@pytest.mark.parametrize("H,W,A,B", [(6, 6, 432, 1000), (8, 8, 768, 300), (6, 6, 432, 64), (8, 8, 768, 4096), (6, 7, 7, 50),
+                                     (5, 5, 300, 129), (8, 8, 768, 1), (6, 6, 432, 16384)])
+def test_large_action_space_head_matches_torch(H, W, A, B):
+    """az_nn_head_large (tcgen05 GEMM + softmax + tanh, fc1 of network.py:48,60-64): priors / values vs torch fp32 on the
+    same bf16-exact inputs.  fp32 accumulation and fp32 logits on both sides -> only summation order differs: the stated
+    bound is 1e-5 absolute + 1e-4 relative on the priors and 2e-5 on the values."""
+    import torch
+    from alphazero_openspiel_b200 import _lib as L
+    lib = L.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(H * 1000 + A + B)
+    K, KR = H * W * 64, (H + 1) * W * 64
+    x = torch.zeros((B, KR), dtype=torch.bfloat16)
+    x[:, :K] = (torch.randn((B, K), generator=g) * 0.5).to(torch.bfloat16)
+    x[:, K:] = 3.0          # the pad row is never read by the head (it is zero in the real tensors)
+    w = torch.zeros((A + 1, KR), dtype=torch.bfloat16)
+    w[:, :K] = (torch.randn((A + 1, K), generator=g) * 0.03).to(torch.bfloat16)
+    w[:, K:] = 5.0
+    bias = torch.randn((A + 1,), generator=g)
+    logits = x[:, :K].double() @ w[:, :K].double().t() + bias.double()
+    p_ref = torch.softmax(logits[:, :A], dim=1)
+    v_ref = torch.tanh(logits[:, A])
+    xd, wd, bd = x.to(dev), w.to(dev), bias.to(dev)
+    pri = torch.full((B, A), -1.0, dtype=torch.float32, device=dev)
+    val = torch.full((B,), -9.0, dtype=torch.float32, device=dev)
+    n = int(lib.az_nn_head_large_scratch_bytes(B, A))
+    scratch = torch.zeros((n + 3) // 4, dtype=torch.int32, device=dev)
+    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    for rep in range(2):   # the second call checks that the tile counters reset themselves
+        pri.fill_(-1.0)
+        rc = lib.az_nn_head_large(ptr(xd), ptr(wd), ptr(bd), ptr(pri), ptr(val), ptr(scratch), B, H, W, A,
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, lib.az_nn_last_error()
+        torch.cuda.synchronize()
+        p, v = pri.cpu().double(), val.cpu().double()
+        assert torch.isfinite(p).all() and (p >= 0).all()
+        assert (p.sum(1) - 1).abs().max().item() < 1e-5
+        err = (p - p_ref).abs()
+        assert bool((err <= 1e-5 + 1e-4 * p_ref).all()), float(err.max())
+        assert (v - v_ref).abs().max().item() < 2e-5
