@@ -11,8 +11,9 @@ F_RECORDS, F_OFFPOLICY, F_PRIORS_F64, F_RANDOM_START = 1 << 4, 1 << 5, 1 << 6, 1
 F_ASYNC_COMPACT = 1 << 8
 F_EAGER_COMPACT = 1 << 9
 F_UCT = 1 << 10
+F_VIRTUAL_LOSS = 1 << 11
 NOISE_NONE, NOISE_DIRICHLET, NOISE_HOST, NOISE_COUNTER = 0, 1, 2, 3
-EVAL_EXTERNAL, EVAL_UNIFORM, EVAL_HASH = 0, 1, 2
+EVAL_EXTERNAL, EVAL_UNIFORM, EVAL_HASH, EVAL_ROLLOUT = 0, 1, 2, 3
 OBS_NONE, OBS_F32_NCHW, OBS_BF16_NHWC = 0, 1, 2
 PH_IDLE, PH_ROOT_EVAL, PH_LEAF_EVAL, PH_SEARCH_DONE, PH_RUN, PH_ERROR = 0, 1, 2, 3, 4, 5
 CTR_NAMES = ["sims", "depth", "children", "expansions", "legal", "terminal", "root_evals", "moves", "games",
@@ -28,7 +29,7 @@ class AzConfig(C.Structure):
         ("num_probabilistic_actions", C.c_int32), ("noise_mode", C.c_int32), ("eval_mode", C.c_int32),
         ("eval_shift", C.c_int32), ("max_sims_per_step", C.c_int32), ("start_plies_mod", C.c_int32),
         ("record_capacity", C.c_int32), ("max_games", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
-        ("seed", C.c_uint64),
+        ("seed", C.c_uint64), ("leaves_per_tree", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -62,6 +62,12 @@ struct __align__(16) TreeHdr {
 };
 static_assert(sizeof(TreeHdr) == 80, "TreeHdr size");
 
+// one in-flight evaluator request of a tree in virtual-loss mode (AZ_F_VIRTUAL_LOSS)
+struct __align__(16) VlPend {
+  uint64_t b0, b1;
+  int32_t node, depth, ply, valid;
+};
+
 struct Node;
 struct Params {
   TreeHdr* hdr;
@@ -74,6 +80,8 @@ struct Params {
   int* compact_list;   // trees waiting for re-root compaction (k_compact work list)
   int* compact_count;  // [0] = entries, [1] = CTAs done
   long long* dbg;      // optional [n_trees][4]: cycles, phase in, sims this step, flags (az_debug_timing)
+  VlPend* vl_pend;     // AZ_F_VIRTUAL_LOSS: [n_trees][vl_k] in-flight requests
+  int vl_k;            // leaves in flight per tree (evaluator rows per tree); 1 in the exact mode
   const double* logtab;  // AZ_F_UCT: log(n) for n < LOGTAB_N, computed on the host with the C library's log() -- the same
                          // function CPython's math.log calls, so the UCT scores are bit-equal to the reference's
   long long rec_cap;
@@ -160,13 +168,31 @@ __device__ __forceinline__ double eval_prior(const Params& p, const StepIO& io, 
     return (p.flags & AZ_F_PRIORS_F64) ? ((const double*)io.priors)[idx] : (double)((const float*)io.priors)[idx];
   }
   if (p.eval_mode == AZ_EVAL_UNIFORM) return 1.0 / (double)p.geo.n_actions;
+  if (p.eval_mode == AZ_EVAL_ROLLOUT) return 1.0;   // np.ones(num_distinct_actions), mcts.py:222
   const uint64_t ha = mix64(ek.k + (uint64_t)(a + 1) * 0xD1B54A32D192ED03ULL);
   return (double)(1 + (int)((ha >> 40) & 0x3FF)) * exp2((double)-(10 + p.eval_shift));
 }
-__device__ __forceinline__ double eval_value(const Params& p, const StepIO& io, int tree, const EvalKey& ek) {
+// MCTS.random_rollout (mcts.py:205-223) on the device: one uniformly random playout from the position, scored for the player
+// to move there.  The move stream is a pure function of (seed, position): r_j = mix64(key + (j+1) * golden), pick = r_j % L
+// (oracle: oz_synth_eval kind 2), so the batched engine, the oracle and repeated runs agree bit for bit.
+template <class GM>
+__device__ double rollout_value(const Params& p, St s, const EvalKey& ek) {
+  const int mover = s.ply & 1;
+  for (uint64_t j = 0;; ++j) {
+    const int out = GM::outcome(s, p.geo);
+    if (out >= 0) return out == 2 ? 0.0 : (out == mover ? 1.0 : -1.0);
+    const typename GM::Legal lg = GM::legal(s, p.geo);
+    const int n = GM::count(lg);
+    const uint64_t r = mix64(ek.k + (j + 1) * 0x9E3779B97F4A7C15ULL);
+    s = GM::apply(s, p.geo, GM::action_of(lg, s, p.geo, (int)(r % (uint64_t)n)));
+  }
+}
+template <class GM>
+__device__ __forceinline__ double eval_value(const Params& p, const StepIO& io, int tree, const EvalKey& ek, const St& s) {
   if (p.eval_mode == AZ_EVAL_EXTERNAL)
     return (p.flags & AZ_F_PRIORS_F64) ? ((const double*)io.values)[tree] : (double)((const float*)io.values)[tree];
   if (p.eval_mode == AZ_EVAL_UNIFORM) return 0.0;
+  if (p.eval_mode == AZ_EVAL_ROLLOUT) return rollout_value<GM>(p, s, ek);
   return (double)((int)((ek.k >> 20) & 31) - 16) / 16.0;
 }
 
@@ -700,7 +726,7 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
         h.err = 1;
         if (lane == 0) ctr_add(s_ctr, AZ_CTR_OVERFLOW, 1);
       }
-      const double v = eval_value(p, io, tree, eval_key(p, s));
+      const double v = eval_value<GM>(p, io, tree, eval_key(p, s), s);
       // node.update_recursive(-leaf_value)   mcts.py:152
       backup_path<G>(a, gpath, h.pend_depth, -v, lane);
       __syncwarp(gm);
@@ -820,6 +846,10 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
         // terminal leaf: leaf_value = -player_return(mover); update_recursive(-leaf_value)   mcts.py:148-152
         backup_path<G>(a, spath, depth, mover_return(out, s.ply), lane);
         __syncwarp(gm);
+        if (p.flags & AZ_F_MANUAL) {  // MCTS.playout(state) leaves `state` at the leaf: keep the path for az_request_info
+          for (int j = lane; j <= depth; j += G) gpath[j] = spath[j];
+          h.pend_depth = depth;
+        }
         h.sims_done += 1;
         c_sims += 1;
         c_depth += depth;
@@ -846,6 +876,212 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
         p.dbg[4 * tree + 2] = sims_this_step;
         p.dbg[4 * tree + 3] = t_consume * 2 + (advanced ? 1 : 0);
       }
+      atomicMax(&s_ctr[AZ_CTR_PEAK_NODES], (unsigned long long)h.alloc);
+      ctr_add(s_ctr, AZ_CTR_SIMS, c_sims);
+      ctr_add(s_ctr, AZ_CTR_DEPTH, c_depth);
+      ctr_add(s_ctr, AZ_CTR_CHILDREN, c_children);
+      ctr_add(s_ctr, AZ_CTR_EXPANSIONS, c_exp);
+      ctr_add(s_ctr, AZ_CTR_LEGAL, c_legal);
+      ctr_add(s_ctr, AZ_CTR_TERMINAL, c_term);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < AZ_CTR_COUNT && s_ctr[threadIdx.x]) {
+    if (threadIdx.x == AZ_CTR_PEAK_NODES) atomicMax(&p.ctr[threadIdx.x], s_ctr[threadIdx.x]);
+    else atomicAdd(&p.ctr[threadIdx.x], s_ctr[threadIdx.x]);
+  }
+}
+
+// ---------------------------------------------------------------- virtual-loss step kernel (AZ_F_VIRTUAL_LOSS)
+// Throughput mode for SMALL pools (BASELINE configs[1]: 1,024 games cannot fill the evaluator with one row per tree): every
+// tree keeps up to K leaves in flight, so the evaluator batch is n_trees * K rows (row = tree * K + slot).  The reference has
+// no such mode (mcts.py:177-179 runs its playouts strictly one after the other); this is the usual virtual-loss scheme and is
+// NOT bit-exact with the reference: while a leaf is in flight every node on its path carries one extra visit with value -1
+// (Q <- (N*Q - 1)/(N + 1), N <- N + 1), which steers the following descents of the same step elsewhere; the real backup
+// replaces that visit (Q <- (N*Q + 1 + v)/N).  A leaf that is already in flight ends the collection for this step (its
+// link carries the marker 0xFFFFFF00).  Everything else -- PUCT arithmetic, expansion, terminal leaves, root noise, move
+// choice, records, re-rooting -- is the code of the exact kernel.  K = 1 through this kernel is still not the exact path.
+constexpr unsigned VL_MARK = 0xFFFFFF00u;
+
+template <int G>
+__device__ __forceinline__ void vl_apply(const Arena& a, const int32_t* path, int depth, int lane) {
+  for (int j = lane; j <= depth; j += G) {
+    const int node = path[j];
+    const uint2 nl = a.nl(node);
+    a.q(node) = ((double)nl.x * a.q(node) - 1.0) / (double)(nl.x + 1u);
+    a.nl(node).x = nl.x + 1u;
+  }
+}
+// real backup of a simulation whose path carries a virtual loss: the visit is already counted
+template <int G>
+__device__ __forceinline__ void vl_backup(const Arena& a, const int32_t* path, int depth, double v_leaf, int lane) {
+  for (int j = lane; j <= depth; j += G) {
+    const int node = path[j];
+    const double v = ((depth - j) & 1) ? -v_leaf : v_leaf;
+    const uint2 nl = a.nl(node);
+    a.q(node) = ((double)nl.x * a.q(node) + 1.0 + v) / (double)nl.x;
+  }
+}
+
+template <class GM>
+__global__ void __launch_bounds__(BLOCK, 4) k_step_vl(const Params p, const StepIO io) {
+  constexpr int G = GM::G;
+  __shared__ int32_t s_path[BLOCK / G][GM::MAXD];
+  __shared__ unsigned long long s_ctr[AZ_CTR_COUNT];
+  if (threadIdx.x < AZ_CTR_COUNT) s_ctr[threadIdx.x] = 0ULL;
+  __syncthreads();
+  const int tree = (int)((blockIdx.x * (unsigned)BLOCK + threadIdx.x) / G);
+  const int lane = threadIdx.x % G;
+  if (tree < p.n_trees) {
+    const unsigned gm = group_mask<G>();
+    const int K = p.vl_k;
+    int32_t* spath = s_path[threadIdx.x / G];
+    int32_t* gpaths = p.path + (size_t)tree * K * GM::MAXD;
+    VlPend* pend = p.vl_pend + (size_t)tree * K;
+    const int row0 = tree * K;
+    TreeHdr h = p.hdr[tree];
+    unsigned long long c_sims = 0, c_depth = 0, c_children = 0, c_exp = 0, c_legal = 0, c_term = 0;
+
+    // ---------------- 1. consume the evaluator rows of the requests in flight
+    if (h.phase == AZ_PH_LEAF_EVAL) {
+      const Arena a = arena_of(p, tree, h.half);
+      for (int slot = 0; slot < K; ++slot) {
+        const VlPend pe = pend[slot];
+        if (!pe.valid) continue;
+        St s;
+        s.b0 = pe.b0;
+        s.b1 = pe.b1;
+        s.ply = pe.ply;
+        if (lane == 0) a.nl(pe.node).y = 0u;   // drop the in-flight marker: expand_node sees a childless node
+        __syncwarp(gm);
+        int L = 0;
+        const bool ok = expand_node<GM, G>(p, io, a, h, row0 + slot, pe.node, s, lane, gm, false, nullptr, &L);
+        if (!ok) {
+          h.err = 1;
+          if (lane == 0) ctr_add(s_ctr, AZ_CTR_OVERFLOW, 1);
+        }
+        const double v = eval_value<GM>(p, io, row0 + slot, eval_key(p, s), s);
+        vl_backup<G>(a, gpaths + (size_t)slot * GM::MAXD, pe.depth, -v, lane);
+        __syncwarp(gm);
+        if (lane == 0) pend[slot].valid = 0;
+        h.sims_done += 1;
+        c_sims += 1;
+        c_depth += pe.depth;
+        c_exp += 1;
+        c_legal += L;
+      }
+      h.phase = AZ_PH_RUN;
+    } else if (h.phase == AZ_PH_ROOT_EVAL) {
+      const Arena a = arena_of(p, tree, h.half);
+      St s;
+      s.b0 = h.root_b0;
+      s.b1 = h.root_b1;
+      s.ply = h.root_ply;
+      const typename GM::Legal lg = GM::legal(s, p.geo);
+      const int L = GM::count(lg);
+      double eta[GM::SLOTS];
+      double sum = 0.0;
+#pragma unroll
+      for (int sl = 0; sl < GM::SLOTS; ++sl) {
+        const int i = lane + sl * G;
+        eta[sl] = 0.0;
+        if (p.noise_mode == AZ_NOISE_DIRICHLET && i < L) eta[sl] = gamma_draw(p.alpha, p.seed, tree, h.game_seq, s.ply, i);
+        else if (p.noise_mode == AZ_NOISE_HOST && i < L) eta[sl] = io.noise[(size_t)tree * GM::MAXC + i];
+        else if (p.noise_mode == AZ_NOISE_COUNTER && i < L)
+          eta[sl] = (double)((counter(p.seed, tree, h.game_seq, s.ply, i, 1) >> 11) + 1ULL) * (1.0 / 9007199254740992.0);
+        sum += eta[sl];
+      }
+      if (p.noise_mode != AZ_NOISE_HOST) {
+        sum = gsumd<G>(gm, sum);
+#pragma unroll
+        for (int sl = 0; sl < GM::SLOTS; ++sl) eta[sl] = sum > 0.0 ? eta[sl] / sum : 1.0 / (double)L;
+      }
+      int L2 = 0;
+      const bool ok = expand_node<GM, G>(p, io, a, h, row0, h.root_node, s, lane, gm, true, eta, &L2);
+      if (!ok) {
+        h.err = 1;
+        if (lane == 0) ctr_add(s_ctr, AZ_CTR_OVERFLOW, 1);
+      }
+      h.phase = AZ_PH_RUN;
+      if (lane == 0) ctr_add(s_ctr, AZ_CTR_ROOT_EVALS, 1);
+    }
+
+    // ---------------- 2. collect up to K new leaves
+    int n_pending = 0, sims_this_step = 0;
+    bool advanced = false;
+    for (;;) {
+      if (h.phase == PH_BEGIN) {
+        h.sims_done = 0;
+        if (p.noise_mode != AZ_NOISE_NONE) {
+          St s;
+          s.b0 = h.root_b0;
+          s.b1 = h.root_b1;
+          s.ply = h.root_ply;
+          h.phase = AZ_PH_ROOT_EVAL;
+          write_obs<GM, G>(p, io, row0, lane, s);
+          n_pending = 1;   // (one evaluator row in use; not a leaf request)
+          break;
+        }
+        h.phase = AZ_PH_RUN;
+      }
+      if (h.phase != AZ_PH_RUN) break;
+      if (h.sims_done + n_pending >= p.n_playouts) {
+        if (n_pending > 0 || advanced) break;
+        finish_move<GM, G>(p, h, tree, lane, gm, s_ctr);
+        advanced = true;
+        continue;
+      }
+      if (n_pending >= K) break;
+      if (p.max_sims > 0 && sims_this_step >= p.max_sims + K) break;
+      const Arena a = arena_of(p, tree, h.half);
+      St s;
+      s.b0 = h.root_b0;
+      s.b1 = h.root_b1;
+      s.ply = h.root_ply;
+      int node, depth;
+      bool dovf = false;
+      sim_select<GM, G, false>(p, a, h.root_node, s, node, depth, spath, lane, gm, c_children, dovf, false);
+      if (dovf) {
+        h.err = 1;
+        h.phase = AZ_PH_ERROR;
+        if (lane == 0) ctr_add(s_ctr, AZ_CTR_OVERFLOW, 1);
+        break;
+      }
+      const int out = depth > 0 ? GM::outcome(s, p.geo) : -1;
+      ++sims_this_step;
+      if (out >= 0) {   // terminal leaf: real backup at once, no virtual loss needed
+        backup_path<G>(a, spath, depth, mover_return(out, s.ply), lane);
+        __syncwarp(gm);
+        h.sims_done += 1;
+        c_sims += 1;
+        c_depth += depth;
+        c_term += 1;
+        continue;
+      }
+      if (a.nl(node).y == VL_MARK) break;   // this leaf is already in flight: stop collecting for this step
+      const int slot = n_pending++;
+      if (lane == 0) {
+        VlPend pe;
+        pe.b0 = s.b0;
+        pe.b1 = s.b1;
+        pe.node = node;
+        pe.depth = depth;
+        pe.ply = s.ply;
+        pe.valid = 1;
+        pend[slot] = pe;
+        a.nl(node).y = VL_MARK;
+      }
+      int32_t* gp = gpaths + (size_t)slot * GM::MAXD;
+      for (int j = lane; j <= depth; j += G) gp[j] = spath[j];
+      __syncwarp(gm);
+      vl_apply<G>(a, spath, depth, lane);
+      __syncwarp(gm);
+      write_obs<GM, G>(p, io, row0 + slot, lane, s);
+    }
+    if (h.phase == AZ_PH_RUN && n_pending > 0) h.phase = AZ_PH_LEAF_EVAL;
+    if (lane == 0) {
+      p.hdr[tree] = h;
+      ctr_add(s_ctr, AZ_CTR_IDLE_SLOTS, (unsigned long long)(K - n_pending));
       atomicMax(&s_ctr[AZ_CTR_PEAK_NODES], (unsigned long long)h.alloc);
       ctr_add(s_ctr, AZ_CTR_SIMS, c_sims);
       ctr_add(s_ctr, AZ_CTR_DEPTH, c_depth);
@@ -1030,8 +1266,14 @@ __global__ void k_command(const Params p, const int32_t* upd, const int32_t* rst
       dirty = true;
     }
     if (beg && beg[tree]) {
-      h.phase = PH_BEGIN;
-      h.sims_done = 0;
+      if (beg[tree] == 2) {  // MCTS.playout (mcts.py:126-153): ONE simulation, no root Dirichlet expansion
+        h.phase = AZ_PH_RUN;
+        h.sims_done = p.n_playouts - 1;
+        h.pend_depth = 0;
+      } else {
+        h.phase = PH_BEGIN;
+        h.sims_done = 0;
+      }
       dirty = true;
     }
     if (dirty && lane == 0) p.hdr[tree] = h;
@@ -1073,7 +1315,8 @@ __global__ void k_request_info(const Params p, uint64_t* bb, int32_t* ply, int32
     bb[2 * tree + 1] = pending ? h.pend_b1 : 0;
   }
   if (ply) ply[tree] = pending ? h.pend_ply : -1;
-  const int depth = h.phase == AZ_PH_LEAF_EVAL ? h.pend_depth : (pending ? 0 : -1);
+  const bool last_path = (p.flags & AZ_F_MANUAL) && h.phase == AZ_PH_SEARCH_DONE;   // path of the last simulation
+  const int depth = (h.phase == AZ_PH_LEAF_EVAL || last_path) ? h.pend_depth : (pending ? 0 : -1);
   if (depth_out) depth_out[tree] = depth;
   if (path_actions && depth > 0) {
     const Arena a = arena_of(p, tree, h.half);
@@ -1316,7 +1559,7 @@ int az_create(const az_config* cfg_in, az_engine** out) {
   if (cfg.noise_weight == 0.0) cfg.noise_weight = 0.25;
   if (cfg.num_probabilistic_actions <= 0) cfg.num_probabilistic_actions = 1000;
   if (cfg.noise_mode < 0 || cfg.noise_mode > 3) return fail(-1, "bad noise_mode");
-  if (cfg.eval_mode < 0 || cfg.eval_mode > 2) return fail(-1, "bad eval_mode");
+  if (cfg.eval_mode < 0 || cfg.eval_mode > 3) return fail(-1, "bad eval_mode");
   const int maxc = cfg.game_id == AZ_GAME_CONNECT_FOUR ? C4::MAXC : BT::MAXC;
   const int maxd = cfg.game_id == AZ_GAME_CONNECT_FOUR ? C4::MAXD : BT::MAXD;
   const int group = cfg.game_id == AZ_GAME_CONNECT_FOUR ? C4::G : BT::G;
@@ -1330,6 +1573,10 @@ int az_create(const az_config* cfg_in, az_engine** out) {
     cfg.node_capacity = (int)c;
   }
   if (cfg.node_capacity >= (1 << 24)) return fail(-1, "node_capacity must be < 2^24");
+  if (cfg.leaves_per_tree <= 0 || !(cfg.flags & AZ_F_VIRTUAL_LOSS)) cfg.leaves_per_tree = 1;
+  if (cfg.leaves_per_tree > 64) return fail(-1, "leaves_per_tree must be <= 64");
+  if ((cfg.flags & AZ_F_VIRTUAL_LOSS) && (cfg.flags & (AZ_F_MANUAL | AZ_F_UCT)))
+    return fail(-1, "AZ_F_VIRTUAL_LOSS is a batched self-play mode (no AZ_F_MANUAL / AZ_F_UCT)");
   if (cfg.record_capacity <= 0) cfg.record_capacity = cfg.n_trees * 64 < (1 << 20) ? (1 << 20) : cfg.n_trees * 64;
   if (!(cfg.flags & AZ_F_RECORDS)) cfg.record_capacity = 1;
 
@@ -1366,6 +1613,7 @@ int az_create(const az_config* cfg_in, az_engine** out) {
   p.rec_stride = (int)((sizeof(az_record) + 6 * (size_t)maxc + 7) / 8 * 8);
   p.max_games = cfg.max_games;
   p.rec_cap = cfg.record_capacity;
+  p.vl_k = cfg.leaves_per_tree;
 
   const size_t nodes = (size_t)cfg.n_trees * 2 * (size_t)cfg.node_capacity;
   size_t bytes = 0;
@@ -1376,7 +1624,8 @@ int az_create(const az_config* cfg_in, az_engine** out) {
   cudaError_t err = cudaSuccess;
   if ((err = alloc((void**)&p.hdr, sizeof(TreeHdr) * (size_t)cfg.n_trees)) != cudaSuccess ||
       (err = alloc((void**)&p.nodes, sizeof(Node) * nodes)) != cudaSuccess ||
-      (err = alloc((void**)&p.path, sizeof(int32_t) * (size_t)cfg.n_trees * maxd)) != cudaSuccess ||
+      (err = alloc((void**)&p.path, sizeof(int32_t) * (size_t)cfg.n_trees * maxd * (size_t)cfg.leaves_per_tree)) != cudaSuccess ||
+      (err = alloc((void**)&p.vl_pend, sizeof(VlPend) * (size_t)cfg.n_trees * (size_t)cfg.leaves_per_tree)) != cudaSuccess ||
       (err = alloc((void**)&p.rec, (size_t)p.rec_stride * (size_t)p.rec_cap)) != cudaSuccess ||
       (err = alloc((void**)&p.rec_count, sizeof(unsigned long long))) != cudaSuccess ||
       (err = alloc((void**)&p.ctr, sizeof(unsigned long long) * AZ_CTR_COUNT)) != cudaSuccess ||
@@ -1406,6 +1655,7 @@ int az_create(const az_config* cfg_in, az_engine** out) {
   CK(cudaMemset(p.ctr, 0, sizeof(unsigned long long) * AZ_CTR_COUNT));
   CK(cudaMemset(e->d_bad, 0, sizeof(int32_t)));
   CK(cudaMemset(p.compact_count, 0, sizeof(int) * 2));
+  CK(cudaMemset(p.vl_pend, 0, sizeof(VlPend) * (size_t)cfg.n_trees * (size_t)cfg.leaves_per_tree));
   *out = e;
   int rc = az_reset(e, nullptr);
   if (rc) return rc;
@@ -1419,6 +1669,7 @@ int az_destroy(az_engine* e) {
   cudaFree(p.hdr);
   cudaFree(p.nodes);
   cudaFree(p.path);
+  cudaFree(p.vl_pend);
   cudaFree(p.rec);
   cudaFree(p.rec_count);
   cudaFree(p.ctr);
@@ -1533,7 +1784,8 @@ int az_step(az_engine* e, const void* priors_dev, const void* values_dev, const 
   }
   dispatch_game(e->cfg.game_id, [&](auto gm) {
     using GM = decltype(gm);
-    if (p.flags & AZ_F_UCT) k_step<GM, true><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
+    if (p.flags & AZ_F_VIRTUAL_LOSS) k_step_vl<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
+    else if (p.flags & AZ_F_UCT) k_step<GM, true><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
     else k_step<GM, false><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
     return 0;
   });

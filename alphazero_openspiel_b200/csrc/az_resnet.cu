@@ -187,6 +187,7 @@ struct Conv8Params {
   const float* stem_st;    // STEM: device [8]: bn1 scale[4], shift[4] of the input planes
   int n_tiles, boards, P, H, W, HP;  // HP = H + 1 row groups per board
   int lrelu, has_res, has_out2, debug, reverse;
+  uint32_t hp_magic;       // ceil(2^32 / HP): g / HP == __umulhi(g, hp_magic) for the group indices that occur (< 2^24)
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -241,7 +242,9 @@ struct Conv8Smem {
   static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
-template <bool STEM, int NE, int S>
+// MODE: bit 0 = LeakyReLU on the result, bit 1 = residual input, bit 2 = second output -- compile-time, so that the
+// epilogue of each layer kind is straight-line code (the runtime flags cost ~25 branch instructions per work item)
+template <bool STEM, int NE, int S, int MODE>
 __global__ void __launch_bounds__(((STEM ? 5 : 2) + NE) * 32, 1)
 k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_res,
         const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2, const Conv8Params p) {
@@ -345,7 +348,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
           bool ok = row < STEM_SLAB && g >= 0 && c < p.W;
           int cell = 0;
           if (ok) {
-            const int b = g / p.HP, r = g - b * p.HP;
+            const int b = (int)__umulhi((uint32_t)g, p.hp_magic), r = g - b * p.HP;
             ok = b < p.boards && r < p.H;
             cell = b * cells + r * p.W + c;
           }
@@ -454,14 +457,14 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       const int et = e * 32 + lane;
       if (et < CH) {
         s_bias[et] = p.bias[et];
-        s_s2[et] = (p.has_out2 && p.s2) ? p.s2[et] : 0.f;
-        s_t2[et] = (p.has_out2 && p.t2) ? p.t2[et] : 0.f;
+        s_s2[et] = ((MODE & 4) && p.s2) ? p.s2[et] : 0.f;
+        s_t2[et] = ((MODE & 4) && p.t2) ? p.t2[et] : 0.f;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(NE * 32) : "memory");
     }
     uint8_t* stg = smem + L::STG_OFF + e * L::STG_WARP;
     const uint32_t stg_u32 = smem_u32(stg);
-    const bool has_res = p.has_res != 0, has_out2 = p.has_out2 != 0;
+    constexpr bool has_res = (MODE & 2) != 0, has_out2 = (MODE & 4) != 0, do_lrelu = (MODE & 1) != 0;
     const int cells = p.H * p.W;
     const int n_items = my_tiles * 2;
     // this thread's row inside a 32-row x 64-byte SWIZZLE_64B box: chunk c lives at chunk position c ^ ((row >> 1) & 3)
@@ -477,7 +480,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     // the projection costs nothing but four weight rows
     auto obs_of = [&](int i) -> uint2 {
       const int g = tile_of(i >> 1) * 16 + q * 4 + (lane >> 3);
-      const int b = g / p.HP, r = g - b * p.HP;
+      const int b = (int)__umulhi((uint32_t)g, p.hp_magic), r = g - b * p.HP;
       if (b < p.boards && r < p.H && cc < p.W) return p.stem_obs[(long long)b * cells + r * p.W + cc];
       return make_uint2(0u, 0u);
     };
@@ -497,7 +500,8 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       const int col0 = half * 32;
       const uint2 xrow = xnext;
       const int g0 = tile_of(it) * 16 + q * 4;                   // first row group of this quarter
-      const bool pad_row = (g0 + (lane >> 3)) % p.HP == p.H;      // this thread's row lies in a board's zero pad row
+      const int grp = g0 + (lane >> 3);
+      const bool pad_row = grp - (int)__umulhi((uint32_t)grp, p.hp_magic) * p.HP == p.H;   // this thread's row lies in a board's zero pad row
       mbar_wait(bar_tfull(acc), (uint32_t)(it / ACC) & 1u);
       tc_fence_after();
       // Channels of this item: half 0 = 0..31; half 1 = 32..49 (18 real filters; 50..63 are written as zeros, the stem
@@ -562,7 +566,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       if (has_res) mbar_wait(bar_res(e, b), (uint32_t)(n >> 1) & 1u);
       uint8_t* io = stg + b * 2048 + row_off;
       uint8_t* o2 = stg + 4096 + row_off;
-      const bool packed_act = p.lrelu && !has_res;   // the usual case: activate the packed result, 1 op per value
+      constexpr bool packed_act = do_lrelu && !has_res;   // the usual case: activate the packed result, 1 op per value
       // pad columns hold don't-care values (the store clips them); the pad row is stored and must stay zero
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
       // one 16-channel block (two 16-byte chunks of this thread's staging row) with NV live values
@@ -578,7 +582,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
           f[k] = __uint_as_float(lo);
           f[k + 1] = __uint_as_float(hi);
         }
-        if (p.lrelu && has_res) {  // (activation before a residual add: keep it in fp32)
+        if (do_lrelu && has_res) {  // (activation before a residual add: keep it in fp32)
 #pragma unroll
           for (int k = 0; k < NV; ++k) f[k] = lrelu(f[k]);
         }
@@ -761,6 +765,7 @@ struct HeadMmaParams {
   float2* stats;       // [boards][n_chunks]: (max, sum exp(l - max)) over the action columns of the chunk
   int* counters;       // [board tiles]: chunk-CTAs finished (self-resetting)
   int boards, A, n_chunks, NC, KB;   // NC = columns per chunk (multiple of 16, <= 256), KB = K / 64
+  int debug;                         // AZ_NN_HEAD_DEBUG experiments: 1 = no softmax pass, 2 = no epilogue at all, 4 = no MMAs
 };
 
 constexpr int HM_STAGES = 4;
@@ -830,8 +835,10 @@ k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       if (elect_one()) {
         const uint32_t a0 = s_base + (uint32_t)stage * stage_bytes;
         const uint64_t ad = umma_desc_sw128(a0), bd = umma_desc_sw128(a0 + HM_A_BYTES);
+        if (!(p.debug & 4)) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(tmem_base, ad + (uint64_t)(j * 2), bd + (uint64_t)(j * 2), idesc, (kb | j) != 0 ? 1u : 0u);
+          for (int j = 0; j < 4; ++j) umma_bf16(tmem_base, ad + (uint64_t)(j * 2), bd + (uint64_t)(j * 2), idesc, (kb | j) != 0 ? 1u : 0u);
+        }
         umma_commit(bar_empty(stage));
         if (kb == p.KB - 1) umma_commit(bar_tfull);
       }
@@ -849,7 +856,7 @@ k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     float mx = -3.0e38f;
-    for (int c0 = 0; c0 < p.NC; c0 += 16) {   // pass 1: logits out, row maximum
+    for (int c0 = 0; c0 < ((p.debug & 2) ? 0 : p.NC); c0 += 16) {   // pass 1: logits out, row maximum
       uint32_t v[16];
       tmem_ld16(taddr + (uint32_t)c0, v);
       tmem_ld_wait();
@@ -875,7 +882,7 @@ k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       }
     }
     float se = 0.f;
-    for (int c0 = 0; c0 < p.NC; c0 += 16) {   // pass 2: sum exp(l - max) (TMEM reads are cheap)
+    for (int c0 = 0; c0 < ((p.debug & 2) ? 0 : p.NC); c0 += 16) {   // pass 2: sum exp(l - max) (TMEM reads are cheap)
       uint32_t v[16];
       tmem_ld16(taddr + (uint32_t)c0, v);
       tmem_ld_wait();
@@ -893,7 +900,7 @@ k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       if (done == p.n_chunks - 1) p.counters[mtile] = 0;   // ready for the next launch (graph replay)
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (*s_last) {
+    if (*s_last && !(p.debug & 3)) {
       // ---- softmax over all A actions of the 128 boards of this tile (network.py:62), in place.  Each lane combines the
       // chunk statistics of one of its warp's 32 boards; the element-wise pass then runs over the 32 x A block as one flat,
       // fully coalesced index space with several independent loads in flight per lane (the logits sit in L2).
@@ -1012,7 +1019,7 @@ static int make_tmap_act(CUtensorMap* m, const void* base, int boards, int H, in
   return 0;
 }
 
-template <bool STEM, int NE, int S>
+template <bool STEM, int NE, int S, int MODE>
 static int launch_conv8(const CUtensorMap& tm_in, const CUtensorMap& tm_res, const CUtensorMap& tm_out, const CUtensorMap& tm_out2,
                         const aznn::Conv8Params& p, int n_ctas, void* stream) {
   using namespace aznn;
@@ -1022,7 +1029,7 @@ static int launch_conv8(const CUtensorMap& tm_in, const CUtensorMap& tm_res, con
   int dev = 0;
   cudaGetDevice(&dev);
   if (!((attr_set >> (dev & 63)) & 1ULL)) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv8<STEM, NE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(k_conv8<STEM, NE, S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute", e);
     attr_set |= 1ULL << (dev & 63);
   }
@@ -1039,7 +1046,7 @@ static int launch_conv8(const CUtensorMap& tm_in, const CUtensorMap& tm_res, con
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = env_int("AZ_NN_PDL", 1) ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv8<STEM, NE, S>, tm_in, tm_res, tm_out, tm_out2, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_conv8<STEM, NE, S, MODE>, tm_in, tm_res, tm_out, tm_out2, p);
   if (e != cudaSuccess) return nn_fail(-2, "k_conv8 launch", e);
   e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_conv8 launch", e);
@@ -1082,8 +1089,24 @@ extern "C" int az_nn_conv3x3(const void* in, const void* wpack, const float* bia
   if (make_tmap_act(&tm_out2, out2 ? out2 : out, boards, H, W, 32, 4, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
   static int ne = -1;
   if (ne < 0) ne = env_int("AZ_NN_NE", 12);
-  return ne == 16 ? launch_conv8<false, 16, 3>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream)
-                  : launch_conv8<false, 12, 4>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream);
+  p.hp_magic = (uint32_t)((0x100000000ULL + (uint64_t)p.HP - 1) / (uint64_t)p.HP);
+  const int mode = (lrelu ? 1 : 0) | (p.has_res ? 2 : 0) | (p.has_out2 ? 4 : 0);
+#define AZ_CONV_CASE(M)                                                                                               \
+  case M:                                                                                                             \
+    return ne == 16 ? launch_conv8<false, 16, 3, M>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream)                \
+                    : launch_conv8<false, 12, 4, M>(tm_in, tm_res, tm_out, tm_out2, p, n_ctas, stream);
+  switch (mode) {
+    AZ_CONV_CASE(0)
+    AZ_CONV_CASE(1)
+    AZ_CONV_CASE(2)
+    AZ_CONV_CASE(3)
+    AZ_CONV_CASE(4)
+    AZ_CONV_CASE(5)
+    AZ_CONV_CASE(6)
+    AZ_CONV_CASE(7)
+  }
+#undef AZ_CONV_CASE
+  return -1;
 }
 
 extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, const float* bn_st, void* u, int32_t boards,
@@ -1113,7 +1136,8 @@ extern "C" int az_nn_stem(const void* obs, const void* wpack, const float* b1, c
   p.debug = env_int("AZ_NN_DEBUG", 0);
   CUtensorMap tm_out;
   if (make_tmap_act(&tm_out, u, boards, H, W, 32, 4, CU_TENSOR_MAP_SWIZZLE_64B)) return -2;
-  return launch_conv8<true, 12, 4>(tm_out, tm_out, tm_out, tm_out, p, n_ctas, stream);
+  p.hp_magic = (uint32_t)((0x100000000ULL + (uint64_t)p.HP - 1) / (uint64_t)p.HP);
+  return launch_conv8<true, 12, 4, 1>(tm_out, tm_out, tm_out, tm_out, p, n_ctas, stream);
 }
 
 extern "C" int az_nn_head(const void* x, const void* w, const float* bias, float* priors, float* values, int32_t boards,
@@ -1228,6 +1252,7 @@ extern "C" int az_nn_head_large(const void* x, const void* w, const float* bias,
   p.n_chunks = chunks;
   p.NC = nc;
   p.KB = (int)(k_elems / 64);
+  p.debug = env_int("AZ_NN_HEAD_DEBUG", 0);
   CUtensorMap tm_x, tm_w;
   if (make_tmap_kmajor(&tm_x, x, boards, row_elems, k_elems, TILE_M)) return -2;
   if (make_tmap_kmajor(&tm_w, w, n_actions + 1, row_elems, k_elems, nc)) return -2;

@@ -56,7 +56,7 @@ class Engine:
     def __init__(self, game_name, n_trees, n_playouts=100, c_puct=2.5, dirichlet_ratio=0.25, temperature=1.0,
                  num_probabilistic_actions=1000, noise_mode=L.NOISE_DIRICHLET, eval_mode=L.EVAL_EXTERNAL,
                  eval_shift=None, flags=L.F_KEEP_TREE, seed=0, device=0, node_capacity=0, max_sims_per_step=0,
-                 start_plies_mod=0, record_capacity=0, max_games=0):
+                 start_plies_mod=0, record_capacity=0, max_games=0, leaves_per_tree=1):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise L.EngineUnavailable("the B200 engine needs a CUDA device; there is no CPU fallback")
@@ -75,6 +75,7 @@ class Engine:
         cfg.max_sims_per_step, cfg.start_plies_mod = max_sims_per_step, start_plies_mod
         cfg.record_capacity, cfg.device, cfg.flags, cfg.seed = record_capacity, device, flags, seed
         cfg.max_games = max_games
+        cfg.leaves_per_tree = leaves_per_tree if (flags & L.F_VIRTUAL_LOSS) else 1
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(self.lib.az_create(C.byref(cfg), C.byref(h)))
@@ -84,6 +85,8 @@ class Engine:
         self.cfg = eff
         self.n_trees = n_trees
         self.flags = flags
+        self.rows_per_tree = int(eff.leaves_per_tree)        # evaluator rows per tree (1 unless AZ_F_VIRTUAL_LOSS)
+        self.n_rows = n_trees * self.rows_per_tree
         self.max_children = self.lib.az_max_children(self.h)
         self.num_actions = self.lib.az_num_actions(self.h)
         self.record_stride = self.lib.az_record_stride(self.h)
@@ -108,8 +111,8 @@ class Engine:
 
     def new_obs(self, obs_format):
         if obs_format == L.OBS_BF16_NHWC:
-            return torch.zeros((self.n_trees, self.rows, self.cols, 4), dtype=torch.bfloat16, device=self.device)
-        return torch.zeros((self.n_trees, 4, self.rows, self.cols), dtype=torch.float32, device=self.device)
+            return torch.zeros((self.n_rows, self.rows, self.cols, 4), dtype=torch.bfloat16, device=self.device)
+        return torch.zeros((self.n_rows, 4, self.rows, self.cols), dtype=torch.float32, device=self.device)
 
     # ---- C-ABI calls
     def reset(self):
@@ -124,7 +127,7 @@ class Engine:
             want = torch.float64 if (self.flags & L.F_PRIORS_F64) else torch.float32
             assert priors.dtype == want and values.dtype == want, "priors/values dtype must be %s" % want
             assert priors.is_contiguous() and values.is_contiguous()
-            assert priors.numel() == self.n_trees * self.num_actions and values.numel() == self.n_trees
+            assert priors.numel() == self.n_rows * self.num_actions and values.numel() == self.n_rows
         if noise is not None:
             assert noise.dtype == torch.float64 and noise.numel() == self.n_trees * self.max_children
         L.check(self.lib.az_step(self.h, _ptr(priors), _ptr(values), _ptr(noise), _ptr(obs), obs_format,

@@ -157,7 +157,7 @@ class SelfPlayRunner:
                  dirichlet_ratio=0.25, temperature=1.0, num_probabilistic_actions=1000, keep_search_tree=True,
                  backup="on-policy", seed=0, max_games=0, auto_restart=True, random_start_mod=0,
                  max_sims_per_step=8, records=True, use_graph=True, noise_mode=None, node_capacity=0,
-                 record_capacity=0, evaluator="fused", **_ignored):
+                 record_capacity=0, evaluator="fused", virtual_loss=0, **_ignored):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.EngineUnavailable("SelfPlayRunner needs a CUDA device; there is no CPU fallback")
@@ -176,6 +176,11 @@ class SelfPlayRunner:
             flags |= L.F_RANDOM_START
         if noise_mode is None:
             noise_mode = L.NOISE_DIRICHLET if use_dirichlet else L.NOISE_NONE
+        # virtual_loss = K > 0: K leaves in flight per tree (AZ_F_VIRTUAL_LOSS, NOT bit-exact with the reference), for pools
+        # too small to fill the evaluator with one row per tree; the evaluator batch becomes n_trees * K rows
+        leaves = int(virtual_loss) if virtual_loss and int(virtual_loss) > 0 else 1
+        if virtual_loss and int(virtual_loss) > 0:
+            flags |= L.F_VIRTUAL_LOSS
         self.backup = backup
         self.game_name = game_name
         with torch.cuda.device(self.device):
@@ -185,12 +190,13 @@ class SelfPlayRunner:
                                  eval_mode=L.EVAL_EXTERNAL, flags=flags, seed=seed, device=dev_index,
                                  max_sims_per_step=max_sims_per_step, start_plies_mod=random_start_mod,
                                  max_games=max_games, node_capacity=node_capacity,
-                                 record_capacity=record_capacity)
+                                 record_capacity=record_capacity, leaves_per_tree=leaves)
+            n_rows = self.engine.n_rows
             if evaluator == "fused":      # hand-written tcgen05 convs (csrc/az_resnet.cu)
                 from .nn_fused import FusedEvaluator
-                self.evaluator = FusedEvaluator(net, n_trees, self.device)
+                self.evaluator = FusedEvaluator(net, n_rows, self.device)
             elif evaluator == "torch":    # cuDNN/cuBLAS through PyTorch (numerics reference for the fused path)
-                self.evaluator = BatchedEvaluator(net, n_trees, self.device, use_graph=False)
+                self.evaluator = BatchedEvaluator(net, n_rows, self.device, use_graph=False)
             else:
                 raise ValueError("evaluator must be 'fused' or 'torch'")
         self.use_graph = use_graph
@@ -270,9 +276,9 @@ class SelfPlayRunner:
 
 class ExampleGenerator:
     def __init__(self, net, game_name, device, n_pools=1, n_processes=1, **kwargs):
-        self.is_test = bool(kwargs.get("is_test", False))
-        if self.is_test:
-            raise NotImplementedError("generate_tests (evaluation harness) is out of scope: SURVEY 8(f).2")
+        self.is_test = bool(kwargs.pop("is_test", False))          # examplegenerator.py:93: a generator for generate_tests
+        self.generate_statistics = bool(kwargs.pop("generate_statistics", False))
+        self.net2 = None                                            # second network of zero-vs-zero (tournament.py:44-48)
         self.n_pools = n_pools            # accepted for signature parity; the GPU batch replaces pools/processes
         self.n_processes = n_processes
         self.net = copy.deepcopy(net)     # weights are frozen for the whole call (examplegenerator.py:86-87)
@@ -320,6 +326,41 @@ class ExampleGenerator:
         self.last_stats = stats
         logger.info("Generated " + str(batch.n_games) + " games")
         return batch
+
+    def generate_tests(self, n_games, game_fn, n_playouts_mcts):
+        """examplegenerator.py:177-195: n_games PAIRS of evaluation games (each `game_fn` call of the reference plays one game
+        with either side moving first) -> average reward in [-1, 1], (avg, statistics) with generate_statistics.  `game_fn`
+        is one of the reference's match-up functions (game_utils.py:51-145) or its name; all pairs run at once on the GPU
+        (evaluate.py).  kwargs follow the reference: c_puct / n_playouts / temperature for the AlphaZero side of
+        test_zero_vs_mcts (tournament.py:24 puts n_playouts into kwargs["settings1"]), settings1 / settings2 for
+        test_zero_vs_zero, `net2` attribute for a second network.  Per-move tree statistics are not collected: the
+        statistics list is empty."""
+        from . import evaluate
+        name = game_fn if isinstance(game_fn, str) else getattr(game_fn, "__name__", str(game_fn))
+        kw = dict(self.kwargs)
+        s1 = dict(kw.get("settings1") or {})
+        s2 = dict(kw.get("settings2") or {})
+        zero = {k: kw[k] for k in ("c_puct", "n_playouts", "temperature", "keep_search_tree", "use_probabilistic_actions")
+                if k in kw}
+        seed = int(kw.get("seed", np.random.randint(0, 2 ** 31 - 1)))
+        dev = self.device
+        if name == "test_zero_vs_mcts":
+            zero.update(s1)
+            a, b = evaluate.zero_vs_mcts(self.net, self.game_name, n_games, n_playouts_mcts, device=dev, seed=seed, **zero)
+        elif name == "test_net_vs_mcts":
+            a, b = evaluate.net_vs_mcts(self.net, self.game_name, n_games, n_playouts_mcts, device=dev, seed=seed)
+        elif name == "test_zero_vs_zero":
+            a, b = evaluate.zero_vs_zero(self.net, self.game_name, n_games, net2=self.net2, settings1=s1, settings2=s2,
+                                         device=dev, seed=seed)
+        elif name == "test_zero_vs_random":
+            a, b = evaluate.zero_vs_random(self.net, self.game_name, n_games, device=dev, seed=seed,
+                                           **{k: v for k, v in zero.items() if k in ("c_puct", "n_playouts", "keep_search_tree")})
+        elif name == "test_net_vs_random":
+            a, b = evaluate.net_vs_random(self.net, self.game_name, n_games, device=dev, seed=seed)
+        else:
+            raise ValueError("unknown evaluation game function %r" % (name,))
+        avg_reward = (a + b) / 2.0            # sum(score1 + score2) / (2 * n_games)
+        return (avg_reward, []) if self.generate_statistics else avg_reward
 
     def _play(self, n_games, seed_offset=0):
         kw = dict(self.kwargs)

@@ -56,3 +56,48 @@ def play_game_self(policy_fn, game_name, **kwargs):
             ex[3] = reward
             reward *= -1
     return examples
+
+
+# ---- the reference's match-up functions (game_utils.py:51-145) as names for ExampleGenerator.generate_tests(n, game_fn, m):
+# the reference passes the function objects; here they are thin single-pair entry points over the batched harness
+# (evaluate.py) with the reference's signatures: (policy_fn-or-net, max_search_nodes, game_name, **kwargs) -> (score1, score2, None)
+def _net_of(policy_fn):
+    net = getattr(policy_fn, "__self__", policy_fn)       # `net.predict` bound method or the net itself
+    if not hasattr(net, "resblock1"):
+        raise TypeError("the batched match-ups need the network (pass net or net.predict), not an arbitrary policy_fn")
+    return net
+
+
+def test_zero_vs_mcts(policy_fn, max_search_nodes, game_name, **kwargs):
+    from . import evaluate
+    s = {k: kwargs[k] for k in ("c_puct", "n_playouts", "temperature", "keep_search_tree") if k in kwargs}
+    a, b = evaluate.zero_vs_mcts(_net_of(policy_fn), game_name, 1, max_search_nodes, **s)
+    return a, b, None
+
+
+def test_net_vs_mcts(policy_fn, max_search_nodes, game_name, **kwargs):
+    from . import evaluate
+    a, b = evaluate.net_vs_mcts(_net_of(policy_fn), game_name, 1, max_search_nodes)
+    return a, b, None
+
+
+def test_net_vs_random(policy_fn, game_name, **kwargs):
+    from . import evaluate
+    return evaluate.net_vs_random(_net_of(policy_fn), game_name, 1)
+
+
+def test_zero_vs_random(policy_fn, game_name="connect_four", **kwargs):
+    from . import evaluate
+    a, b = evaluate.zero_vs_random(_net_of(policy_fn), game_name, 1)
+    return a, b, None
+
+
+def test_zero_vs_zero(policy_fn, max_search_nodes, game_name, policy_fn2=None, generate_statistics=False, **kwargs):
+    from . import evaluate
+    a, b = evaluate.zero_vs_zero(_net_of(policy_fn), game_name, 1, net2=_net_of(policy_fn2) if policy_fn2 else None,
+                                 settings1=kwargs.get("settings1"), settings2=kwargs.get("settings2"))
+    return a, b, {}
+
+
+for _f in (test_zero_vs_mcts, test_net_vs_mcts, test_net_vs_random, test_zero_vs_random, test_zero_vs_zero):
+    _f.__test__ = False     # reference API names, not pytest tests

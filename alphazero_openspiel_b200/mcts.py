@@ -127,7 +127,43 @@ class MCTS:
         return self.get_normalized_visit_counts()
 
     def playout(self, state):
-        raise NotImplementedError("single playouts are fused into search() on the device")
+        """One simulation from the current root (mcts.py:126-153): select to a leaf applying the actions to `state` IN PLACE
+        (pass a copy, as the reference asks), evaluate the leaf with policy_fn unless it is terminal, expand, back up.
+        No root Dirichlet expansion -- that belongs to search() (mcts.py:174-175).  One az_command(begin = 2) + at most
+        two az_step calls.  (`state` must be the position of the tree's root and non-terminal, as in MCTS.search.)"""
+        eng = self._engine(state)
+        self._sync_position(eng, state)
+        self._root_cache = None
+        eng.command(begin=[2])
+        have = False
+        for _ in range(4):
+            eng.step(self._priors if have else None, self._values if have else None,
+                     self._noise if self.use_dirichlet else None)
+            st = eng.status()
+            phase = int(st["phase"][0])
+            if phase == L.PH_SEARCH_DONE:
+                break
+            if phase == L.PH_ERROR:
+                raise RuntimeError("search tree overflow (node_capacity / depth)")
+            assert phase == L.PH_LEAF_EVAL, phase
+            info = eng.request_info(max_depth=192)
+            for a in info["path"][0][:max(int(info["depth"][0]), 0)]:
+                state.apply_action(int(a))                  # the caller's state walks to the leaf
+            prior_ps, leaf_value = self.policy_fn(state)     # mcts.py:146
+            self.evaluations += 1
+            pri = np.asarray(prior_ps, dtype=np.float64).reshape(-1)
+            self._priors.copy_(torch.from_numpy(pri).view(1, -1))
+            self._values.fill_(float(leaf_value))
+            have = True
+        else:
+            raise RuntimeError("playout did not finish")
+        if not have:
+            # terminal leaf (mcts.py:147-149): the engine backed it up itself; replay the path of that simulation
+            info = eng.request_info(max_depth=192)
+            for a in info["path"][0][:max(int(info["depth"][0]), 0)]:
+                state.apply_action(int(a))
+        if eng.counters()["overflow"]:
+            raise RuntimeError("search tree overflow (node_capacity)")
 
     def _stats(self):
         if self._root_cache is None:

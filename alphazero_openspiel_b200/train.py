@@ -6,8 +6,8 @@ PyTorch (MSE value loss + cross-entropy against the visit-count targets, Adam lr
 With torch.distributed initialised (one process per GPU): every rank plays its share of the games, the records are
 all-gathered, rank 0 trains and the new weights are broadcast over NCCL (parallel.broadcast_weights) -- the reference
 "broadcasts" by pickling a deepcopy of the net into every handler process (examplegenerator.py:121).
-Strength evaluation (test_agent, train.py:238-270): the matches against a uniform-random player run batched on the GPU
-(evaluate.py); the ones against OpenSpiel's MCTSBot are not reproduced.
+Strength evaluation (test_agent, train.py:238-270): all four match-ups run batched on the GPU (evaluate.py); the MCTS
+opponent is the reference's own search in UCT mode with its random-rollout evaluator, on the device.
 """
 import logging
 import time
@@ -204,9 +204,10 @@ class Trainer:
             self.n_games_buffer += self.n_games_per_generation
 
     def test_agent(self):
-        """train.py:238-270, the opponents that need no OpenSpiel bot: the network alone and the full AlphaZero bot against
-        a uniform-random player, n_tests games each way, batched on the GPU (evaluate.py).  The reference's matches against
-        OpenSpiel's MCTSBot are not reproduced."""
+        """train.py:238-270: the network alone against a uniform-random player, then -- through
+        ExampleGenerator.generate_tests -- the network alone against the 100- and 200-simulation MCTS bot and the full
+        AlphaZero bot against the 200-simulation MCTS bot, n_tests game pairs each, all batched on the GPU (evaluate.py;
+        the MCTS bot is the device UCT + random-rollout bot described there)."""
         from . import evaluate
         if parallel.rank_world()[0] != 0:
             return None
@@ -215,13 +216,21 @@ class Trainer:
             return None
         start = time.time()
         logger.info("Testing...")
+        generator = ExampleGenerator(self.current_net, self.name_game, self.device, is_test=True,
+                                     temperature=self.temperature, dirichlet_ratio=self.dirichlet_ratio,
+                                     c_puct=self.uct_test, n_pools=self.n_pools, n_processes=self.n_processes)
+        out = {}
         s1, s2 = evaluate.net_vs_random(self.current_net, self.name_game, self.n_tests, device=self.device)
-        logger.info("Average score vs random (net only):" + str((s1 + s2) / 2))
-        z1, z2 = evaluate.zero_vs_random(self.current_net, self.name_game, self.n_tests, n_playouts=self.n_playouts_train,
-                                         c_puct=self.uct_test, device=self.device)
-        logger.info("Average score vs random:" + str((z1 + z2) / 2))
+        out["net_vs_random"] = (s1 + s2) / 2
+        logger.info("Average score vs random (net only):" + str(out["net_vs_random"]))
+        out["net_vs_mcts100"] = generator.generate_tests(self.n_tests, "test_net_vs_mcts", 100)
+        logger.info("Average score vs mcts100 (net only):" + str(out["net_vs_mcts100"]))
+        out["zero_vs_mcts200"] = generator.generate_tests(self.n_tests, "test_zero_vs_mcts", 200)
+        logger.info("Average score vs mcts200:" + str(out["zero_vs_mcts200"]))
+        out["net_vs_mcts200"] = generator.generate_tests(self.n_tests, "test_net_vs_mcts", 200)
+        logger.info("Average score vs mcts200 (net only):" + str(out["net_vs_mcts200"]))
         logger.info("Testing took: " + str(time.time() - start) + "seconds")
-        return {"net_vs_random": (s1 + s2) / 2, "zero_vs_random": (z1 + z2) / 2}
+        return out
 
     def run(self, **engine_kwargs):
         """Main loop (train.py:272-293): generate -> train -> (save)."""

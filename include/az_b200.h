@@ -65,6 +65,12 @@ extern "C" {
                                           as in the reference the formula belongs to the nodes: only a tree whose root was
                                           created by update_root on a leaf root (mcts.py:199-200) uses it */
 
+#define AZ_F_VIRTUAL_LOSS   (1u << 11) /* throughput mode for small pools, NOT bit-exact with the reference (which runs its
+                                          playouts strictly in sequence, mcts.py:177-179): up to az_config.leaves_per_tree
+                                          leaves in flight per tree, each path carrying a virtual loss until its evaluator
+                                          row arrives.  The evaluator batch is n_trees * leaves_per_tree rows, row =
+                                          tree * leaves_per_tree + slot, for priors, values and observations alike */
+
 /* root noise (mcts.py:182-190) */
 #define AZ_NOISE_NONE      0 /* use_dirichlet=False */
 #define AZ_NOISE_DIRICHLET 1 /* device Dirichlet(alpha) from the counter stream (throughput mode) */
@@ -75,6 +81,9 @@ extern "C" {
 #define AZ_EVAL_EXTERNAL 0 /* priors/values come from the caller (the ResNet), az_step inputs */
 #define AZ_EVAL_UNIFORM  1 /* in-kernel uniform 1/A priors, value 0 (tree-kernel-only throughput) */
 #define AZ_EVAL_HASH     2 /* in-kernel hash evaluator (oracle oz_synth_eval kind 1) */
+#define AZ_EVAL_ROLLOUT  3 /* MCTS.random_rollout (mcts.py:205-223) in the kernel: priors = 1 for every action, value = the result
+                             of one uniformly random playout from the leaf for the player to move there; the move stream is
+                             a counter hash of (seed, position) (oracle oz_synth_eval kind 2) */
 
 /* observation formats written by az_step (network.py:9-18 planes + current-player plane) */
 #define AZ_OBS_NONE      0
@@ -110,6 +119,8 @@ typedef struct az_config {
   int32_t device;              /* CUDA device ordinal */
   uint32_t flags;              /* AZ_F_* */
   uint64_t seed;
+  int32_t leaves_per_tree;     /* AZ_F_VIRTUAL_LOSS: evaluator rows (leaves in flight) per tree; else 1 */
+  int32_t reserved0;
 } az_config;
 
 typedef struct az_engine az_engine;
@@ -171,14 +182,15 @@ int az_set_positions(az_engine* e, const int32_t* hist_host, const int32_t* len_
  *   update_root_host[i] >= 0 : MCTS.update_root(action) mcts.py:192-203 (also advances the tree's position)
  *   reset_tree_host[i] != 0  : self.mcts = MCTS(...) (alphazerobot.py:66-68) -- fresh root; the value 2 builds the root that
  *                              update_root creates for a leaf root instead (it carries use_puct, see AZ_F_UCT)
- *   begin_host[i] != 0       : MCTS.search(state) mcts.py:164-180 -- start n_playouts simulations
+ *   begin_host[i] != 0       : MCTS.search(state) mcts.py:164-180 -- start n_playouts simulations; the value 2 runs
+ *                              MCTS.playout(state) mcts.py:126-153 instead: ONE simulation, no root Dirichlet expansion
  * Order applied: reset, update_root, begin. */
 int az_command(az_engine* e, const int32_t* update_root_host, const int32_t* reset_tree_host,
                const int32_t* begin_host, void* stream);
 
 /* One evaluator round trip.  priors_dev [n_trees][num_actions] and values_dev [n_trees] answer the requests
  * produced by the previous az_step/az_reset (ignored for trees without a request; may be NULL on the first
- * call or with an in-kernel evaluator).  noise_dev [n_trees][max_children] doubles (AZ_NOISE_HOST).
+ * call or with an in-kernel evaluator; with AZ_F_VIRTUAL_LOSS the batch is n_trees * leaves_per_tree rows).  noise_dev [n_trees][max_children] doubles (AZ_NOISE_HOST).
  * obs_dev receives the next requests in obs_format.  policy_fn(state) of mcts.py:146,183 is thus batched as
  * eval_batch(obs) -> (priors, values). */
 int az_step(az_engine* e, const void* priors_dev, const void* values_dev, const double* noise_dev,
@@ -201,7 +213,8 @@ int az_status(az_engine* e, int32_t* phase_dev, int32_t* sims_dev, int32_t* ply_
 
 /* Pending request positions: canonical bitboards [n_trees][2], ply [n_trees], and the action path from the
  * root to the requested leaf [n_trees][max_depth] with its length depth_dev[n_trees] -- lets a host policy_fn
- * rebuild the leaf state (root.clone() + apply_action along the path). */
+ * rebuild the leaf state (root.clone() + apply_action along the path).  In manual mode a tree in AZ_PH_SEARCH_DONE reports
+ * the path of its LAST simulation (depth >= 0, bitboards 0 / ply -1): MCTS.playout leaves the caller's state at the leaf. */
 int az_request_info(az_engine* e, uint64_t* bb_dev, int32_t* ply_dev, int32_t* path_actions_dev,
                     int32_t* depth_dev, int32_t max_depth, void* stream);
 

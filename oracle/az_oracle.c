@@ -205,6 +205,23 @@ void oz_synth_eval(const oz_state* s, int kind, uint64_t seed, int shift, double
   uint64_t bb[2];
   oz_bitboards(s, bb);
   const uint64_t k = oz_mix64(bb[0] ^ oz_mix64(bb[1] ^ oz_mix64(seed + (uint64_t)s->player)));
+  if (kind == 2) {
+    /* MCTS.random_rollout (mcts.py:205-223): priors = ones, value = player_return(mover) of one uniformly random playout;
+     * the "random" picks are the counter hash r_j = mix64(k + (j+1)*golden) % n_legal, a pure function of the position */
+    for (int a = 0; a < A; ++a) priors[a] = 1.0;
+    oz_state t = *s;
+    const int mover = s->player;
+    for (uint64_t j = 0; !oz_terminal(&t); ++j) {
+      int32_t legal[OZ_MAX_LEGAL];
+      const int n = oz_legal(&t, legal);
+      const uint64_t r = oz_mix64(k + (j + 1) * 0x9E3779B97F4A7C15ULL);
+      oz_apply(&t, legal[r % (uint64_t)n]);
+    }
+    double ret[2];
+    oz_returns(&t, ret);
+    *value = ret[mover];
+    return;
+  }
   const double scale = ldexp(1.0, -(10 + shift));
   for (int a = 0; a < A; ++a) {
     const uint64_t ha = oz_mix64(k + (uint64_t)(a + 1) * 0xD1B54A32D192ED03ULL);

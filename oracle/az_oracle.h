@@ -69,7 +69,8 @@ void oz_bitboards(const oz_state* s, uint64_t out[2]);
 /* ---- counter-based hash "RNG" + synthetic evaluator (shared definition with the CUDA engine) ---- */
 uint64_t oz_mix64(uint64_t x);
 uint64_t oz_counter(uint64_t seed, uint64_t tree, uint64_t game_seq, uint64_t ply, uint64_t idx, uint64_t stream);
-/* kind 0: uniform 1/A, value 0.  kind 1: hash priors (1+r10)*2^-(10+shift), value on a 1/16 grid */
+/* kind 0: uniform 1/A, value 0.  kind 1: hash priors (1+r10)*2^-(10+shift), value on a 1/16 grid.
+   kind 2: MCTS.random_rollout (mcts.py:205-223): priors = 1, value = one random playout with hash-stream move picks */
 void oz_synth_eval(const oz_state* s, int kind, uint64_t seed, int shift, double* priors, double* value);
 
 /* the same evaluator for n positions given as canonical bitboards + ply (fp32 out; rows with ply < 0 untouched) */

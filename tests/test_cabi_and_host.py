@@ -30,9 +30,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_config_struct_layout_matches_header():
     from alphazero_openspiel_b200 import _lib as L
-    # field order/size as declared in the header: 6 int32, 5 double, 10 int32/uint32, 1 uint64
-    assert C.sizeof(L.AzConfig) == 6 * 4 + 5 * 8 + 10 * 4 + 8
-    assert L.AzConfig.seed.offset == 104 and L.AzConfig.c_puct.offset == 24
+    # field order/size as declared in the header: 6 int32, 5 double, 10 int32/uint32, 1 uint64, 2 int32 (appended in r02)
+    assert C.sizeof(L.AzConfig) == 6 * 4 + 5 * 8 + 10 * 4 + 8 + 2 * 4
+    assert L.AzConfig.seed.offset == 104 and L.AzConfig.c_puct.offset == 24 and L.AzConfig.leaves_per_tree.offset == 112
     assert C.sizeof(L.AzRecord) == 72
 
 

@@ -61,6 +61,44 @@ def test_mcts_search_update_root_matches_reference_port(shim, game):
 
 
 @pytest.mark.parametrize("game", ["connect_four", "breakthrough(rows=6,columns=6)"])
+def test_mcts_playout_matches_reference_port(shim, game):
+    """MCTS.playout(state) (mcts.py:126-153): one simulation per call, the caller's state is walked to the leaf in place,
+    no root Dirichlet expansion.  After every playout the root statistics and the leaf reached equal the port's; a search()
+    afterwards continues from the same tree.  A position two plies from the end exercises the terminal-leaf branch."""
+    from oracle import ref_port
+    from alphazero_openspiel_b200.mcts import MCTS
+    g = shim.load_game(game)
+    A = g.num_distinct_actions()
+    fn = _hash_policy()
+    s = g.new_initial_state()
+    if game == "connect_four":
+        for a in [3, 3, 4, 4, 5, 0]:      # x threatens 2-3-4-5-6: terminal leaves appear within a few playouts
+            s.apply_action(a)
+    ours = MCTS(fn, A, n_playouts=50, use_dirichlet=True, game_name=game)
+    ref = ref_port.PortMCTS(fn, A, n_playouts=50, use_dirichlet=True)
+    terminal_leaves = 0
+    for i in range(70):
+        a, b = s.clone(), s.clone()
+        ours.playout(a)
+        ref.playout(b)
+        assert a.history() == b.history(), i
+        terminal_leaves += a.is_terminal()
+        assert ours.root.N == ref.visits[ref.root] and ours.root.Q == ref.mean[ref.root]
+        kids = ours.root.children
+        acts, ids = ref.kids[ref.root]
+        assert list(kids.keys()) == acts
+        for act, j in zip(acts, ids):
+            assert kids[act].N == ref.visits[j] and kids[act].Q == ref.mean[j] and kids[act].P == ref.prior[j]
+    if game == "connect_four":
+        assert terminal_leaves > 0
+    np.random.seed(3)
+    x = ours.search(s)
+    np.random.seed(3)
+    y = ref.search(s)
+    assert x == y
+
+
+@pytest.mark.parametrize("game", ["connect_four", "breakthrough(rows=6,columns=6)"])
 def test_mcts_use_puct_false_matches_reference_port(shim, game):
     """use_puct=False (mcts.py:80) with the reference's actual semantics (the port is pinned to the live
     reference in test_oracle_golden): a freshly constructed MCTS still searches with PUCT, a tree whose root was created by
@@ -309,6 +347,41 @@ def test_net_only_match_up_and_trainer_test_agent(shim):
     assert t1 + t2 > 1.2 and t1 + t2 > b1 + b2 + 0.4, (t1, t2, b1, b2)
     tr = Trainer(n_tests=8, n_playouts_train=8)
     tr.current_net.load_state_dict(net.state_dict())
-    out = tr.test_agent()
-    assert set(out) == {"net_vs_random", "zero_vs_random"} and all(-1.0 <= v <= 1.0 for v in out.values())
-    assert out["zero_vs_random"] >= 0.75
+    out = tr.test_agent()      # train.py:238-270: net vs random, net vs mcts100, zero vs mcts200, net vs mcts200
+    assert set(out) == {"net_vs_random", "net_vs_mcts100", "zero_vs_mcts200", "net_vs_mcts200"}
+    assert all(-1.0 <= v <= 1.0 for v in out.values())
+    assert out["net_vs_random"] > 0.5
+
+
+def test_tournament_alphazero_vs_mcts_with_the_shipped_breakthrough_checkpoint(shim):
+    """tournament.py:19-27, the reference's only published number: with models/example_model_breakthrough(6x6).pth an
+    AlphaZero bot with 100 playouts "should win over 99% of games" against the MCTS bot with 200 playouts.  Here both bots
+    run batched on the device (evaluate.zero_vs_mcts through ExampleGenerator.generate_tests; the MCTS bot is the UCT +
+    random-rollout bot of evaluate.py) -- an end-to-end pin of the Breakthrough game kernels, the observation encoding and
+    the large-action-space evaluator head.  The untrained network does not get there."""
+    import os
+    import torch
+    from alphazero_openspiel_b200.examplegenerator import ExampleGenerator
+    from alphazero_openspiel_b200.game_utils import test_zero_vs_mcts, test_zero_vs_zero
+    from alphazero_openspiel_b200.network import Net
+    game = "breakthrough(rows=6,columns=6)"
+    ck = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example_model_breakthrough_6x6.pth")
+    net = Net([3, 6, 6], 432)
+    net.load_state_dict(torch.load(ck, map_location="cpu", weights_only=True))
+    net.eval()
+    gen = ExampleGenerator(net, game, torch.device("cuda:0"), is_test=True, generate_statistics=False, seed=11)
+    gen.kwargs["settings1"] = {"n_playouts": 100}
+    avg = gen.generate_tests(48, test_zero_vs_mcts, 200)          # 96 games
+    win_rate = avg * 0.5 + 0.5
+    assert win_rate >= 0.95, win_rate
+    torch.manual_seed(0)
+    blank = ExampleGenerator(Net([3, 6, 6], 432).eval(), game, torch.device("cuda:0"), is_test=True, seed=11)
+    blank.kwargs["settings1"] = {"n_playouts": 100}
+    assert blank.generate_tests(48, test_zero_vs_mcts, 200) * 0.5 + 0.5 < win_rate - 0.1
+    # zero vs zero (tournament.py:30-53): more playouts must not lose to fewer with the same network
+    gen2 = ExampleGenerator(net, game, torch.device("cuda:0"), is_test=True, generate_statistics=True, seed=5)
+    gen2.kwargs["settings1"] = {"n_playouts": 200, "use_probabilistic_actions": True}
+    gen2.kwargs["settings2"] = {"n_playouts": 20, "use_probabilistic_actions": True}
+    avg2, stats = gen2.generate_tests(32, test_zero_vs_zero, None)
+    assert -1.0 <= avg2 <= 1.0 and stats == []
+    assert avg2 > 0.0, avg2

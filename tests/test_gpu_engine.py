@@ -40,14 +40,15 @@ def test_game_dynamics_bit_exact(game):
 
 
 def _run_engine_selfplay(game, n_trees, n_playouts, seed, noise, sample, keep, flags_extra=0, max_steps=200000,
-                         max_sims_per_step=0):
+                         max_sims_per_step=0, eval_mode=None, c_puct=2.5):
     from alphazero_openspiel_b200 import engine as E, _lib as L
     flags = L.F_RECORDS | L.F_OFFPOLICY | flags_extra
     if keep:
         flags |= L.F_KEEP_TREE
     if sample:
         flags |= L.F_SAMPLE_MOVES
-    eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=noise, eval_mode=L.EVAL_HASH, flags=flags,
+    eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=noise, flags=flags, c_puct=c_puct,
+                   eval_mode=L.EVAL_HASH if eval_mode is None else eval_mode,
                    seed=seed, max_sims_per_step=max_sims_per_step)
     steps = 0
     while True:
@@ -332,3 +333,68 @@ def test_batched_external_evaluator_path_bit_exact(game, n_trees, n_playouts):
             assert g["root_q"] == r["root_q"] and g["root_n"] == r["root_n"]
             assert g["v_a0c"] == r["v_a0c"] and g["v_offpolicy"] == r["v_offpolicy"]
             assert (int(g["bb"][0]), int(g["bb"][1])) == r["bb"]
+
+
+@pytest.mark.parametrize("game,n_trees,n_playouts", [("connect_four", 64, 80), ("breakthrough(rows=6,columns=6)", 32, 40)])
+def test_device_random_rollout_evaluator_bit_exact(game, n_trees, n_playouts):
+    """AZ_EVAL_ROLLOUT = MCTS.random_rollout (mcts.py:205-223) in the kernel: priors of ones and the outcome of one random
+    playout from the leaf for the player to move there.  Whole self-play games must equal the oracle running the same
+    evaluator (oz_synth_eval kind 2) ply by ply -- this also pins the device playout loop (legal / apply / outcome)."""
+    from alphazero_openspiel_b200 import _lib as L
+    seed = 55
+    recs, ctr = _run_engine_selfplay(game, n_trees, n_playouts, seed, L.NOISE_COUNTER, 1, 1, eval_mode=L.EVAL_ROLLOUT, c_puct=1.0)
+    assert ctr["overflow"] == 0
+    cfg = ou.selfplay_cfg(game, n_playouts, c_puct=1.0, use_dirichlet=2, sample_moves=1, keep_tree=1, seed=seed, eval_kind=2)
+    for t in range(n_trees):
+        plies = recs[(recs["tree"] == t) & (recs["kind"] == 0)]
+        plies = plies[np.argsort(plies["ply"])]
+        ref, ret, _ = ou.selfplay_game(cfg, t)
+        assert len(plies) == len(ref)
+        for r, g in zip(ref, plies):
+            assert list(g["counts"][:r["n_legal"]]) == r["counts"] and g["action"] == r["action"], (t, r["ply"])
+            assert g["root_q"] == r["root_q"] and g["root_n"] == r["root_n"] and g["v_offpolicy"] == r["v_offpolicy"]
+
+
+def _first_search_counts(game, n_trees, n_playouts, leaves, seed=31):
+    """Root visit counts of every tree's FIRST search (ply 0) with the hash evaluator, no root noise, argmax moves."""
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    flags = L.F_RECORDS | L.F_KEEP_TREE | (L.F_VIRTUAL_LOSS if leaves else 0)
+    eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=L.NOISE_NONE, eval_mode=L.EVAL_HASH, flags=flags,
+                   seed=seed, leaves_per_tree=max(leaves, 1), eval_shift=0)
+    steps = 0
+    while True:
+        for _ in range(32):
+            eng.step()
+        steps += 32
+        recs = eng.drain_records()
+        first = recs[(recs["kind"] == 0) & (recs["ply"] == 0)]
+        if len(first) or steps > 100000:
+            break
+    ctr = eng.counters()
+    eng.close()
+    assert ctr["overflow"] == 0
+    return first, steps, ctr
+
+
+@pytest.mark.parametrize("game,n_playouts", [("connect_four", 400), ("breakthrough(rows=6,columns=6)", 200)])
+def test_virtual_loss_mode_is_close_to_the_exact_search(game, n_playouts):
+    """AZ_F_VIRTUAL_LOSS (K leaves in flight per tree) is a labelled NON-bit-exact throughput mode (the reference runs its
+    playouts strictly in sequence, mcts.py:177-179).  It must finish a search in ~1/K of the evaluator round trips, run
+    exactly n_playouts simulations, and its root visit distribution must stay close to the exact one: same evaluator, same
+    position, total-variation distance of the normalised visit counts below the bound stated here, same most-visited move
+    in most searches.  K = 0 (flag off) remains the bit-exact kernel (covered by the parity tests above)."""
+    n_trees = 64   # the hash evaluator depends on the seed only: every tree runs the same search; trees differ by nothing
+    exact, steps1, _ = _first_search_counts(game, n_trees, n_playouts, 0)
+    assert len(exact) == n_trees
+    a = exact["counts"][0].astype(np.float64)
+    assert np.all(exact["counts"] == exact["counts"][0])
+    for K, tv_bound in [(4, 0.12), (8, 0.2)]:
+        vl, stepsK, ctr = _first_search_counts(game, n_trees, n_playouts, K)
+        assert len(vl) == n_trees
+        b = vl["counts"][0].astype(np.float64)
+        assert np.all(vl["counts"] == vl["counts"][0])            # deterministic: same inputs, same schedule
+        assert b.sum() == a.sum() == n_playouts - 1                # n_playouts simulations, the first one expands the root
+        assert stepsK <= steps1 / K * 1.6 + 64                     # ~K leaves per round trip
+        tv = 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
+        assert tv < tv_bound, (K, tv, a, b)
+        assert int(np.argmax(a)) == int(np.argmax(b)), (K, a, b)
