@@ -74,6 +74,7 @@ SIGNATURES = {
     "az_counters": (C.c_int, [C.c_void_p, _VP, _VP]),
     "az_game_replay": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32P, _I32P, C.c_int32, _U64P, _I32P,
                                  _F64P, _I32P, _I32P, _VP, C.c_int32, _VP]),
+    "az_observations": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _U64P, _I32P, _VP, _VP, C.c_int32, _VP]),
     "az_game_random_playouts": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, _I32P,
                                           _I32P, _VP]),
     "az_nn_last_error": (C.c_char_p, []),

@@ -1446,6 +1446,27 @@ __global__ void k_game_replay(const Geo geo, int n, const int32_t* hist, const i
   }
 }
 
+// state_to_board (network.py:9-18) for a gathered minibatch: example idx[i] (or i) of a replay buffer held as canonical
+// bitboards + ply -> observation planes in obs_format.  The trainer's minibatch builder (train.py:108-112 builds the same
+// planes from Python lists of numpy boards).
+template <class GM>
+__global__ void k_observations(const Geo geo, int n, const uint64_t* bb, const int32_t* ply, const int64_t* idx, void* obs,
+                               int obs_format) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long src = idx ? idx[i] : (long long)i;
+  St s;
+  s.b0 = bb[2 * src];
+  s.b1 = bb[2 * src + 1];
+  s.ply = ply[src];
+  Params p;
+  p.geo = geo;
+  StepIO io;
+  io.obs = obs;
+  io.obs_format = obs_format;
+  write_obs<GM, 1>(p, io, i, 0, s);
+}
+
 template <class GM>
 __global__ void k_game_random_playouts(const Geo geo, int n, uint64_t seed, int max_plies, int32_t* hist, int32_t* len) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1902,6 +1923,21 @@ int az_game_replay(int32_t game_id, int32_t rows, int32_t cols, int32_t n, const
     k_game_replay<GM><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(geo, n, hist_dev, len_dev, max_len, bb_dev, status_dev,
                                                                         returns0_dev, n_legal_dev, legal_dev, obs_dev,
                                                                         obs_format);
+    return 0;
+  });
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int az_observations(int32_t game_id, int32_t rows, int32_t cols, int32_t n, const uint64_t* bb_dev, const int32_t* ply_dev,
+                    const int64_t* idx_dev, void* obs_dev, int32_t obs_format, void* stream) {
+  if (check_game(game_id, rows, cols)) return -1;
+  if (n <= 0) return 0;
+  if (!bb_dev || !ply_dev || !obs_dev || obs_format < 1 || obs_format > 2) return fail(-1, "az_observations: bad argument");
+  const Geo geo = make_geo(game_id, rows, cols);
+  dispatch_game(game_id, [&](auto gm) {
+    using GM = decltype(gm);
+    k_observations<GM><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(geo, n, bb_dev, ply_dev, idx_dev, obs_dev, obs_format);
     return 0;
   });
   CK(cudaGetLastError());

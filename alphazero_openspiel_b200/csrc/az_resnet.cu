@@ -744,7 +744,7 @@ k_head(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __
 // logits[b][n] = sum_k X[b][k] * Wfc[n][k] + bias[n] is a real GEMM, M = boards, K = H*W*64, N = A + 1, so it runs on the
 // tensor cores: A operand = the last activation tensor viewed as [boards][(H+1)*W*64] (only the first K columns, i.e. the
 // board cells, are read; the zero pad row is skipped), B operand = the bf16 weight rows [A+1][(H+1)*W*64], both K-major
-// through SWIZZLE_128B TMA boxes of 64 k; tcgen05.mma M128 x N=NC x K16 into one TMEM accumulator; 4-stage smem ring.
+// through SWIZZLE_128B TMA boxes of 64 k; tcgen05.mma M128 x N=NC x K16 into one TMEM accumulator; 2-stage smem ring, 2 CTAs/SM.
 // A CTA owns one (128-board tile, NC-column chunk) of the logits.  Its epilogue adds the bias, writes the raw fp32 logits of
 // the action columns into `priors`, tanh of column A into `values`, and (max, sum exp) of its chunk into `stats`.  The LAST
 // chunk-CTA of a board tile to finish (device counter) turns the tile's logits into the softmax in place:
@@ -768,11 +768,14 @@ struct HeadMmaParams {
   int debug;                         // AZ_NN_HEAD_DEBUG experiments: 1 = no softmax pass, 2 = no epilogue at all, 4 = no MMAs
 };
 
-constexpr int HM_STAGES = 4;
+// Two smem stages and <= 43 KB per stage: two CTAs fit on an SM (2 x 256 TMEM columns), so one CTA's epilogue (TMEM ->
+// logits -> HBM, then possibly the tile's softmax pass) overlaps the other's main loop.  Measured on B200 (8,192 boards of
+// 8x8 Breakthrough): main loop alone 50 us, epilogue + softmax pass alone 71 us, 121 us with one CTA per SM.
+constexpr int HM_STAGES = 2;
 constexpr int HM_THREADS = 192;
 constexpr int HM_A_BYTES = TILE_M * 128;  // one k-block of the A operand: 128 rows x 64 bf16
 
-__global__ void __launch_bounds__(HM_THREADS, 1)
+__global__ void __launch_bounds__(HM_THREADS, 2)
 k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const HeadMmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

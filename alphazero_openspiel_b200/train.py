@@ -57,8 +57,17 @@ class Trainer:
         # Extension: keep the replay buffer as arrays (replay.ExampleBatch) instead of Python lists.
         # Same sampling calls, duplicate merging and losses; `self.buffer` stays empty in this mode.
         self.array_buffer = False
-        # Extension: keep the array buffer on the device and build minibatches there (device_replay.py)
+        # Extension: keep the replay buffer ON THE DEVICE (device_replay.DeviceReplay): duplicates are
+        # merged by a device sort + segment mean and every minibatch is gathered / encoded by the az_observations kernel, so an
+        # optimisation step moves only its 256 sample indices over PCIe.  Implies the array form of the examples.
         self.device_training = False
+        # Extension: with torch.distributed, `ddp=True` trains data-parallel -- every rank takes batch_size / world of each
+        # minibatch and the gradients are averaged with one NCCL all-reduce per step -- instead of rank 0 training alone.
+        self.ddp = False
+        # Extension: capture the whole device optimisation step (forward, losses, backward, Adam) in ONE CUDA graph with
+        # static minibatch buffers -- the 5x50 network at batch 256 is launch-bound in eager mode (~60 kernels of a few
+        # microseconds per step).  Same arithmetic, same sampling calls.  Needs device_training; not combined with ddp.
+        self.graph_step = False
         for k, v in overrides.items():
             if not hasattr(self, k):
                 raise TypeError("unknown Trainer setting %r" % k)
@@ -69,6 +78,7 @@ class Trainer:
         self.generation = 0
         self.buffer = []
         self.abuffer = None
+        self.dbuffer = None
         self.state_shape, self.num_distinct_actions = game_shape(self.name_game)
         self.games_played = 0
         self.start_time = datetime.now().strftime("%Y-%m-%d-%H-%M-%S")
@@ -79,7 +89,10 @@ class Trainer:
         self.current_net = Net(self.state_shape, self.num_distinct_actions, device=self.device)
         self.current_net.to(self.device)
         parallel.broadcast_weights(self.current_net, src=0, device=self.device)  # identical initial weights on every rank
-        self.optimizer = torch.optim.Adam(self.current_net.parameters(), lr=self.lr, weight_decay=0.0001)
+        self.optimizer = torch.optim.Adam(self.current_net.parameters(), lr=self.lr, weight_decay=0.0001,
+                                          capturable=bool(self.graph_step and self.device.type == "cuda"))
+        self._step_graph = None
+        self._pending_capture = None
         self.criterion_value = nn.MSELoss()
         self.current_net.eval()
         self.last_generation_stats = {}
@@ -100,6 +113,75 @@ class Trainer:
         self.optimizer.step()
         self.it += 1
         return loss_p, loss_v
+
+    def net_step_device(self, replay, first, pol, val):
+        """net_step (train.py:95-130) on the device replay buffer: the same `np.random.randint` sampling call, the board planes
+        of the sampled examples come from the az_observations gather kernel, targets are gathered on the device; with
+        `ddp` every rank trains on its slice of the minibatch and the gradients are averaged over NCCL."""
+        sample_ids = np.random.randint(int(first.numel()), size=self.batch_size)
+        rank, world = parallel.rank_world()
+        if self.graph_step and not (self.ddp and world > 1):
+            return self._net_step_graphed(replay, first, pol, val, sample_ids)
+        self.current_net.zero_grad()
+        if self.ddp and world > 1:
+            sample_ids = sample_ids[rank::world]
+        ids = torch.from_numpy(sample_ids).to(self.device)
+        x = replay.boards(first[ids])
+        p_t, v_t = self.current_net(x)
+        p_r = pol[ids].float()
+        v_r = val[ids].float()
+        loss_v = self.criterion_value(v_t, v_r.unsqueeze(1))
+        loss_p = -torch.sum(p_r * torch.log(p_t)) / p_r.size()[0]
+        (loss_v + loss_p).backward()
+        if self.ddp and world > 1:
+            parallel.allreduce_gradients(self.current_net, self.device)
+        self.optimizer.step()
+        self.it += 1
+        return loss_p, loss_v
+
+    def _net_step_graphed(self, replay, first, pol, val, sample_ids):
+        """The device step as one CUDA-graph replay: the minibatch is gathered into static buffers (az_observations kernel +
+        two index_selects), then forward / MSE + cross-entropy / backward / Adam replay from the captured graph."""
+        dev = self.device
+        ids = torch.from_numpy(sample_ids).to(dev)
+        x = replay.boards(first[ids])
+        p_r = pol[ids].float()
+        v_r = val[ids].float().unsqueeze(1)
+        if self._step_graph is None:
+            self._gx, self._gp, self._gv = x.clone(), p_r.clone(), v_r.clone()
+
+            def step():
+                self.optimizer.zero_grad(set_to_none=False)
+                p_t, v_t = self.current_net(self._gx)
+                loss_v = self.criterion_value(v_t, self._gv)
+                loss_p = -torch.sum(self._gp * torch.log(p_t)) / self._gp.size()[0]
+                (loss_v + loss_p).backward()
+                self.optimizer.step()
+                return loss_p.detach(), loss_v.detach()
+
+            # the first step runs eagerly on a side stream (allocates the gradients and the Adam state), then the same
+            # closure is captured; both count as optimisation steps of this call sequence
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self.optimizer.zero_grad(set_to_none=False)
+                out = step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self._step_graph = torch.cuda.CUDAGraph()
+            self._pending_capture = step
+            self.it += 1
+            return out[0].clone(), out[1].clone()
+        self._gx.copy_(x)
+        self._gp.copy_(p_r)
+        self._gv.copy_(v_r)
+        if self._pending_capture is not None:
+            with torch.cuda.graph(self._step_graph):
+                self._glp, self._glv = self._pending_capture()
+            self._pending_capture = None
+            # (capture does not execute: replay below performs this step)
+        self._step_graph.replay()
+        self.it += 1
+        return self._glp.clone(), self._glv.clone()
 
     def net_step(self, flattened_buffer):
         self.current_net.zero_grad()
@@ -122,15 +204,19 @@ class Trainer:
     def train_network(self):
         rank, world = parallel.rank_world()
         losses = []
-        if rank == 0:
+        if rank == 0 or (self.ddp and self.device_training):
             self.current_net.train()
-            if self.array_buffer:
+            if self.device_training:
+                first, pol, val = self.dbuffer.remove_duplicates()
+            elif self.array_buffer:
                 first, pol, val = self.abuffer.remove_duplicates()
             else:
                 flat = self.remove_duplicates([sample for game in self.buffer for sample in game])
             run_p = run_v = 0
             for i in range(self.n_batches_per_generation):
-                if self.array_buffer:
+                if self.device_training:
+                    loss_p, loss_v = self.net_step_device(self.dbuffer, first, pol, val)
+                elif self.array_buffer:
                     loss_p, loss_v = self.net_step_arrays(self.abuffer, first, pol, val)
                 else:
                     loss_p, loss_v = self.net_step(flat)
@@ -141,8 +227,8 @@ class Trainer:
                     losses.append((float(run_p) / 100., float(run_v) / 100.))
                     run_p = run_v = 0
             self.current_net.eval()
-        if world > 1:
-            parallel.broadcast_weights(self.current_net, src=0, device=self.device)
+        if world > 1 and not (self.ddp and self.device_training):
+            parallel.broadcast_weights(self.current_net, src=0, device=self.device)   # (ddp keeps the ranks in lock step)
         return losses
 
     @staticmethod
@@ -179,8 +265,15 @@ class Trainer:
                                      n_playouts=self.n_playouts_train, temperature=self.temperature,
                                      dirichlet_ratio=self.dirichlet_ratio, c_puct=self.uct_train, backup=self.backup,
                                      tree_strap=self.tree_strap, n_pools=self.n_pools, n_processes=self.n_processes,
-                                     rank0_only=True, **engine_kwargs)
-        if self.array_buffer:
+                                     rank0_only=not (self.ddp and self.device_training), **engine_kwargs)
+        if self.device_training:
+            from .device_replay import DeviceReplay
+            new = generator.generate_batch(n_games)
+            n_new = new.n_games
+            if self.dbuffer is None:
+                self.dbuffer = DeviceReplay(self.name_game, self.device)
+            self.dbuffer.append(new)
+        elif self.array_buffer:
             from .replay import ExampleBatch
             new = generator.generate_batch(n_games)
             n_new = new.n_games
@@ -194,7 +287,9 @@ class Trainer:
         self.last_generation_stats = dict(generator.last_stats, seconds=time.time() - start, games=n_new)
         logger.info("Finished Generating Data. Took: " + str(time.time() - start) + " seconds")
         self.update_buffer_size()
-        if self.array_buffer:
+        if self.device_training:
+            self.dbuffer.keep_last_games(self.n_games_buffer)
+        elif self.array_buffer:
             self.abuffer = self.abuffer.last_games(self.n_games_buffer)
         elif len(self.buffer) > self.n_games_buffer:
             del self.buffer[:len(self.buffer) - self.n_games_buffer]

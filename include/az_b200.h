@@ -246,6 +246,12 @@ int az_game_replay(int32_t game_id, int32_t rows, int32_t cols, int32_t n, const
                    double* returns0_dev, int32_t* n_legal_dev, int32_t* legal_dev, void* obs_dev,
                    int32_t obs_format, void* stream);
 
+/* state_to_board (network.py:9-18) for a gathered minibatch of a replay buffer held on the device as canonical bitboards
+ * [.][2] + ply [.]: row i of obs_dev (obs_format AZ_OBS_F32_NCHW / AZ_OBS_BF16_NHWC) = the planes of example idx_dev[i]
+ * (int64; NULL = example i).  The trainer's minibatch builder (train.py:108-112). */
+int az_observations(int32_t game_id, int32_t rows, int32_t cols, int32_t n, const uint64_t* bb_dev, const int32_t* ply_dev,
+                    const int64_t* idx_dev, void* obs_dev, int32_t obs_format, void* stream);
+
 /* Random playouts entirely on the device from counter stream 3 (seed, i): plays up to max_plies uniformly
  * random legal moves per game and writes the action history (hist_dev [n][max_plies], len_dev [n]).  Used to
  * generate full-size property-test inputs without host work. */

@@ -39,6 +39,11 @@ def _worker(rank, world, port, q):
     out["q"] = allr["root_q"].tolist()
     empty = parallel.gather_records(np.zeros((0,), dtype=dt))
     out["empty"] = len(empty)
+    # data-parallel gradient averaging (Trainer(ddp=True)): grads = rank + 1 on every parameter -> mean 1.5
+    for p_ in net.parameters():
+        p_.grad = torch.full_like(p_, float(rank + 1))
+    parallel.allreduce_gradients(net)
+    out["grad"] = sorted({float(p_.grad.flatten()[0]) for p_ in net.parameters()})
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -63,6 +68,7 @@ def test_world_size_2_gloo():
         assert res[r]["trees"] == [0, 1, 2] + [(1 << 20) + i for i in range(5)]
         assert res[r]["plies"] == [0, 1, 2, 100, 101, 102, 103, 104]
         assert res[r]["q"] == [0.5] * 3 + [1.5] * 5
+        assert res[r]["grad"] == [1.5]
 
 
 def test_shard_covers_everything():
