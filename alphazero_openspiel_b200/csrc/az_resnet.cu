@@ -765,6 +765,7 @@ struct HeadMmaParams {
   float2* stats;       // [boards][n_chunks]: (max, sum exp(l - max)) over the action columns of the chunk
   int* counters;       // [board tiles]: chunk-CTAs finished (self-resetting)
   int boards, A, n_chunks, NC, KB;   // NC = columns per chunk (multiple of 16, <= 256), KB = K / 64
+  int mode;                          // 1 = rendezvous (logits stay in TMEM, probabilities written once), 0 = last-arriver pass
   int debug;                         // AZ_NN_HEAD_DEBUG experiments: 1 = no softmax pass, 2 = no epilogue at all, 4 = no MMAs
 };
 
@@ -858,6 +859,85 @@ k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     mbar_wait(bar_tfull, 0u);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (p.mode == 1) {
+      // ---- rendezvous mode: the logits never leave TMEM until they are final.  Pass A: (max, sum exp) of this chunk per
+      // board, online over 16-column blocks; the chunk-CTAs of the board tile then meet at a device counter (they have
+      // consecutive block indices and are co-resident: grids are dispatched in block order, so every sibling is running or
+      // about to be dispatched; the spin is bounded all the same); pass B: p = exp(l - M) / S straight from TMEM, written once.
+      float mx = -3.0e38f, se = 0.f;
+      for (int c0 = 0; c0 < p.NC; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float x[16], bm = -3.0e38f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          x[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+          if (n0 + c0 + j < p.A) bm = fmaxf(bm, x[j]);
+          else if (n0 + c0 + j == p.A && live) p.values[board] = tanhf(x[j]);   // network.py:63
+        }
+        if (bm > mx) {
+          se *= __expf(mx - bm);
+          mx = bm;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + c0 + j < p.A) se += __expf(x[j] - mx);
+      }
+      if (live) p.stats[(size_t)board * p.n_chunks + chunk] = make_float2(mx, se);
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      int* arrive = p.counters + 2 * mtile;
+      if (warp == 2 && lane == 0) {
+        atomicAdd(arrive, 1);
+        for (int spin = 0; spin < (1 << 24); ++spin) {
+          if (*reinterpret_cast<volatile int*>(arrive) >= p.n_chunks) break;
+          __nanosleep(64);
+        }
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float M = -3.0e38f, S = 0.f;
+      if (live) {
+        const float2* st = p.stats + (size_t)board * p.n_chunks;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const float2 w = __ldcg(st + c);
+          if (w.y > 0.f) {
+            const float Mn = fmaxf(M, w.x);
+            S = S * __expf(M - Mn) + w.y * __expf(w.x - Mn);
+            M = Mn;
+          }
+        }
+      }
+      const float inv = S > 0.f ? 1.f / S : 0.f;
+      for (int c0 = 0; c0 < p.NC; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (!live) continue;
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = __expf(__uint_as_float(v[j]) + s_bias[c0 + j] - M) * inv;
+        if (vec_ok && n0 + c0 + 16 <= p.A) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(prow + n0 + c0 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < p.A) prow[n0 + c0 + j] = x[j];
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        const int gone = atomicAdd(arrive + 1, 1);
+        if (gone == p.n_chunks - 1) {   // everybody is past the rendezvous: ready for the next launch (graph replay)
+          arrive[0] = 0;
+          arrive[1] = 0;
+        }
+      }
+    } else {
     float mx = -3.0e38f;
     for (int c0 = 0; c0 < ((p.debug & 2) ? 0 : p.NC); c0 += 16) {   // pass 1: logits out, row maximum
       uint32_t v[16];
@@ -898,9 +978,9 @@ k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     __threadfence();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (warp == 2 && lane == 0) {
-      const int done = atomicAdd(p.counters + mtile, 1);
+      const int done = atomicAdd(p.counters + 2 * mtile, 1);
       *s_last = done == p.n_chunks - 1;
-      if (done == p.n_chunks - 1) p.counters[mtile] = 0;   // ready for the next launch (graph replay)
+      if (done == p.n_chunks - 1) p.counters[2 * mtile] = 0;   // ready for the next launch (graph replay)
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (*s_last && !(p.debug & 3)) {
@@ -966,6 +1046,7 @@ k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -1226,7 +1307,7 @@ extern "C" int64_t az_nn_head_large_scratch_bytes(int32_t boards, int32_t n_acti
   int chunks, nc;
   head_chunks(boards, n_actions, &chunks, &nc);
   const int tiles = (boards + aznn::TILE_M - 1) / aznn::TILE_M;
-  return (int64_t)boards * chunks * 8 + (((int64_t)tiles * 4 + 7) & ~(int64_t)7);
+  return (int64_t)boards * chunks * 8 + (int64_t)tiles * 8;
 }
 
 extern "C" int az_nn_head_large(const void* x, const void* w, const float* bias, float* priors, float* values, void* scratch,
@@ -1248,14 +1329,17 @@ extern "C" int az_nn_head_large(const void* x, const void* w, const float* bias,
   p.bias = bias;
   p.priors = priors;
   p.values = values;
-  p.counters = reinterpret_cast<int*>(scratch);                        // [tiles] first (zeroed once by the caller)
-  p.stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + (((size_t)tiles * 4 + 7) & ~(size_t)7));
+  p.counters = reinterpret_cast<int*>(scratch);                        // [tiles][2] first (zeroed once by the caller)
+  p.stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(scratch) + (size_t)tiles * 8);
   p.boards = boards;
   p.A = n_actions;
   p.n_chunks = chunks;
   p.NC = nc;
   p.KB = (int)(k_elems / 64);
   p.debug = env_int("AZ_NN_HEAD_DEBUG", 0);
+  // rendezvous needs every chunk-CTA of a board tile resident at once: <= 2 CTAs per SM x 148 SMs cover any tile (<= 13
+  // chunks); the debug switches belong to the other mode
+  p.mode = (env_int("AZ_NN_HEAD_MODE", 1) == 1 && p.debug == 0) ? 1 : 0;
   CUtensorMap tm_x, tm_w;
   if (make_tmap_kmajor(&tm_x, x, boards, row_elems, k_elems, TILE_M)) return -2;
   if (make_tmap_kmajor(&tm_w, w, n_actions + 1, row_elems, k_elems, nc)) return -2;

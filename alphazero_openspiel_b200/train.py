@@ -227,8 +227,10 @@ class Trainer:
                     losses.append((float(run_p) / 100., float(run_v) / 100.))
                     run_p = run_v = 0
             self.current_net.eval()
-        if world > 1 and not (self.ddp and self.device_training):
-            parallel.broadcast_weights(self.current_net, src=0, device=self.device)   # (ddp keeps the ranks in lock step)
+        if world > 1:
+            # rank 0's weights to everyone; under ddp the parameters are already equal and this only re-synchronises the
+            # BatchNorm running statistics, which every rank accumulated from its own slice of the minibatches
+            parallel.broadcast_weights(self.current_net, src=0, device=self.device)
         return losses
 
     @staticmethod

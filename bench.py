@@ -492,7 +492,7 @@ def run_train(args):
     np.random.seed(rank)
     tr = Trainer(name="bench", name_game=args.game, device=dev, save=False, n_playouts_train=args.playouts,
                  array_buffer=not args.list_buffer, device_training=not args.list_buffer,
-                 graph_step=not (args.list_buffer or args.eager_train))
+                 graph_step=not (args.list_buffer or args.eager_train or args.ddp), ddp=args.ddp)
     gens = max(1, args.generations)
 
     def sync():
@@ -554,7 +554,9 @@ def run_train(args):
                 "generation_s": gen_t / gens, "train_s": train_t / gens, "broadcast_ms": bcast_ms,
                 "sims_per_sec_in_generation": all_sims / gen_t if gen_t > 0 else None,
                 "games_per_generation": games / gens, "buffer": "arrays on device" if not args.list_buffer else "python lists",
-                "train_step": "one CUDA graph per optimisation step" if tr.graph_step else "eager PyTorch",
+                "train_step": ("one CUDA graph per optimisation step" if tr.graph_step else "eager PyTorch") +
+                              (", data-parallel over %d ranks (gradient all-reduce)" % world if tr.ddp and world > 1
+                               else (", rank 0 trains + NCCL weight broadcast" if world > 1 else "")),
                 "clocks": clocks}
         print(json.dumps(line))
     if world > 1:
@@ -562,6 +564,9 @@ def run_train(args):
 
 
 def main():
+    # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION, set on some boxes) off it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20, help="timed steps; one step = %d evaluator round trips" % ROUNDS_PER_STEP)
@@ -581,6 +586,7 @@ def main():
     ap.add_argument("--node-capacity", type=int, default=0)
     ap.add_argument("--virtual-loss", type=int, default=0, help="K leaves in flight per tree (non-bit-exact mode); 0 = off")
     ap.add_argument("--generations", type=int, default=3, help="--config train: generations timed")
+    ap.add_argument("--ddp", action="store_true", help="--config train: data-parallel optimisation steps (NCCL gradient all-reduce)")
     ap.add_argument("--eager-train", action="store_true", help="--config train: eager optimisation steps (no CUDA graph)")
     ap.add_argument("--list-buffer", action="store_true", help="--config train: the reference's Python-list replay buffer")
     ap.add_argument("--no-keep-tree", action="store_true", help="experiment: fresh tree every move (no re-root compaction)")

@@ -20,7 +20,7 @@ for r in data:
     nm = r[ix["Kernel Name"]]
     b = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
         to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
-    if "k_conv8" in nm and "(bool)0" in nm:
+    if "k_conv8<0" in nm.replace("(bool)", "") or "k_conv8<false" in nm:
         conv.append(b)
 with open(os.path.join(root, "profiles", name + "_raw.csv"), "w", newline="") as f:
     w = csv.writer(f)
