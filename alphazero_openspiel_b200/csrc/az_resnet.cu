@@ -493,7 +493,7 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     uint2 xnext = make_uint2(0u, 0u);
     if (j0 < n_items) {
       if (STEM) xnext = obs_of(j0);
-      if (has_res && !skip_all && lane == 0) load_res(j0, 0);
+      if (has_res && !skip_all && elect_one()) load_res(j0, 0);
     }
     for (int i = j0, n = 0; i < n_items; i += NEQ, ++n) {
       const int it = i >> 1, half = i & 1, acc = it % ACC, b = n & 1;
@@ -509,10 +509,11 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       // a conv, NV = 2 live values: its TMEM loads, shuffles and epilogue arithmetic shrink accordingly.
       uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C8_N + col0);
-      const bool short_blk = !STEM && half == 1;      // block cb = 1 of this item has only 2 live channels (48, 49)
+      const bool short_blk = half == 1;      // block cb = 1 of this item has only 2 live channels (48, 49)
       if constexpr (STEM) {
         tmem_ld16(taddr, &v[0]);
-        tmem_ld16(taddr + 16u, &v[16]);
+        if (short_blk) tmem_ld2(taddr + 16u, &v[16]);
+        else tmem_ld16(taddr + 16u, &v[16]);
         tmem_ld_wait();
       } else {
         // accumulator columns: D_-1 at [0, 50), D_0 at [50, 100), D_+1 at [100, 150)   (n = dx*50 + co)
@@ -548,21 +549,22 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty(acc));
-      if (skip_all) continue;
-      // Staging buffers must have been read by their TMA stores before they are overwritten: with a residual (prefetched
-      // into io[b^1]) or a second output (single buffer) that is the previous item's store group; otherwise only io[b] is
-      // written now, last stored two items ago, and the previous item's store may stay in flight.
-      if (lane == 0) {
-        if (has_res || has_out2) bulk_wait_read0();
-        else bulk_wait_read1();
+      const int inext = i + NEQ;
+      // One elected lane (always the same one: it owns this warp's bulk async-groups) releases the accumulator, waits until
+      // the staging buffers have been read by their TMA stores and prefetches the next residual.  Staging rule: with a
+      // residual (prefetched into io[b^1]) or a second output (single buffer) the previous item's store group must have
+      // been read; otherwise only io[b] is written now, last stored two items ago, and the previous store may stay in flight.
+      if (elect_one()) {
+        mbar_arrive(bar_tempty(acc));
+        if (!skip_all) {
+          if (has_res || has_out2) bulk_wait_read0();
+          else bulk_wait_read1();
+          if (has_res && inext < n_items) load_res(inext, b ^ 1);
+        }
       }
       __syncwarp();
-      const int inext = i + NEQ;
-      if (inext < n_items) {
-        if (STEM) xnext = obs_of(inext);
-        if (has_res && lane == 0) load_res(inext, b ^ 1);
-      }
+      if (skip_all) continue;
+      if (STEM && inext < n_items) xnext = obs_of(inext);
       if (has_res) mbar_wait(bar_res(e, b), (uint32_t)(n >> 1) & 1u);
       uint8_t* io = stg + b * 2048 + row_off;
       uint8_t* o2 = stg + 4096 + row_off;
@@ -645,13 +647,14 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       else finish(std::integral_constant<int, 16>{}, 1);
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         tma_store_3d(&tm_out, col0, 0, g0, stg_u32 + (uint32_t)b * 2048u);
         if (has_out2) tma_store_3d(&tm_out2, col0, 0, g0, stg_u32 + 4096u);
         bulk_commit();
       }
     }
-    if (lane == 0) bulk_wait0();
+    __syncwarp();
+    if (elect_one()) bulk_wait0();
   }
 
   tc_fence_before();

@@ -398,3 +398,46 @@ def test_virtual_loss_mode_is_close_to_the_exact_search(game, n_playouts):
         tv = 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
         assert tv < tv_bound, (K, tv, a, b)
         assert int(np.argmax(a)) == int(np.argmax(b)), (K, a, b)
+
+
+def test_external_evaluator_rows_at_full_pool_size():
+    """Size-independent property at BASELINE configs[2]'s pool size (16,384 trees, synthetic random starts, auto-restart,
+    simulation cap): answering every request with fp32 rows computed by the oracle's evaluator from the az_request_info
+    bitboards (the AZ_EVAL_EXTERNAL read path the benchmark uses) must reproduce the in-kernel AZ_EVAL_HASH engine
+    exactly -- every record of the first moves of every tree and all counters."""
+    import torch
+    from oracle import cbind
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    n_trees, n_playouts, seed, steps = 16384, 100, 9, 330
+    flags = L.F_RECORDS | L.F_KEEP_TREE | L.F_SAMPLE_MOVES | L.F_AUTO_RESTART | L.F_RANDOM_START
+    olib = cbind.lib()
+    out = {}
+    for mode in (L.EVAL_HASH, L.EVAL_EXTERNAL):
+        eng = E.Engine("connect_four", n_trees, n_playouts=n_playouts, noise_mode=L.NOISE_COUNTER, eval_mode=mode, flags=flags,
+                       seed=seed, start_plies_mod=21, max_sims_per_step=8)
+        if mode == L.EVAL_EXTERNAL:
+            pri_h = torch.zeros((n_trees, 7), dtype=torch.float32).pin_memory()
+            val_h = torch.zeros((n_trees,), dtype=torch.float32).pin_memory()
+            pri_d = torch.zeros((n_trees, 7), dtype=torch.float32, device=eng.device)
+            val_d = torch.zeros((n_trees,), dtype=torch.float32, device=eng.device)
+            eng.step()
+            for _ in range(steps - 1):
+                info = eng.request_info(max_depth=1)
+                bb, ply = np.ascontiguousarray(info["bb"]), np.ascontiguousarray(info["ply"])
+                olib.oz_synth_eval_bb(7, n_trees, bb.ctypes.data, ply.ctypes.data, 1, seed, 2, pri_h.data_ptr(), val_h.data_ptr())
+                pri_d.copy_(pri_h, non_blocking=True)
+                val_d.copy_(val_h, non_blocking=True)
+                eng.step(pri_d, val_d)
+                torch.cuda.synchronize()
+        else:
+            for _ in range(steps):
+                eng.step()
+        out[mode] = (eng.drain_records(), eng.counters())
+        eng.close()
+    (ra, ca), (rb, cb) = out[L.EVAL_HASH], out[L.EVAL_EXTERNAL]
+    assert ca == cb and ca["overflow"] == 0 and ca["moves"] > 2 * n_trees
+    key = lambda r: np.lexsort((r["kind"], r["ply"], r["game_seq"], r["tree"]))  # noqa: E731
+    a, b = ra[key(ra)], rb[key(rb)]
+    assert len(a) == len(b) > 2 * n_trees
+    for f in a.dtype.names:
+        assert np.array_equal(a[f], b[f]), f

@@ -322,3 +322,21 @@ def test_device_replay_matches_the_array_buffer():
     tr.generate_examples(tr.n_games_per_generation)
     tr.train_network()
     assert tr.dbuffer.n_games == 32 and tr.it == 10
+
+
+def test_device_replay_key_hash_groups_like_the_reference_keys():
+    """device_replay.key_hash (host part of the device buffer): two examples get the same 64-bit hash exactly when the
+    reference's info-state keys (action history; plus the start position of random-start games) are equal."""
+    from alphazero_openspiel_b200.device_replay import key_hash
+    from alphazero_openspiel_b200.replay import ExampleBatch
+    for start_mod in (0, 9):
+        recs = _oracle_records(n_games=12, start_mod=start_mod, seed=3)
+        b = ExampleBatch.concat([ExampleBatch.from_records(recs, "connect_four")] * 2)
+        h = key_hash(b)
+        keys = [b.key(i) for i in range(len(b))]
+        by_key, by_hash = {}, {}
+        for i, (k, x) in enumerate(zip(keys, h.tolist())):
+            by_key.setdefault(k, []).append(i)
+            by_hash.setdefault(x, []).append(i)
+        assert sorted(by_key.values()) == sorted(by_hash.values())
+        assert len(by_key) < len(b)          # duplicates exist (every game appears twice)
