@@ -79,6 +79,7 @@ SIGNATURES = {
                                           _I32P, _VP]),
     "az_nn_last_error": (C.c_char_p, []),
     "az_nn_conv3x3": (C.c_int, [_VP] * 8 + [C.c_int32] * 6 + [_VP]),
+    "az_nn_block": (C.c_int, [_VP] * 9 + [C.c_int32] * 4 + [_VP]),
     "az_nn_stem": (C.c_int, [_VP] * 5 + [C.c_int32] * 4 + [_VP]),
     "az_nn_head": (C.c_int, [_VP] * 5 + [C.c_int32] * 5 + [_VP]),
     "az_nn_head_large_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32]),

@@ -49,6 +49,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// mbar_wait with a watchdog: a protocol error in a new kernel traps after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spins & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -660,6 +678,378 @@ k_conv8(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
   tc_fence_before();
   __syncthreads();
   if (warp == NPROD) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_block: one whole residual block without projection (network.py:99-104, blocks 2-5) in ONE kernel:
+//     U  = LeakyReLU(conv1(T) + b1)            (bn2 folded into conv1)
+//     X <- conv2(U) + b2 + X                   (residual stream, in place)
+//     T' = LeakyReLU(s2 * X + t2)              (the next block's bn1 + LeakyReLU; optional)
+// The intermediate tensor U never leaves the SM: conv1's epilogue writes it as bf16 rows straight into a shared-memory ring
+// in the SWIZZLE_128B K-major image that conv2's MMAs read, so a block moves 4 activation passes through HBM (read T, read
+// X, write X, write T') instead of 6.  Both 61 KB weight images stay resident for the whole launch; to make that fit, the
+// conv2 epilogue reads the residual and writes its outputs with plain 16-byte global accesses (row per thread) instead of
+// TMA staging buffers: smem = 2 x 61,440 (weights) + 2 x 18,432 (T slabs) + 3 x 18,432 (U slots) = 215 KB.
+//
+// Work unit: a SUPER-TILE of 16 boards = HP tiles of 128 virtual rows (16*HP groups of 8 rows: always whole tiles), so the rows
+// above the first and below the last tile of a super-tile are board pad rows (zeros) and no halo is ever recomputed.  A U slot
+// has the layout of a T slab (halo group above + 16 groups + halo group below); the first / last group of tile j is written
+// twice, into its own slot and into the halo of slot j-1 / j+1.
+//   MMA order per super-tile: c1(0) c1(1) [c1(j) c2(j-2)] for j = 2..NT-1, c2(NT-2) c2(NT-1): conv2 trails conv1 by two
+//   tiles, which gives conv1's epilogue one MMA time to publish the slot; three TMEM accumulators rotate over that sequence.
+//   warp 0: TMA producer (weights, T slabs)   warp 1: MMA issuer   warps 2-13: epilogue (items (element, quarter, half),
+//   three warps per TMEM lane quarter, round-robin), conv1 items -> U ring, conv2 items -> HBM.
+//
+// STATUS (r02, measured on B200, 16,384 Connect Four boards, scripts/block_microbench.py): bit-for-bit within the conv
+// tolerance on 12 shapes, but SLOWER than the two launches it replaces: 139.5 vs 114.5 us (with second output), 111.3 vs
+// 101.9 us (last block).  Without any global access in the conv2 epilogue the fused pipeline alone takes 106 us (no ufull
+// wait, no U writes: still 99-104 us = 1,960 cycles per tile and conv against 1,790 of k_conv8): two T stages instead of
+// four, and three TMEM accumulators shared by two interleaved MMA streams; the row-per-thread 16-byte global accesses (32
+// different 128-byte lines per instruction) add 33 us on top.  It is therefore OFF by default (AZ_NN_BLOCK=1 enables it in
+// FusedEvaluator); what it would need: a linear U ring (frees 4 KB -> a third T stage) and quad-transposed (coalesced)
+// global accesses or TMA-store staging, for which no shared memory is left next to two resident weight images.
+// ---------------------------------------------------------------------------------------------------------------------
+struct BlockParams {
+  const __nv_bfloat16* w1;
+  const __nv_bfloat16* w2;
+  const float* b1;
+  const float* b2;
+  const float* s2;
+  const float* t2;
+  __nv_bfloat16* x;       // residual stream [boards][H+1][W][64], read and written in place
+  __nv_bfloat16* t_out;   // next block's activated input (must not alias the TMA input), or nullptr
+  int boards, H, W, HP, NT, n_super, n_groups;
+  uint32_t hp_magic;
+  int debug;              // AZ_NN_BLOCK_DEBUG experiments: 1 = no residual loads, 2 = no global stores
+};
+
+struct BlockSmem {
+  static constexpr int W_IMG = 3 * C8_N * 128;           // 61,440 B per conv
+  static constexpr int W1_OFF = 0, W2_OFF = W_IMG;
+  static constexpr int T_OFF = 2 * W_IMG;                 // 122,880 (1024-aligned)
+  static constexpr int T_STAGES = 2;
+  static constexpr int U_OFF = T_OFF + T_STAGES * C8_A_ST;
+  static constexpr int U_SLOTS = 3;
+  static constexpr int PAR_OFF = U_OFF + U_SLOTS * C8_A_ST;   // b1, b2, s2, t2: 4 x 64 floats
+  static constexpr int BAR_OFF = PAR_OFF + 1024;          // tfull[2] tempty[2] ufull[3] uempty[3] afull[3] aempty[3] w
+  static constexpr int N_BARS = 2 * T_STAGES + 2 * U_SLOTS + 2 * C8_ACC + 1;
+  static constexpr int TOTAL = BAR_OFF + N_BARS * 8 + 16;
+  static_assert(T_OFF % 1024 == 0 && U_OFF % 1024 == 0, "operand alignment");
+  static_assert(TOTAL <= 232448, "shared memory budget");
+};
+
+// element e of a super-tile's MMA sequence -> (kind: 0 = conv1, 1 = conv2; local tile j)
+__device__ __forceinline__ void block_decode(int e, int NT, int& kind, int& j) {
+  if (e < 2) {
+    kind = 0;
+    j = e;
+  } else if (e >= 2 * NT - 2) {
+    kind = 1;
+    j = e - NT;                       // 2NT-2 -> NT-2, 2NT-1 -> NT-1
+  } else {
+    kind = e & 1;
+    j = kind ? (e - 3) >> 1 : 2 + ((e - 2) >> 1);
+  }
+}
+
+template <bool HAS_OUT2>
+__global__ void __launch_bounds__(14 * 32, 1)
+k_block(const __grid_constant__ CUtensorMap tm_in, const BlockParams p) {
+  using L = BlockSmem;
+  constexpr int ACC = C8_ACC, NE = 12, NEQ = 3;
+  constexpr int W_ROW_BYTES = C8_N * 128;
+  constexpr uint32_t TMEM_COLS = 512u;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_w1 = s_base + L::W1_OFF, s_w2 = s_base + L::W2_OFF, s_t = s_base + L::T_OFF, s_u = s_base + L::U_OFF;
+  float* s_b1 = reinterpret_cast<float*>(smem + L::PAR_OFF);
+  float* s_b2 = s_b1 + 64;
+  float* s_s2 = s_b1 + 128;
+  float* s_t2 = s_b1 + 192;
+  const uint32_t s_bar = s_base + L::BAR_OFF;
+  auto bar_tfull = [&](int s) { return s_bar + 8u * s; };
+  auto bar_tempty = [&](int s) { return s_bar + 8u * (2 + s); };
+  auto bar_ufull = [&](int u) { return s_bar + 8u * (4 + u); };
+  auto bar_uempty = [&](int u) { return s_bar + 8u * (7 + u); };
+  auto bar_afull = [&](int a) { return s_bar + 8u * (10 + a); };
+  auto bar_aempty = [&](int a) { return s_bar + 8u * (13 + a); };
+  const uint32_t bar_w = s_bar + 8u * 16;
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + L::BAR_OFF + L::N_BARS * 8);
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull(i), 1);
+      mbar_init(bar_tempty(i), 1);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(bar_ufull(i), 12);   // 8 body items + 2 halo-above + 2 halo-below arrivals
+      mbar_init(bar_uempty(i), 1);
+      mbar_init(bar_afull(i), 1);
+      mbar_init(bar_aempty(i), 8);
+    }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)s_tmem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;   // parameters of the pad channels 50..63 are forced to zero: those channels stay zero
+    s_b1[c] = c < NF ? p.b1[c] : 0.f;
+    s_b2[c] = c < NF ? p.b2[c] : 0.f;
+    s_s2[c] = (c < NF && HAS_OUT2 && p.s2) ? p.s2[c] : 0.f;
+    s_t2[c] = (c < NF && HAS_OUT2 && p.t2) ? p.t2[c] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int NT = p.NT;
+  const int my_super = (p.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto super_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+  const int n_elems = my_super * 2 * NT;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // =========================== TMA producer ===========================
+      mbar_expect_tx(bar_w, (uint32_t)(2 * L::W_IMG));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        bulk_g2s(s_w1 + (uint32_t)i * W_ROW_BYTES, reinterpret_cast<const uint8_t*>(p.w1) + i * W_ROW_BYTES, W_ROW_BYTES, bar_w);
+        bulk_g2s(s_w2 + (uint32_t)i * W_ROW_BYTES, reinterpret_cast<const uint8_t*>(p.w2) + i * W_ROW_BYTES, W_ROW_BYTES, bar_w);
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are the previous layer's output
+      for (int g = 0; g < my_super * NT; ++g) {
+        const int stage = g & 1;
+        const int tile = super_of(g / NT) * NT + g % NT;
+        mbar_wait_wd(bar_tempty(stage), ((uint32_t)(g >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(bar_tfull(stage), (uint32_t)C8_A_ST);
+        tma_load_3d(s_t + (uint32_t)stage * C8_A_ST, &tm_in, 0, 0, tile * 16 - 1, bar_tfull(stage));
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)C8_N);
+    mbar_wait_wd(bar_w, 0u);
+    for (int n = 0; n < n_elems; ++n) {
+      const int k = n / (2 * NT), e = n - k * 2 * NT, acc = n % ACC;
+      int kind, j;
+      block_decode(e, NT, kind, j);
+      const int g = k * NT + j;
+      mbar_wait_wd(bar_aempty(acc), ((uint32_t)(n / ACC) & 1u) ^ 1u);
+      uint32_t a_base, b_base;
+      if (kind == 0) {
+        mbar_wait_wd(bar_tfull(g & 1), (uint32_t)(g >> 1) & 1u);
+        a_base = s_t + (uint32_t)(g & 1) * C8_A_ST;
+        b_base = s_w1;
+      } else {
+        mbar_wait_wd(bar_ufull(g % 3), (uint32_t)(g / 3) & 1u);
+        a_base = s_u + (uint32_t)(g % 3) * C8_A_ST;
+        b_base = s_w2;
+      }
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = tmem_base + (uint32_t)(acc * C8_N);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const uint64_t at = umma_desc_sw128(a_base + (uint32_t)dy * 1024u);
+          const uint64_t bt = umma_desc_sw128(b_base + (uint32_t)dy * (uint32_t)W_ROW_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(d, at + (uint64_t)(ks * 2), bt + (uint64_t)(ks * 2), idesc, (dy | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(kind == 0 ? bar_tempty(g & 1) : bar_uempty(g % 3));   // operand buffer reusable once the MMAs have read it
+        umma_commit(bar_afull(acc));
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int e_id = warp - 2;
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int j0 = e_id >> 2;     // round-robin slot among the three warps of this quarter
+    const int cc = lane & 7;      // board column of this thread's row (quarters start at c = 0)
+    const float w_up = (p.W == 8 && cc == 0) ? 0.f : 1.f, w_dn = (p.W == 8 && cc == 7) ? 0.f : 1.f;
+    const uint64_t w_up2 = f32x2(w_up, w_up), w_dn2 = f32x2(w_dn, w_dn);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // residual reads / output writes depend on the previous layer
+    const int n_items = n_elems * 2;
+    for (int m = j0; m < n_items; m += NEQ) {
+      const int n = m >> 1, half = m & 1, acc = n % ACC;
+      const int k = n / (2 * NT), e = n - k * 2 * NT;
+      int kind, j;
+      block_decode(e, NT, kind, j);
+      const int g = k * NT + j;                                  // running tile index of this CTA (slot / phase bookkeeping)
+      const int tile = super_of(k) * NT + j;                     // global tile
+      const int grp = tile * 16 + q * 4 + (lane >> 3);           // this thread's row group (board * HP + board row)
+      const bool pad_row = grp - (int)__umulhi((uint32_t)grp, p.hp_magic) * p.HP == p.H;
+      const bool live = !pad_row && cc < p.W && grp < p.n_groups;   // a real board cell
+      const int col0 = half * 32;
+      // conv2: fetch this thread's residual values early (16-byte global loads, 64 / 48 bytes of its row)
+      uint4 res[4] = {z, z, z, z};
+      const size_t goff = ((size_t)grp * p.W + cc) * CH + col0;     // element offset of (row, first channel of this half)
+      if (kind == 1 && live && !(p.debug & 1)) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.x + goff);
+        res[0] = rp[0];   // (plain loads: the same thread overwrites these bytes below)
+        res[1] = rp[1];
+        res[2] = rp[2];
+        if (half == 0) res[3] = rp[3];
+      }
+      mbar_wait_wd(bar_afull(acc), (uint32_t)(n / ACC) & 1u);
+      tc_fence_after();
+      // ---- drain: TMEM -> registers with the dx recombination (see k_conv8)
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C8_N + col0);
+      auto combine = [&](auto nv_tag, int cb) {
+        constexpr int NV = decltype(nv_tag)::value;
+        uint32_t dm[NV], d0[NV], dp[NV];
+        if constexpr (NV == 16) {
+          tmem_ld16(taddr + (uint32_t)(cb * 16), dm);
+          tmem_ld16(taddr + (uint32_t)(NF + cb * 16), d0);
+          tmem_ld16(taddr + (uint32_t)(2 * NF + cb * 16), dp);
+        } else {
+          tmem_ld2(taddr + (uint32_t)(cb * 16), dm);
+          tmem_ld2(taddr + (uint32_t)(NF + cb * 16), d0);
+          tmem_ld2(taddr + (uint32_t)(2 * NF + cb * 16), dp);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < NV; t += 2) {
+          const float up0 = __shfl_sync(0xffffffffu, __uint_as_float(dm[t]), (lane + 31) & 31);
+          const float up1 = __shfl_sync(0xffffffffu, __uint_as_float(dm[t + 1]), (lane + 31) & 31);
+          const float dn0 = __shfl_sync(0xffffffffu, __uint_as_float(dp[t]), (lane + 1) & 31);
+          const float dn1 = __shfl_sync(0xffffffffu, __uint_as_float(dp[t + 1]), (lane + 1) & 31);
+          const uint64_t a2 = fma_f32x2(w_up2, f32x2(up0, up1), f32x2(__uint_as_float(d0[t]), __uint_as_float(d0[t + 1])));
+          unpack_f32x2(fma_f32x2(w_dn2, f32x2(dn0, dn1), a2), v[cb * 16 + t], v[cb * 16 + t + 1]);
+        }
+      };
+      combine(std::integral_constant<int, 16>{}, 0);
+      if (half == 1) {
+        combine(std::integral_constant<int, 2>{}, 1);
+#pragma unroll
+        for (int t = 18; t < 24; ++t) v[t] = 0u;   // channels 50..55: zero sums + zero bias / scale / shift stay zero
+      } else {
+        combine(std::integral_constant<int, 16>{}, 1);
+      }
+      const int nchunk = half == 0 ? 4 : 3;        // 8-channel chunks with live data in this half (56..63 are never touched)
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) mbar_arrive(bar_aempty(acc));
+      __syncwarp();
+
+      if (kind == 0) {
+        // ---- conv1 item: U = LeakyReLU(conv + b1) as bf16 into the U ring (SWIZZLE_128B rows: chunk c of row r at c ^ (r & 7))
+        uint4 o[4];   // the four 16-byte chunks (8 channels each) of this half of the row
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          o[c] = z;
+          if (c < nchunk) {
+            float f[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) f[t] = __uint_as_float(v[8 * c + t]) + s_b1[col0 + 8 * c + t];
+            o[c] = lrelu_bf16x8(pack8(f));
+          }
+          if (!live) o[c] = z;   // pad rows, pad columns, missing boards: zeros
+        }
+        const int u = g % 3;
+        const bool first = j == 0, last = j == NT - 1;
+        // the slot must have been consumed by the conv2 of three tiles ago (completion number g/3 - 1; -1 passes at once)
+        mbar_wait_wd(bar_uempty(u), (uint32_t)(g / 3 - 1) & 1u);
+        {
+          const int row = 8 + q * 32 + lane;
+          uint8_t* dst = smem + L::U_OFF + u * C8_A_ST + row * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + (((4 * half + c) ^ (row & 7)) << 4)) = o[c];
+        }
+        int extra_same = 0, extra_next = 0, extra_prev = 0;
+        if (q == 3) {
+          if (!last) {   // my last group is the halo above the next tile
+            const int un = (g + 1) % 3;
+            mbar_wait_wd(bar_uempty(un), (uint32_t)((g + 1) / 3 - 1) & 1u);
+            if (lane >= 24) {
+              const int row = lane - 24;
+              uint8_t* dst = smem + L::U_OFF + un * C8_A_ST + row * 128;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + (((4 * half + c) ^ (row & 7)) << 4)) = o[c];
+            }
+            extra_next = 1;
+          } else {       // last tile of the super-tile: the rows below are a board pad row
+            if (lane >= 24) {
+              const int row = 8 + 128 + (lane - 24);
+              uint8_t* dst = smem + L::U_OFF + u * C8_A_ST + row * 128;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + (((4 * half + c) ^ (row & 7)) << 4)) = z;
+            }
+            extra_same = 1;
+          }
+        } else if (q == 0) {
+          if (!first) {  // my first group is the halo below the previous tile
+            const int up = (g - 1) % 3;
+            mbar_wait_wd(bar_uempty(up), (uint32_t)((g - 1) / 3 - 1) & 1u);
+            if (lane < 8) {
+              const int row = 8 + 128 + lane;
+              uint8_t* dst = smem + L::U_OFF + up * C8_A_ST + row * 128;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + (((4 * half + c) ^ (row & 7)) << 4)) = o[c];
+            }
+            extra_prev = 1;
+          } else {       // first tile of the super-tile: the rows above are a board pad row
+            if (lane < 8) {
+              const int row = lane;
+              uint8_t* dst = smem + L::U_OFF + u * C8_A_ST + row * 128;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + (((4 * half + c) ^ (row & 7)) << 4)) = z;
+            }
+            extra_same = 1;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+          mbar_arrive(bar_ufull(u));
+          if (extra_same) mbar_arrive(bar_ufull(u));
+          if (extra_next) mbar_arrive(bar_ufull((g + 1) % 3));
+          if (extra_prev) mbar_arrive(bar_ufull((g - 1) % 3));
+        }
+        __syncwarp();
+      } else {
+        // ---- conv2 item: X <- conv + b2 + X ; T' = LeakyReLU(s2 * X + t2); 16-byte global stores, row per thread
+        // (half 1: channels 32..49 live, 50..55 written as zeros, 56..63 untouched = zero)
+        const bool store = live && !(p.debug & 2);
+        uint4* xp = reinterpret_cast<uint4*>(p.x + goff);
+        uint4* tp = reinterpret_cast<uint4*>(p.t_out + goff);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < nchunk) {
+            const uint32_t rw[4] = {res[c].x, res[c].y, res[c].z, res[c].w};
+            float f[8];
+#pragma unroll
+            for (int t = 0; t < 8; t += 2) {
+              f[t] = __uint_as_float(v[8 * c + t]) + s_b2[col0 + 8 * c + t] + __uint_as_float(rw[t >> 1] << 16);
+              f[t + 1] = __uint_as_float(v[8 * c + t + 1]) + s_b2[col0 + 8 * c + t + 1] + __uint_as_float(rw[t >> 1] & 0xffff0000u);
+            }
+            if (store) xp[c] = pack8(f);
+            if (HAS_OUT2) {
+              float h2[8];
+#pragma unroll
+              for (int t = 0; t < 8; ++t) h2[t] = s_s2[col0 + 8 * c + t] * f[t] + s_t2[col0 + 8 * c + t];
+              if (store) tp[c] = lrelu_bf16x8(pack8(h2));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1358,5 +1748,72 @@ extern "C" int az_nn_head_large(const void* x, const void* w, const float* bias,
   k_head_mma<<<tiles * chunks, HM_THREADS, smem, (cudaStream_t)stream>>>(tm_x, tm_w, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return nn_fail(-2, "k_head_mma launch", e);
+  return 0;
+}
+
+// ---- fused residual block ----
+extern "C" int az_nn_block(const void* t_in, const void* w1, const float* b1, const void* w2, const float* b2, void* x, void* t_out,
+                           const float* s2, const float* t2, int32_t boards, int32_t H, int32_t W, int32_t n_ctas, void* stream) {
+  using namespace aznn;
+  if (!t_in || !w1 || !b1 || !w2 || !b2 || !x) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_block: null argument");
+    return -1;
+  }
+  if (boards <= 0 || H < 3 || H > 16 || W < 2 || W > 8) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_block: needs boards > 0, 3 <= H <= 16, 2 <= W <= 8");
+    return -1;
+  }
+  if (t_out == t_in || x == t_in) {
+    snprintf(g_nn_err, sizeof(g_nn_err), "az_nn_block: outputs must not alias the conv1 input");
+    return -1;
+  }
+  BlockParams p;
+  memset(&p, 0, sizeof(p));
+  p.w1 = (const __nv_bfloat16*)w1;
+  p.w2 = (const __nv_bfloat16*)w2;
+  p.b1 = b1;
+  p.b2 = b2;
+  p.s2 = s2;
+  p.t2 = t2;
+  p.x = (__nv_bfloat16*)x;
+  p.t_out = (__nv_bfloat16*)t_out;
+  p.boards = boards;
+  p.H = H;
+  p.W = W;
+  p.HP = H + 1;
+  p.NT = p.HP;                                   // 16 boards x HP groups = HP tiles of 16 groups
+  p.n_super = (boards + 15) / 16;
+  p.n_groups = boards * p.HP;
+  p.hp_magic = (uint32_t)((0x100000000ULL + (uint64_t)p.HP - 1) / (uint64_t)p.HP);
+  p.debug = env_int("AZ_NN_BLOCK_DEBUG", 0);
+  CUtensorMap tm_in;
+  if (make_tmap_act(&tm_in, t_in, boards, H, W, CH, C8_GROUPS, CU_TENSOR_MAP_SWIZZLE_128B)) return -2;
+  const bool out2 = t_out != nullptr;
+  auto kern = out2 ? k_block<true> : k_block<false>;
+  static unsigned long long attr_set[2] = {0ULL, 0ULL};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_set[out2] >> (dev & 63)) & 1ULL)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BlockSmem::TOTAL);
+    if (e != cudaSuccess) return nn_fail(-2, "cudaFuncSetAttribute(k_block)", e);
+    attr_set[out2] |= 1ULL << (dev & 63);
+  }
+  int grid = n_ctas > 0 ? n_ctas : 148;
+  if (grid > p.n_super) grid = p.n_super;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(14 * 32);
+  cfg.dynamicSmemBytes = BlockSmem::TOTAL;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = env_int("AZ_NN_PDL", 1) ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_in, p);
+  if (e != cudaSuccess) return nn_fail(-2, "k_block launch", e);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return nn_fail(-2, "k_block launch", e);
   return 0;
 }

@@ -74,6 +74,10 @@ class FusedEvaluator:
         if self.fused_head and not self.small_head:
             n = int(self.lib.az_nn_head_large_scratch_bytes(batch, self.A))
             self.head_scratch = torch.zeros((n + 3) // 4, dtype=torch.int32, device=dev)
+        # AZ_NN_BLOCK=1: blocks 2-5 as ONE kernel each (k_block: conv1 -> conv2 with the intermediate tensor in shared
+        # memory, 4 instead of 6 HBM passes per block).  Correct (tests/test_gpu_nn.py) but measured slower than the two conv
+        # launches it replaces (az_resnet.cu, k_block STATUS), so the default stays two launches per block.
+        self.fused_blocks = os.environ.get("AZ_NN_BLOCK", "0") == "1"
         self.timing = None   # set to a list to collect (kernel, start_event, end_event) per launch (bench.py roofline)
         self.load(net)
 
@@ -180,9 +184,20 @@ class FusedEvaluator:
         # last (still in L2); the stem writes front to back, so the first conv goes back to front.
         # block 1, second conv: X = conv(U) + conv1x1(obs) ; T = lrelu(bn1_2(X))   (skip projection inside the conv)
         self._conv(self.U, P_["w2_0"], P_["b2_0"], None, self.X, self.T, P_["s_1"], P_["t_1"], False, flags=L.NN_F_REVERSE)
+        t_in, t_alt = self.T, self.U     # fused blocks ping-pong the activated tensor between T and U
         for k in range(1, 5):
-            self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True)
             last = k == 4
+            if self.fused_blocks:
+                t_out = None if last else t_alt
+                rc = self._timed("block" if last else "block+out2", lambda: self.lib.az_nn_block(
+                    p(t_in), p(P_["w1_%d" % k]), p(P_["b1_%d" % k]), p(P_["w2_%d" % k]), p(P_["b2_%d" % k]), p(self.X),
+                    None if last else p(t_out), None if last else p(P_["s_%d" % (k + 1)]),
+                    None if last else p(P_["t_%d" % (k + 1)]), self.batch, self.h, self.w, self.n_ctas, self._stream()))
+                if rc:
+                    raise RuntimeError("az_nn_block: " + self.lib.az_nn_last_error().decode())
+                t_in, t_alt = t_alt, t_in
+                continue
+            self._conv(self.T, P_["w1_%d" % k], P_["b1_%d" % k], None, self.U, None, None, None, True)
             self._conv(self.U, P_["w2_%d" % k], P_["b2_%d" % k], self.X, self.X, None if last else self.T,
                        None if last else P_["s_%d" % (k + 1)], None if last else P_["t_%d" % (k + 1)], False,
                        flags=L.NN_F_REVERSE)

@@ -279,6 +279,13 @@ int az_game_random_playouts(int32_t game_id, int32_t rows, int32_t cols, int32_t
  * az_nn_head: the FC head (fc1, network.py:48,61-66) for games with n_actions + 1 <= 8 outputs: priors [.][n_actions] =
  *   softmax(x_flat @ w[0..A-1]^T + bias), values = tanh(x_flat @ w[A]^T + bias[A]), fp32.  w is bf16 [8][H*W*64] over the
  *   H*W cells of one board (zero on pad channels / unused outputs; the pad row is not read), bias fp32 [8]. */
+/* az_nn_block: one whole residual block without projection (network.py:99-104, blocks 2-5) in one launch:
+ *   U = LeakyReLU(conv3x3(t_in; w1) + b1) (bn2 folded into w1 / b1), x <- conv3x3(U; w2) + b2 + x (in place),
+ *   t_out = LeakyReLU(s2 * x + t2) when t_out != NULL (the next block's bn1 + LeakyReLU).  The intermediate U stays in shared
+ *   memory (4 instead of 6 activation passes through HBM).  w1 / w2: the wpack images of az_nn_conv3x3; tensors as there;
+ *   t_out and x must not alias t_in. */
+int az_nn_block(const void* t_in, const void* w1, const float* b1, const void* w2, const float* b2, void* x, void* t_out,
+                const float* s2, const float* t2, int32_t boards, int32_t H, int32_t W, int32_t n_ctas, void* stream);
 #define AZ_NN_F_REVERSE 1 /* walk the 128-row tiles back to front (alternate per layer: the tail of the previous layer's
                              output is still in L2) */
 const char* az_nn_last_error(void);

@@ -226,3 +226,60 @@ def test_large_action_space_head_matches_torch(H, W, A, B):
         err = (p - p_ref).abs()
         assert bool((err <= 1e-5 + 1e-4 * p_ref).all()), float(err.max())
         assert (v - v_ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("H,W,B", [(6, 7, 37), (6, 6, 300), (8, 8, 129), (6, 7, 4096), (5, 7, 1000), (3, 2, 50), (8, 8, 3000),
+                                   (6, 7, 1), (16, 8, 5), (6, 7, 16), (6, 7, 17), (6, 7, 2500)])
+def test_fused_residual_block_matches_torch(H, W, B):
+    """az_nn_block (k_block): U = LeakyReLU(conv1(T) + b1) kept in shared memory, X <- conv2(U) + b2 + X in place,
+    T' = LeakyReLU(s2*X + t2) (network.py:99-104 with the BatchNorms folded / carried as in FusedEvaluator) against torch fp32
+    with U rounded to bf16 like the kernel does.  Tolerance: bf16-exact inputs and weights, fp32 accumulation -> the final
+    bf16 rounding (rel 2^-8) plus the effect of single-ulp differences in U (stated bound: 2^-6 relative + 3e-2 absolute).
+    Covers super-tile edges (16 boards), partial super-tiles, W = 8 (no pad column), one board, one CTA."""
+    import torch
+    import torch.nn.functional as F
+    from alphazero_openspiel_b200 import _lib as L
+    from alphazero_openspiel_b200.nn_fused import pack_conv3x3
+    lib = L.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(7 * H + W + B)
+    t = torch.randn((B, 64, H, W), generator=g).to(dev).to(torch.bfloat16).float()
+    x = torch.randn((B, 64, H, W), generator=g).to(dev).to(torch.bfloat16).float()
+    x[:, 50:] = 0.0                                   # layout invariant: the pad channels of the residual stream are zero
+    w1 = (torch.randn((64, 64, 3, 3), generator=g) * 0.05).to(dev).to(torch.bfloat16).float()
+    w2 = (torch.randn((64, 64, 3, 3), generator=g) * 0.05).to(dev).to(torch.bfloat16).float()
+    w1[50:] = 0.0
+    w2[50:] = 0.0
+    w2[:, 50:] = 0.0                                  # conv2 sees the 50 channels of U
+    b1 = torch.randn((64,), generator=g).to(dev)
+    b2 = torch.randn((64,), generator=g).to(dev)
+    b1[50:] = 0.0
+    b2[50:] = 0.0
+    s2 = (torch.rand((64,), generator=g) + 0.5).to(dev)
+    t2 = torch.randn((64,), generator=g).to(dev)
+    u = F.leaky_relu(F.conv2d(t, w1, b1, padding=1))
+    u[:, 50:] = 0.0
+    u = u.to(torch.bfloat16).float()
+    want_x = F.conv2d(u, w2, b2, padding=1) + x
+    want_x[:, 50:] = 0.0
+    want_t = F.leaky_relu(want_x * s2.view(1, -1, 1, 1) + t2.view(1, -1, 1, 1))
+    want_t[:, 50:] = 0.0
+    ptr = lambda a: None if a is None else C.c_void_p(a.data_ptr())  # noqa: E731
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p1, p2 = pack_conv3x3(w1).to(dev), pack_conv3x3(w2).to(dev)
+    for with_out2 in (True, False):
+        tin, xio = _nhwc(t), _nhwc(x)
+        tout = torch.zeros((B, H + 1, W, 64), dtype=torch.bfloat16, device=dev) if with_out2 else None
+        rc = lib.az_nn_block(ptr(tin), ptr(p1), ptr(b1), ptr(p2), ptr(b2), ptr(xio), ptr(tout), ptr(s2) if with_out2 else None,
+                             ptr(t2) if with_out2 else None, B, H, W, 0, st)
+        assert rc == 0, lib.az_nn_last_error()
+        torch.cuda.synchronize()
+        got = xio[:, :H].float().permute(0, 3, 1, 2)
+        assert float(xio[:, H].float().abs().max()) == 0.0           # pad rows untouched (zero)
+        err = (got - want_x).abs()
+        assert bool((err <= 2.0 ** -6 * want_x.abs() + 3e-2).all()), (with_out2, float(err.max()))
+        if with_out2:
+            got_t = tout[:, :H].float().permute(0, 3, 1, 2)
+            assert float(tout[:, H].float().abs().max()) == 0.0
+            err_t = (got_t - want_t).abs()
+            assert bool((err_t <= 2.0 ** -6 * want_t.abs() + 4e-2).all()), float(err_t.max())
