@@ -92,7 +92,7 @@ class Trainer:
         self.optimizer = torch.optim.Adam(self.current_net.parameters(), lr=self.lr, weight_decay=0.0001,
                                           capturable=bool(self.graph_step and self.device.type == "cuda"))
         self._step_graph = None
-        self._pending_capture = None
+        self._gids = None
         self.criterion_value = nn.MSELoss()
         self.current_net.eval()
         self.last_generation_stats = {}
@@ -140,45 +140,50 @@ class Trainer:
         return loss_p, loss_v
 
     def _net_step_graphed(self, replay, first, pol, val, sample_ids):
-        """The device step as one CUDA-graph replay: the minibatch is gathered into static buffers (az_observations kernel +
-        two index_selects), then forward / MSE + cross-entropy / backward / Adam replay from the captured graph."""
+        """The device step as ONE CUDA-graph replay: minibatch gather (az_observations kernel + two index_selects from the
+        de-duplicated targets), forward, MSE + cross-entropy, backward, Adam.  Per step the host only draws the sample ids
+        (the reference's np.random.randint call) and copies 2 KB of indices to the device; the graph is re-captured
+        when a new generation brings new target tensors."""
         dev = self.device
-        ids = torch.from_numpy(sample_ids).to(dev)
-        x = replay.boards(first[ids])
-        p_r = pol[ids].float()
-        v_r = val[ids].float().unsqueeze(1)
-        if self._step_graph is None:
-            self._gx, self._gp, self._gv = x.clone(), p_r.clone(), v_r.clone()
+        if getattr(self, "_gids", None) is None:
+            self._gids = torch.zeros(self.batch_size, dtype=torch.int64, device=dev)
+            self._graph_key = None
+            self._graph_warm = False
+        # (pageable source: the driver stages the 2 KB before returning, so the next step may overwrite sample_ids)
+        self._gids.copy_(torch.from_numpy(np.ascontiguousarray(sample_ids, dtype=np.int64)))
 
-            def step():
-                self.optimizer.zero_grad(set_to_none=False)
-                p_t, v_t = self.current_net(self._gx)
-                loss_v = self.criterion_value(v_t, self._gv)
-                loss_p = -torch.sum(self._gp * torch.log(p_t)) / self._gp.size()[0]
-                (loss_v + loss_p).backward()
-                self.optimizer.step()
-                return loss_p.detach(), loss_v.detach()
+        def step():
+            ids = self._gids
+            x = replay.boards(first[ids])
+            p_r = pol[ids].float()
+            v_r = val[ids].float().unsqueeze(1)
+            self.optimizer.zero_grad(set_to_none=False)
+            p_t, v_t = self.current_net(x)
+            loss_v = self.criterion_value(v_t, v_r)
+            loss_p = -torch.sum(p_r * torch.log(p_t)) / p_r.size()[0]
+            (loss_v + loss_p).backward()
+            self.optimizer.step()
+            return loss_p.detach(), loss_v.detach()
 
-            # the first step runs eagerly on a side stream (allocates the gradients and the Adam state), then the same
-            # closure is captured; both count as optimisation steps of this call sequence
+        if not self._graph_warm:
+            # the very first step runs eagerly on a side stream (cuDNN / allocator warm-up, gradient and Adam state
+            # allocation); it is a real optimisation step
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 self.optimizer.zero_grad(set_to_none=False)
                 out = step()
             torch.cuda.current_stream(dev).wait_stream(side)
-            self._step_graph = torch.cuda.CUDAGraph()
-            self._pending_capture = step
+            self._graph_warm = True
             self.it += 1
             return out[0].clone(), out[1].clone()
-        self._gx.copy_(x)
-        self._gp.copy_(p_r)
-        self._gv.copy_(v_r)
-        if self._pending_capture is not None:
+        key = (first.data_ptr(), pol.data_ptr(), val.data_ptr(), int(first.numel()), replay.bb.data_ptr())
+        if key != self._graph_key:
+            torch.cuda.current_stream(dev).synchronize()
+            self._step_graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._step_graph):
-                self._glp, self._glv = self._pending_capture()
-            self._pending_capture = None
-            # (capture does not execute: replay below performs this step)
+                self._glp, self._glv = step()
+            self._graph_key = key          # (capture does not execute: the replay below performs this step)
         self._step_graph.replay()
         self.it += 1
         return self._glp.clone(), self._glv.clone()
