@@ -283,3 +283,30 @@ def test_fused_residual_block_matches_torch(H, W, B):
             assert float(tout[:, H].float().abs().max()) == 0.0
             err_t = (got_t - want_t).abs()
             assert bool((err_t <= 2.0 ** -6 * want_t.abs() + 4e-2).all()), float(err_t.max())
+
+
+@pytest.mark.parametrize("game", ["connect_four", "breakthrough"])
+def test_evaluator_with_fused_blocks_matches_the_default_path(game, monkeypatch):
+    """AZ_NN_BLOCK=1 (one k_block launch per residual block instead of two conv launches; opt-in, see az_resnet.cu): the
+    whole evaluator agrees with the default path to bf16 rounding noise (both round the intermediate tensors to bf16 at
+    the same places; only the order of fp32 operations inside the epilogues differs)."""
+    import torch
+    from alphazero_openspiel_b200 import engine as E, _lib as L
+    from alphazero_openspiel_b200.network import Net
+    from alphazero_openspiel_b200.nn_fused import FusedEvaluator
+    shape, A = E.game_shape(game)
+    torch.manual_seed(21)
+    net = Net(shape, A).eval()
+    B = 700
+    hist, lens = E.game_random_playouts(game, B, seed=8, max_plies=30)
+    xbf = E.game_replay_dev(game, hist, lens, L.OBS_BF16_NHWC)["obs"]
+    monkeypatch.setenv("AZ_NN_BLOCK", "0")
+    p0, v0 = FusedEvaluator(net, B, "cuda:0").eval_batch(xbf)
+    monkeypatch.setenv("AZ_NN_BLOCK", "1")
+    fe = FusedEvaluator(net, B, "cuda:0")
+    assert fe.fused_blocks
+    p1, v1 = fe.eval_batch(xbf)
+    assert torch.isfinite(p1).all() and torch.isfinite(v1).all()
+    assert (p1 - p0).abs().max().item() < 2e-3 and (v1 - v0).abs().max().item() < 1e-2
+    p2, v2 = fe.eval_batch(xbf)                    # deterministic and re-entrant (the ring / barrier state is per launch)
+    assert torch.equal(p1, p2) and torch.equal(v1, v2)
