@@ -1283,9 +1283,10 @@ k_head_mma(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       int* arrive = p.counters + 2 * mtile;
       if (warp == 2 && lane == 0) {
         atomicAdd(arrive, 1);
-        for (int spin = 0; spin < (1 << 24); ++spin) {
-          if (*reinterpret_cast<volatile int*>(arrive) >= p.n_chunks) break;
+        int spin = 0;
+        while (*reinterpret_cast<volatile int*>(arrive) < p.n_chunks) {
           __nanosleep(64);
+          if (++spin > (1 << 24)) __trap();   // > 1 s: a sibling CTA never arrived -- fail loudly, never write wrong priors
         }
         __threadfence();
       }
