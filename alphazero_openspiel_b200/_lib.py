@@ -64,7 +64,6 @@ SIGNATURES = {
     "az_set_positions": (C.c_int, [C.c_void_p, _I32P, _I32P, C.c_int32, _VP]),
     "az_command": (C.c_int, [C.c_void_p, _I32P, _I32P, _I32P, _VP]),
     "az_step": (C.c_int, [C.c_void_p, _VP, _VP, _F64P, _VP, C.c_int32, _VP]),
-    "az_set_step_ctas": (C.c_int, [C.c_void_p, C.c_int32]),
     "az_compact": (C.c_int, [C.c_void_p, _VP]),
     "az_debug_timing": (C.c_int, [C.c_void_p, _VP]),
     "az_status": (C.c_int, [C.c_void_p, _I32P, _I32P, _I32P, _I32P, _VP]),

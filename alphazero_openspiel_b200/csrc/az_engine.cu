@@ -89,7 +89,6 @@ struct Params {
   int rec_stride;
   int n_trees, cap;
   int n_playouts, num_prob, noise_mode, eval_mode, eval_shift, max_sims, start_mod;
-  int step_ctas;       // 0 = one lane group per tree; else the k_step grid (az_set_step_ctas)
   uint32_t flags;
   uint64_t seed;
   double c_puct, keep, noise_w, alpha, temperature;
@@ -702,11 +701,9 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
   __shared__ unsigned long long s_ctr[AZ_CTR_COUNT];
   if (threadIdx.x < AZ_CTR_COUNT) s_ctr[threadIdx.x] = 0ULL;
   __syncthreads();
+  const int tree = (int)((blockIdx.x * (unsigned)BLOCK + threadIdx.x) / G);
   const int lane = threadIdx.x % G;
-  // one lane group per tree; with fewer CTAs than trees / (BLOCK / G) (az_set_step_ctas: a small persistent grid that can
-  // share the SMs with the evaluator's CTAs) every group walks over several trees
-  const int tree_stride = (int)(gridDim.x * (unsigned)(BLOCK / G));
-  for (int tree = (int)((blockIdx.x * (unsigned)BLOCK + threadIdx.x) / G); tree < p.n_trees; tree += tree_stride) {
+  if (tree < p.n_trees) {
     const unsigned gm = group_mask<G>();
     int32_t* spath = s_path[threadIdx.x / G];
     int32_t* gpath = p.path + (size_t)tree * GM::MAXD;
@@ -1808,21 +1805,12 @@ int az_step(az_engine* e, const void* priors_dev, const void* values_dev, const 
   }
   dispatch_game(e->cfg.game_id, [&](auto gm) {
     using GM = decltype(gm);
-    int grid = groups_grid(p.n_trees, GM::G, BLOCK);
-    if (p.flags & AZ_F_VIRTUAL_LOSS) k_step_vl<GM><<<grid, BLOCK, 0, st>>>(p, io);
-    else if (p.flags & AZ_F_UCT) k_step<GM, true><<<grid, BLOCK, 0, st>>>(p, io);
-    else if (p.step_ctas > 0 && p.step_ctas < grid) k_step<GM, false><<<p.step_ctas, BLOCK, 0, st>>>(p, io);
-    else k_step<GM, false><<<grid, BLOCK, 0, st>>>(p, io);
+    if (p.flags & AZ_F_VIRTUAL_LOSS) k_step_vl<GM><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
+    else if (p.flags & AZ_F_UCT) k_step<GM, true><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
+    else k_step<GM, false><<<groups_grid(p.n_trees, GM::G, BLOCK), BLOCK, 0, st>>>(p, io);
     return 0;
   });
   CK(cudaGetLastError());
-  return 0;
-}
-
-int az_set_step_ctas(az_engine* e, int32_t n_ctas) {
-  if (!e) return fail(-1, "null engine");
-  if (n_ctas < 0) return fail(-1, "n_ctas must be >= 0");
-  e->p.step_ctas = n_ctas;
   return 0;
 }
 

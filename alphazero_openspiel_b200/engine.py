@@ -133,10 +133,6 @@ class Engine:
         L.check(self.lib.az_step(self.h, _ptr(priors), _ptr(values), _ptr(noise), _ptr(obs), obs_format,
                                  self._stream()))
 
-    def set_step_ctas(self, n_ctas):
-        """Run az_step as a small persistent grid (see include/az_b200.h); 0 restores one lane group per tree."""
-        L.check(self.lib.az_set_step_ctas(self.h, int(n_ctas)))
-
     def compact(self, stream=None):
         """Re-root compaction of the trees that just moved (only needed with F_ASYNC_COMPACT)."""
         st = self._stream() if stream is None else C.c_void_p(stream.cuda_stream)

@@ -196,12 +196,6 @@ int az_command(az_engine* e, const int32_t* update_root_host, const int32_t* res
 int az_step(az_engine* e, const void* priors_dev, const void* values_dev, const double* noise_dev,
             void* obs_dev, int32_t obs_format, void* stream);
 
-/* Launch geometry of az_step: n_ctas > 0 runs the step kernel as a small persistent grid of n_ctas CTAs of 128 threads whose
- * lane groups walk over several trees each (default 0: one lane group per tree, all trees resident in one wave).  A small
- * grid (e.g. one CTA per SM) fits beside the evaluator's persistent CTAs, so the step of one game pool can run underneath
- * the evaluator of another (examplegenerator.DualPoolRunner).  Results are identical for any geometry. */
-int az_set_step_ctas(az_engine* e, int32_t n_ctas);
-
 /* Re-root compaction (MCTS.update_root, mcts.py:192-203) of the trees that played a move in the last az_step: BFS-copies
  * the kept subtree into the other arena half, one warp per tree.  az_step runs it first by itself unless
  * AZ_F_ASYNC_COMPACT is set; then the caller must call it once between two az_step calls, on any stream ordered after

@@ -441,24 +441,3 @@ def test_external_evaluator_rows_at_full_pool_size():
     assert len(a) == len(b) > 2 * n_trees
     for f in a.dtype.names:
         assert np.array_equal(a[f], b[f]), f
-
-
-def test_step_kernel_geometry_does_not_change_results():
-    """az_set_step_ctas: the step kernel as a small persistent grid whose lane groups walk over several trees must produce
-    exactly the records and counters of the default geometry (one lane group per tree)."""
-    from alphazero_openspiel_b200 import engine as E, _lib as L
-    out = []
-    for ctas in (0, 3, 40):
-        flags = L.F_RECORDS | L.F_OFFPOLICY | L.F_KEEP_TREE | L.F_SAMPLE_MOVES
-        eng = E.Engine("connect_four", 700, n_playouts=40, noise_mode=L.NOISE_COUNTER, eval_mode=L.EVAL_HASH, flags=flags, seed=77)
-        eng.set_step_ctas(ctas)
-        for _ in range(2200):
-            eng.step()
-        assert int((eng.phases() != L.PH_IDLE).sum()) == 0
-        recs = eng.drain_records()
-        out.append((recs[np.lexsort((recs["kind"], recs["ply"], recs["tree"]))], eng.counters()))
-        eng.close()
-    for recs, ctr in out[1:]:
-        assert ctr == out[0][1]
-        for f in recs.dtype.names:
-            assert np.array_equal(recs[f], out[0][0][f]), f
