@@ -29,7 +29,7 @@ class AzConfig(C.Structure):
         ("num_probabilistic_actions", C.c_int32), ("noise_mode", C.c_int32), ("eval_mode", C.c_int32),
         ("eval_shift", C.c_int32), ("max_sims_per_step", C.c_int32), ("start_plies_mod", C.c_int32),
         ("record_capacity", C.c_int32), ("max_games", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
-        ("seed", C.c_uint64), ("leaves_per_tree", C.c_int32), ("reserved0", C.c_int32),
+        ("seed", C.c_uint64), ("leaves_per_tree", C.c_int32), ("step_cycle_budget", C.c_int32),
     ]
 
 

@@ -89,6 +89,7 @@ struct Params {
   int rec_stride;
   int n_trees, cap;
   int n_playouts, num_prob, noise_mode, eval_mode, eval_shift, max_sims, start_mod;
+  int cycle_budget;  // az_config.step_cycle_budget
   uint32_t flags;
   uint64_t seed;
   double c_puct, keep, noise_w, alpha, temperature;
@@ -708,6 +709,7 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
     int32_t* spath = s_path[threadIdx.x / G];
     int32_t* gpath = p.path + (size_t)tree * GM::MAXD;
     const long long t_start = p.dbg ? clock64() : 0;
+    const long long t_begin = p.cycle_budget > 0 ? clock64() : 0;
     TreeHdr h = p.hdr[tree];
     const int phase_in = h.phase;
     long long t_consume = 0;
@@ -824,6 +826,16 @@ __global__ void __launch_bounds__(BLOCK, K_STEP_MIN_BLOCKS) k_step(const Params 
       if (p.max_sims > 0 && sims_this_step >= p.max_sims) {
         if (lane == 0) ctr_add(s_ctr, AZ_CTR_IDLE_SLOTS, 1);
         break;
+      }
+      // step_cycle_budget: a tree whose simulations keep ending in terminal leaves stops once the launch has run this long
+      // (the launch lasts as long as its slowest tree).  How the simulations of a search are spread over steps does not
+      // change any result, only how many evaluator rows stay empty.
+      if (p.cycle_budget > 0 && sims_this_step > 0) {
+        const int over = gshfl<G>(gm, (int)(clock64() - t_begin > (long long)p.cycle_budget), 0);
+        if (over) {
+          if (lane == 0) ctr_add(s_ctr, AZ_CTR_IDLE_SLOTS, 1);
+          break;
+        }
       }
       // ---- one simulation (mcts.py:126-153)
       const Arena a = arena_of(p, tree, h.half);
@@ -1622,6 +1634,7 @@ int az_create(const az_config* cfg_in, az_engine** out) {
   p.eval_mode = cfg.eval_mode;
   p.eval_shift = cfg.eval_shift;
   p.max_sims = cfg.max_sims_per_step;
+  p.cycle_budget = cfg.step_cycle_budget > 0 ? cfg.step_cycle_budget : 0;
   p.start_mod = cfg.start_plies_mod;
   p.flags = cfg.flags;
   p.seed = cfg.seed;

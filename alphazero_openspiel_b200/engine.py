@@ -56,7 +56,7 @@ class Engine:
     def __init__(self, game_name, n_trees, n_playouts=100, c_puct=2.5, dirichlet_ratio=0.25, temperature=1.0,
                  num_probabilistic_actions=1000, noise_mode=L.NOISE_DIRICHLET, eval_mode=L.EVAL_EXTERNAL,
                  eval_shift=None, flags=L.F_KEEP_TREE, seed=0, device=0, node_capacity=0, max_sims_per_step=0,
-                 start_plies_mod=0, record_capacity=0, max_games=0, leaves_per_tree=1):
+                 start_plies_mod=0, record_capacity=0, max_games=0, leaves_per_tree=1, step_cycle_budget=0):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise L.EngineUnavailable("the B200 engine needs a CUDA device; there is no CPU fallback")
@@ -76,6 +76,7 @@ class Engine:
         cfg.record_capacity, cfg.device, cfg.flags, cfg.seed = record_capacity, device, flags, seed
         cfg.max_games = max_games
         cfg.leaves_per_tree = leaves_per_tree if (flags & L.F_VIRTUAL_LOSS) else 1
+        cfg.step_cycle_budget = step_cycle_budget
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(self.lib.az_create(C.byref(cfg), C.byref(h)))

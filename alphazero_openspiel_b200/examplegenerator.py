@@ -157,7 +157,7 @@ class SelfPlayRunner:
                  dirichlet_ratio=0.25, temperature=1.0, num_probabilistic_actions=1000, keep_search_tree=True,
                  backup="on-policy", seed=0, max_games=0, auto_restart=True, random_start_mod=0,
                  max_sims_per_step=8, records=True, use_graph=True, noise_mode=None, node_capacity=0,
-                 record_capacity=0, evaluator="fused", virtual_loss=0, **_ignored):
+                 record_capacity=0, evaluator="fused", virtual_loss=0, step_cycle_budget=64000, **_ignored):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.EngineUnavailable("SelfPlayRunner needs a CUDA device; there is no CPU fallback")
@@ -190,7 +190,8 @@ class SelfPlayRunner:
                                  eval_mode=L.EVAL_EXTERNAL, flags=flags, seed=seed, device=dev_index,
                                  max_sims_per_step=max_sims_per_step, start_plies_mod=random_start_mod,
                                  max_games=max_games, node_capacity=node_capacity,
-                                 record_capacity=record_capacity, leaves_per_tree=leaves)
+                                 record_capacity=record_capacity, leaves_per_tree=leaves,
+                                 step_cycle_budget=step_cycle_budget)
             n_rows = self.engine.n_rows
             if evaluator == "fused":      # hand-written tcgen05 convs (csrc/az_resnet.cu)
                 from .nn_fused import FusedEvaluator
@@ -380,7 +381,8 @@ class ExampleGenerator:
         # runs at most max(1, max_sims_per_step) simulations per round, so at most 2 * n_trees * sims_per_round / n_playouts
         # records arrive per round; drain when half the capacity could be used.
         n_playouts = max(1, int(kw.get("n_playouts", 100)))
-        sims_per_round = max(1, int(kw.get("max_sims_per_step", 8)))
+        cap = int(kw.get("max_sims_per_step", 8))
+        sims_per_round = cap if cap > 0 else 64    # no count cap: the cycle budget / tree depth bound it far below this
         capacity = int(runner.engine.cfg.record_capacity)
         drain_every = max(64, int(capacity * n_playouts / (4.0 * sims_per_round * n_trees)) // 64 * 64)
         # upper bound on the round trips a generation can need: every game <= max plies, every ply <= n_playouts + 2 rounds

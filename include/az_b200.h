@@ -120,7 +120,10 @@ typedef struct az_config {
   uint32_t flags;              /* AZ_F_* */
   uint64_t seed;
   int32_t leaves_per_tree;     /* AZ_F_VIRTUAL_LOSS: evaluator rows (leaves in flight) per tree; else 1 */
-  int32_t reserved0;
+  int32_t step_cycle_budget;   /* > 0: a tree that already ran a simulation in this az_step starts no further in-kernel
+                                  (terminal-leaf) simulation once the launch is this many SM cycles old; bounds the
+                                  launch's tail like max_sims_per_step, but by time instead of count; results are
+                                  unaffected (exact kernel only; ignored with AZ_F_VIRTUAL_LOSS) */
 } az_config;
 
 typedef struct az_engine az_engine;

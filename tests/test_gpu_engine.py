@@ -40,7 +40,7 @@ def test_game_dynamics_bit_exact(game):
 
 
 def _run_engine_selfplay(game, n_trees, n_playouts, seed, noise, sample, keep, flags_extra=0, max_steps=200000,
-                         max_sims_per_step=0, eval_mode=None, c_puct=2.5):
+                         max_sims_per_step=0, eval_mode=None, c_puct=2.5, step_cycle_budget=0):
     from alphazero_openspiel_b200 import engine as E, _lib as L
     flags = L.F_RECORDS | L.F_OFFPOLICY | flags_extra
     if keep:
@@ -49,7 +49,7 @@ def _run_engine_selfplay(game, n_trees, n_playouts, seed, noise, sample, keep, f
         flags |= L.F_SAMPLE_MOVES
     eng = E.Engine(game, n_trees, n_playouts=n_playouts, noise_mode=noise, flags=flags, c_puct=c_puct,
                    eval_mode=L.EVAL_HASH if eval_mode is None else eval_mode,
-                   seed=seed, max_sims_per_step=max_sims_per_step)
+                   seed=seed, max_sims_per_step=max_sims_per_step, step_cycle_budget=step_cycle_budget)
     steps = 0
     while True:
         for _ in range(64):
@@ -102,12 +102,16 @@ def test_selfplay_visit_counts_bit_exact(game, n_trees, n_playouts, keep):
 
 
 def test_no_dirichlet_argmax_and_sim_cap():
-    """use_dirichlet=False + argmax moves; a per-step simulation cap must not change any result."""
+    """use_dirichlet=False + argmax moves; a per-step simulation cap (by count, max_sims_per_step, or by SM cycles,
+    step_cycle_budget) must not change any result."""
     from alphazero_openspiel_b200 import _lib as L
     game, n_trees, n_playouts, seed = "connect_four", 32, 60, 7
     cfg = ou.selfplay_cfg(game, n_playouts, use_dirichlet=0, sample_moves=0, keep_tree=1, seed=seed)
-    for cap in (0, 3):
-        recs, ctr = _run_engine_selfplay(game, n_trees, n_playouts, seed, L.NOISE_NONE, 0, 1, max_sims_per_step=cap)
+    idle = {}
+    for cap, budget in ((0, 0), (3, 0), (0, 1), (0, 30000), (8, 20000)):
+        recs, ctr = _run_engine_selfplay(game, n_trees, n_playouts, seed, L.NOISE_NONE, 0, 1, max_sims_per_step=cap,
+                                         step_cycle_budget=budget)
+        idle[(cap, budget)] = ctr["idle_slots"]
         assert ctr["overflow"] == 0
         for t in range(0, n_trees, 8):
             plies = recs[(recs["tree"] == t) & (recs["kind"] == 0)]
@@ -117,6 +121,7 @@ def test_no_dirichlet_argmax_and_sim_cap():
             for r, g in zip(ref, plies):
                 assert list(g["counts"][:r["n_legal"]]) == r["counts"] and g["action"] == r["action"]
                 assert g["root_q"] == r["root_q"]
+    assert idle[(0, 1)] > idle[(0, 0)]     # a one-cycle budget really stops trees after their first simulation
 
 
 def test_full_size_pool_matches_oracle_on_sampled_trees():
