@@ -156,8 +156,8 @@ class SelfPlayRunner:
     def __init__(self, net, game_name, device, n_trees, n_playouts=100, c_puct=2.5, use_dirichlet=True,
                  dirichlet_ratio=0.25, temperature=1.0, num_probabilistic_actions=1000, keep_search_tree=True,
                  backup="on-policy", seed=0, max_games=0, auto_restart=True, random_start_mod=0,
-                 max_sims_per_step=8, records=True, use_graph=True, noise_mode=None, node_capacity=0,
-                 record_capacity=0, evaluator="fused", virtual_loss=0, step_cycle_budget=64000, **_ignored):
+                 max_sims_per_step=16, records=True, use_graph=True, noise_mode=None, node_capacity=0,
+                 record_capacity=0, evaluator="fused", virtual_loss=0, step_cycle_budget=None, **_ignored):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise L.EngineUnavailable("SelfPlayRunner needs a CUDA device; there is no CPU fallback")
@@ -181,6 +181,11 @@ class SelfPlayRunner:
         leaves = int(virtual_loss) if virtual_loss and int(virtual_loss) > 0 else 1
         if virtual_loss and int(virtual_loss) > 0:
             flags |= L.F_VIRTUAL_LOSS
+        if step_cycle_budget is None:
+            # time bound on a tree's in-kernel (terminal-leaf) simulations per launch, in SM cycles: the longer the evaluator
+            # of a round trip runs, the more k_step time an extra simulation per row is worth (measured, profiles/
+            # r02_summary.md: 16,384 Connect Four trees best at 60-80 k, 1,024 Breakthrough 6x6 trees at 30 k)
+            step_cycle_budget = 64000 if n_trees * leaves >= 4096 else 30000
         self.backup = backup
         self.game_name = game_name
         with torch.cuda.device(self.device):
@@ -381,7 +386,7 @@ class ExampleGenerator:
         # runs at most max(1, max_sims_per_step) simulations per round, so at most 2 * n_trees * sims_per_round / n_playouts
         # records arrive per round; drain when half the capacity could be used.
         n_playouts = max(1, int(kw.get("n_playouts", 100)))
-        cap = int(kw.get("max_sims_per_step", 8))
+        cap = int(kw.get("max_sims_per_step", 16))
         sims_per_round = cap if cap > 0 else 64    # no count cap: the cycle budget / tree depth bound it far below this
         capacity = int(runner.engine.cfg.record_capacity)
         drain_every = max(64, int(capacity * n_playouts / (4.0 * sims_per_round * n_trees)) // 64 * 64)

@@ -433,7 +433,8 @@ def run_ours(args):
                                  if args.evaluator == "fused" else "ResNet 5x50 bf16 channels-last via PyTorch")
                    + ", " + weights,
                    "noise": "device Dirichlet(0.3), ratio 0.25", "start": "counter % 21 random plies",
-                   "sim_cap_per_step": args.sim_cap, "step_cycle_budget": args.cycle_budget, "cuda_graph": not args.no_graph,
+                   "sim_cap_per_step": args.sim_cap, "step_cycle_budget": int(runner.engine.cfg.step_cycle_budget),
+                   "cuda_graph": not args.no_graph,
                    "virtual_loss_leaves": args.virtual_loss,
                    "l2_policy": "working set (%.1f GB node arenas + %.0f MB activations per round trip) exceeds the 126 MB L2"
                                 % (node_bytes / 1e9, rows_per_round * rows * cols * 64 * 2 * 3 / 1e6)},
@@ -576,9 +577,10 @@ def main():
     ap.add_argument("--game", default=None)
     ap.add_argument("--trees", type=int, default=None)
     ap.add_argument("--playouts", type=int, default=None)
-    ap.add_argument("--sim-cap", type=int, default=8)
-    ap.add_argument("--cycle-budget", type=int, default=64000,
-                    help="az_config.step_cycle_budget: SM cycles after which a tree starts no further in-kernel simulation")
+    ap.add_argument("--sim-cap", type=int, default=16)
+    ap.add_argument("--cycle-budget", type=int, default=None,
+                    help="az_config.step_cycle_budget: SM cycles after which a tree starts no further in-kernel simulation "
+                         "(default: SelfPlayRunner's choice by pool size)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-settle", action="store_true", help="profiling runs: skip the steady-state settle phase")
     ap.add_argument("--no-cpu-baseline", action="store_true")
