@@ -43,6 +43,16 @@ CONFIGS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of this run, on the process's original stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def conv_dram_traffic(game, trees):
     """dram__bytes_read.sum + dram__bytes_write.sum per conv launch (averaged over the conv launches of one evaluation)
     from the committed `ncu --set full` capture of this shape: profiles/conv_traffic.json is written by
@@ -192,7 +202,7 @@ def run_reference(args):
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(args):
@@ -463,7 +473,7 @@ def run_ours(args):
                                     "sample": "failed: %r" % (e,)}
     if overflow:
         sys.stderr.write("WARNING: %d arena/record overflows in the timed region -- raise --node-capacity\n" % overflow)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -559,15 +569,12 @@ def run_train(args):
                               (", data-parallel over %d ranks (gradient all-reduce)" % world if tr.ddp and world > 1
                                else (", rank 0 trains + NCCL weight broadcast" if world > 1 else "")),
                 "clocks": clocks}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
-    # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION, set on some boxes) off it
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20, help="timed steps; one step = %d evaluator round trips" % ROUNDS_PER_STEP)
@@ -595,6 +602,12 @@ def main():
     ap.add_argument("--list-buffer", action="store_true", help="--config train: the reference's Python-list replay buffer")
     ap.add_argument("--no-keep-tree", action="store_true", help="experiment: fresh tree every move (no re-root compaction)")
     args = ap.parse_args()
+    # stdout carries ONE JSON line and nothing else: whatever libraries write to file descriptor 1 (NCCL prints its version
+    # banner there when NCCL_DEBUG is VERSION or higher, as on some boxes) is sent to stderr; emit() writes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     cfg = CONFIGS[args.config]
     args.game = args.game or cfg["game"]
     args.trees = args.trees or cfg["trees"]

@@ -1,5 +1,6 @@
 """profiles/r02_configs.json: the committed bench lines of every BASELINE config (verdict r01 item 5), collected from the
-gpurun outputs of scripts/gpu_r02l.sh (1 GPU) and scripts/gpu_r02k.sh (8 GPUs)."""
+gpurun outputs of scripts/gpu_r03z.sh (1 GPU) and scripts/gpu_r03y.sh (8 GPUs; the training loop and the 2-GPU line are
+from scripts/gpu_r02k.sh / gpu_r02i.sh)."""
 import json, os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def load(p):
@@ -11,15 +12,16 @@ def load(p):
             return json.loads(line)
 out = {
     "note": "one bench.py JSON line per BASELINE.json config; clocks sampled during the timed region are inside every line",
-    "configs[2] connect_four 800 sims 16384 trees, 1 GPU (python bench.py)": load("r02l_c4.json"),
-    "configs[2] 8 GPUs (torchrun, --gpus 8 --steps 20 --warmup 5)": load("r02k_c4_n8.json"),
+    "configs[2] connect_four 800 sims 16384 trees, 1 GPU (python bench.py)": load("r03z_c4.json"),
+    "configs[2] 8 GPUs (torchrun, --gpus 8 --steps 20 --warmup 5)": load("r03y_c4_n8.json"),
     "configs[2] 2 GPUs": load("r02i_bench_c4_n2.json"),
-    "configs[1] breakthrough 6x6 200 sims 1024 games shipped checkpoint, exact mode (--config bt6)": load("r02l_bt6.json"),
-    "configs[1] virtual-loss mode K=8, NOT bit-exact (--config bt6 --virtual-loss 8)": load("r02l_bt6_vl8.json"),
-    "configs[3] breakthrough 8x8 800 sims random-init net, 1 GPU (--config bt8)": load("r02l_bt8.json"),
-    "configs[3] 8 GPUs (torchrun, --config bt8)": load("r02k_bt8_n8.json"),
-    "configs[4] full train.py loop, 1 GPU (--config train)": load("r02l_train.json"),
+    "configs[1] breakthrough 6x6 200 sims 1024 games shipped checkpoint, exact mode (--config bt6)": load("r03z_bt6.json"),
+    "configs[1] virtual-loss mode K=8, NOT bit-exact (--config bt6 --virtual-loss 8)": load("r03z_bt6_vl8.json"),
+    "configs[3] breakthrough 8x8 800 sims random-init net, 1 GPU (--config bt8)": load("r03z_bt8.json"),
+    "configs[3] 8 GPUs (torchrun, --config bt8)": load("r03y_bt8_n8.json"),
+    "configs[4] full train.py loop, 1 GPU (--config train)": load("r03z_train.json"),
     "configs[4] 8 GPUs (torchrun, --config train)": load("r02k_train_n8.json"),
+    "reference arm (python bench.py --impl reference --gpus 1 --steps 20 --warmup 5): CPU port, all host cores": load("r03z_ref.json"),
     "configs[0] connect_four single game 100 sims on CPU": "cpu_baseline.single_process_100sims_sims_per_s of the configs[2] line",
 }
 json.dump(out, open(os.path.join(root, "profiles", "r02_configs.json"), "w"), indent=1)
