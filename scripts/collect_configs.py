@@ -1,6 +1,6 @@
 """profiles/r02_configs.json: the committed bench lines of every BASELINE config (verdict r01 item 5), collected from the
-gpurun outputs of scripts/gpu_r03z.sh (1 GPU) and scripts/gpu_r03y.sh (8 GPUs; the training loop and the 2-GPU line are
-from scripts/gpu_r02k.sh / gpu_r02i.sh)."""
+gpurun outputs of scripts/gpu_r03z.sh (1 GPU) and scripts/gpu_r03y.sh (8 GPUs), scripts/gpu_r03x.sh (2 GPUs); the 8-GPU training loop is
+from scripts/gpu_r02k.sh)."""
 import json, os, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def load(p):
@@ -14,7 +14,7 @@ out = {
     "note": "one bench.py JSON line per BASELINE.json config; clocks sampled during the timed region are inside every line",
     "configs[2] connect_four 800 sims 16384 trees, 1 GPU (python bench.py)": load("r03z_c4.json"),
     "configs[2] 8 GPUs (torchrun, --gpus 8 --steps 20 --warmup 5)": load("r03y_c4_n8.json"),
-    "configs[2] 2 GPUs": load("r02i_bench_c4_n2.json"),
+    "configs[2] 2 GPUs": load("r03x_c4_n2.json"),
     "configs[1] breakthrough 6x6 200 sims 1024 games shipped checkpoint, exact mode (--config bt6)": load("r03z_bt6.json"),
     "configs[1] virtual-loss mode K=8, NOT bit-exact (--config bt6 --virtual-loss 8)": load("r03z_bt6_vl8.json"),
     "configs[3] breakthrough 8x8 800 sims random-init net, 1 GPU (--config bt8)": load("r03z_bt8.json"),
