@@ -5,11 +5,13 @@
 // kernels (profiles/r01_summary.md: 57 % of a round trip was un-fused elementwise traffic).
 //
 // Activations are NHWC bf16 tensors [boards][H+1][W][64] (50 filters zero-padded to 64; board row H is a zero pad row that
-// separates consecutive boards).  Three kernels:
+// separates consecutive boards).  Kernels:
 //   k_conv8<false>  3x3 conv 64 -> 64 with bias / LeakyReLU / residual / next-BatchNorm epilogues
 //   k_conv8<true>   the 4-plane stem (first conv of block 1), same pipeline with a computing producer
-//   k_head          FC + softmax + tanh for small action spaces
-// Measured history of the conv kernel (limiters, what was tried) is in profiles/r01_summary.md.
+//   k_head          FC + softmax + tanh for small action spaces (Connect Four)
+//   k_head_mma      FC + softmax + tanh as a tcgen05 GEMM for large action spaces (Breakthrough: 433 / 769 outputs)
+//   k_block         a whole residual block in one launch (opt-in: measured slower than its two conv launches)
+// Measured history of the kernels (limiters, what was tried) is in profiles/r01_summary.md and profiles/r02_summary.md.
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -180,21 +182,22 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // groups before the first / after the last board.  A tile is 128 consecutive virtual rows (16 groups); its slab is the tile
 // plus one group above and below: ONE box of (64, 8, 18), SWIZZLE_128B, i.e. one 128-byte line per virtual row.
 //
-// Tensor core: the three dx taps of a kernel row share ONE A view and become the N dimension,
-//   D[v][dx*64 + co] = sum_dy,k A[v + dy*8][k] W(dy,dx)[k][co]          (12 MMAs of M128 N192 K16 per tile)
+// Tensor core: the three dx taps of a kernel row share ONE A view and become the N dimension, packed without padding,
+//   D[v][dx*50 + co] = sum_dy,k A[v + dy*8][k] W(dy,dx)[k][co]          (12 MMAs of M128 N160 K16 per tile)
 // (the dy view is the slab shifted by whole groups) and the epilogue recombines
 //   out[v] = D_-1[v-1] + D_0[v] + D_+1[v+1]
 // with one-lane warp shuffles: a 32-row TMEM lane quarter starts at c = 0, so the only cross-quarter neighbours are the
 // masked c = 0 / c = W-1 ones.  Compared with nine row-shifted views of N = 64 the slab is fetched from shared memory 3x
-// instead of 9x per tile (the shared-memory datapath, 128 B/clk, was the limiter of that version).
+// instead of 9x per tile (the shared-memory datapath, 128 B/clk, was the limiter of that version and, at 108 KB of operands
+// per tile, still paces the launches that are not HBM-bound: profiles/r02_summary.md).
 //
 //   warp 0      one thread: bulk-copies the weight image, then one TMA box per tile into a ring of S smem stages
 //               (STEM: warps 0-3 build the slab of their stage from the 4 observation planes instead)
-//   next warp   MMA issuer (tcgen05.mma, two 192-column accumulators in TMEM)
-//   NE warps    epilogue; a work item is (tile, 32-row lane quarter, 32-channel half) and the NE/4 warps of a quarter take
-//               items round-robin, so several tiles' epilogues are in flight per scheduler.  Residual rows arrive by TMA
-//               one item ahead, the result is written in place into the staging buffer (SWIZZLE_64B, row per thread,
-//               conflict-free) and leaves by TMA store - no per-row predicates, no LDS/STG copy-out.
+//   next warp   MMA issuer (tcgen05.mma, three 160-column accumulators in TMEM)
+//   NE warps    epilogue; a work item is (tile, 32-row lane quarter, channel half: 32 or 18 channels) and the NE/4 warps of a
+//               quarter take items round-robin, so several tiles' epilogues are in flight per scheduler.  Residual rows
+//               arrive by TMA one item ahead, the result is written in place into the staging buffer (SWIZZLE_64B, row per
+//               thread, conflict-free) and leaves by TMA store - no per-row predicates, no LDS/STG copy-out.
 // ---------------------------------------------------------------------------------------------------------------------
 struct Conv8Params {
   const __nv_bfloat16* wpack;
